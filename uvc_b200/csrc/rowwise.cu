@@ -1,0 +1,415 @@
+// Bandwidth-bound row-wise kernels of the ViT block: LayerNorm fwd/bwd, softmax fwd/bwd over
+// attention rows, bias-gradient column sums, gate blend + gate-gradient dot products, im2col for the
+// 16x16/16 patch-embed conv, token assembly (cls + pos-embed + patch gate).  All are warp-per-row or
+// thread-per-column with float4 accesses; none of them reshapes work to reach the tensor cores.
+//
+// Reference spans: models/model_distilled.py:199,204,288,507 (LayerNorm), :179-181 (softmax),
+// :433-471 (patch embed, gates, cls/pos), :477-503 (block gate blend).
+#include "common.cuh"
+
+namespace uvc {
+
+constexpr int kMaxVec = 8;   // float4 per lane -> C <= 1024
+
+// ------------------------------------------------------------------------------------------ LayerNorm fwd
+// one warp per row; two-pass moments in registers (mean, then centred variance) like ATen's RowwiseMoments.
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, float* __restrict__ y, long long ldy,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  const int nv = C >> 2;
+  float4 v[kMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  float4* yr = reinterpret_cast<float4*>(y + (long long)row * ldy);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nv) {
+      const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      yr[c] = o;
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx[row] = r1[row] + s2 * r2[row] + rstd * (g - mean(g) - xhat * mean(g * xhat)),   g = dy * gamma
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (register partials per lane -> smem -> atomics)
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ r1, const float* __restrict__ r2,
+                                                            const float* __restrict__ s2_dev, float* __restrict__ dx, long long lddx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C, int rows_per_block) {
+  __shared__ float red[2][8][32 * 4 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int nv = C >> 2;
+  const float s2 = (r2 && s2_dev) ? __ldg(s2_dev) : 1.0f;
+  float4 ag[kMaxVec], ab[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(M, row0 + rows_per_block);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  for (int row = row0 + warp; row < row1; row += nwarps) {
+    const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * lddy);
+    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[kMaxVec], gg[kMaxVec];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        const float4 d = dyr[c], xv = xr[c], gm = __ldg(g4 + c);
+        xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
+        gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
+        sg += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+        sgx += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    const float mg = warp_sum(sg) / (float)C, mgx = warp_sum(sgx) / (float)C;
+    float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * lddx);
+    const float4* r1r = r1 ? reinterpret_cast<const float4*>(r1 + (long long)row * lddx) : nullptr;
+    const float4* r2r = r2 ? reinterpret_cast<const float4*>(r2 + (long long)row * lddx) : nullptr;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (gg[i].x - mg - xh[i].x * mgx); o.y = rs * (gg[i].y - mg - xh[i].y * mgx);
+        o.z = rs * (gg[i].z - mg - xh[i].z * mgx); o.w = rs * (gg[i].w - mg - xh[i].w * mgx);
+        if (r1r) { const float4 a = r1r[c]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (r2r) { const float4 a = r2r[c]; o.x += s2 * a.x; o.y += s2 * a.y; o.z += s2 * a.z; o.w += s2 * a.w; }
+        dxr[c] = o;
+      }
+    }
+  }
+  if (!dgamma) return;
+  // cross-warp reduction of the per-lane column partials, one 128-column slab (i) at a time
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    if (i * 32 >= nv) break;
+    __syncthreads();
+    float* rg = &red[0][warp][lane * 4];
+    float* rb = &red[1][warp][lane * 4];
+    rg[0] = ag[i].x; rg[1] = ag[i].y; rg[2] = ag[i].z; rg[3] = ag[i].w;
+    rb[0] = ab[i].x; rb[1] = ab[i].y; rb[2] = ab[i].z; rb[3] = ab[i].w;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int col = i * 128 + threadIdx.x;
+      if (col < C) {
+        float sgm = 0.f, sbt = 0.f;
+        for (int w = 0; w < nwarps; ++w) { sgm += red[0][w][threadIdx.x]; sbt += red[1][w][threadIdx.x]; }
+        atomicAdd(dgamma + col, sgm);
+        atomicAdd(dbeta + col, sbt);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ softmax over attention rows
+// in place on S[rows][ld], n valid columns (<= 256); one warp per row
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S, long long ld, long long rows, int n) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* s = S + row * ld;
+  float v[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; v[i] = (c < n) ? s[c] : -INFINITY; mx = fmaxf(mx, v[i]); }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; v[i] = (c < n) ? expf(v[i] - mx) : 0.f; sum += v[i]; }
+  const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; if (c < n) s[c] = v[i] * inv; }
+}
+
+// dS = scale * P .* (dP - sum_j dP_j P_j), written over dP
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, long long ld, long long rows, int n, float scale) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* p = P + row * ld;
+  float* d = dP + row * ld;
+  float pv[8], dv[8];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    pv[i] = (c < n) ? p[c] : 0.f; dv[i] = (c < n) ? d[c] : 0.f;
+    dot += pv[i] * dv[i];
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; if (c < n) d[c] = scale * pv[i] * (dv[i] - dot); }
+}
+
+// ------------------------------------------------------------------------------------------ column sums (bias grads)
+// out[col] += scale * sum_rows X[row, col]; thread per column, grid.y row chunks, atomics to combine
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X, long long ld, int M, int N, const float* __restrict__ scale_dev,
+                                                     float* __restrict__ out, int rows_per_block) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  if (col >= N) return;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    a0 += X[(long long)r * ld + col]; a1 += X[(long long)(r + 1) * ld + col];
+    a2 += X[(long long)(r + 2) * ld + col]; a3 += X[(long long)(r + 3) * ld + col];
+  }
+  for (; r < r1; ++r) a0 += X[(long long)r * ld + col];
+  const float sc = scale_dev ? __ldg(scale_dev) : 1.0f;
+  atomicAdd(out + col, sc * ((a0 + a1) + (a2 + a3)));
+}
+
+// ------------------------------------------------------------------------------------------ block gate blend
+// out = d[1] * t + d[0] * x           (models/model_distilled.py:493)
+__global__ void __launch_bounds__(256) blend_fwd_kernel(const float4* __restrict__ t, const float4* __restrict__ x, const float* __restrict__ d,
+                                                        float4* __restrict__ out, long long n4) {
+  const float d0 = __ldg(d), d1 = __ldg(d + 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = t[i], b = x[i];
+    out[i] = make_float4(d1 * a.x + d0 * b.x, d1 * a.y + d0 * b.y, d1 * a.z + d0 * b.z, d1 * a.w + d0 * b.w);
+  }
+}
+// dots[0] += <g, x>, dots[1] += <g, t>   (gradients of the loss wrt the blend weights d0, d1)
+__global__ void __launch_bounds__(256) blend_dots_kernel(const float4* __restrict__ g, const float4* __restrict__ t, const float4* __restrict__ x,
+                                                         float* __restrict__ dots, long long n4) {
+  float sx = 0.f, st = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 gg = g[i], a = t[i], b = x[i];
+    sx += (gg.x * b.x + gg.y * b.y) + (gg.z * b.z + gg.w * b.w);
+    st += (gg.x * a.x + gg.y * a.y) + (gg.z * a.z + gg.w * a.w);
+  }
+  __shared__ float rs[2][8];
+  sx = warp_sum(sx); st = warp_sum(st);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { rs[0][warp] = sx; rs[1][warp] = st; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += rs[0][w]; b += rs[1][w]; }
+    atomicAdd(dots, a); atomicAdd(dots + 1, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ patch embed glue
+// im2col of the 16x16 stride-16 conv: out[(b*196 + py*14 + px), c*256 + ky*16 + kx] = x[b, c, py*16+ky, px*16+kx]
+__global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Cin, int HW, int P) {
+  const int G = HW / P;                       // patches per side
+  const long long total4 = (long long)B * G * G * Cin * P * (P / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int kx4 = (int)(t % (P / 4)); t /= (P / 4);
+    const int ky = (int)(t % P); t /= P;
+    const int c = (int)(t % Cin); t /= Cin;
+    const int px = (int)(t % G); t /= G;
+    const int py = (int)(t % G); t /= G;
+    const int b = (int)t;
+    const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * Cin + c) * HW + (py * P + ky)) * HW + px * P + kx4 * 4);
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+// scatter-add inverse (not needed: the input image needs no gradient)
+
+// tok[b,0,:] = cls + pos[0];  tok[b,1+p,:] = pe[b*np+p,:] * pscale[p] * tmask[b,p] + pos[1+p]
+__global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __restrict__ pe, const float* __restrict__ cls, const float* __restrict__ pos,
+                                                              const float* __restrict__ pscale, const float* __restrict__ tmask,
+                                                              float* __restrict__ tok, int B, int np, int C) {
+  const int nv = C >> 2;
+  const long long total = (long long)B * (np + 1) * nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % nv);
+    const long long r = i / nv;
+    const int n = (int)(r % (np + 1));
+    const int b = (int)(r / (np + 1));
+    const float4 po = __ldg(reinterpret_cast<const float4*>(pos) + (long long)n * nv + c);
+    float4 o;
+    if (n == 0) {
+      const float4 cl = __ldg(reinterpret_cast<const float4*>(cls) + c);
+      o = make_float4(cl.x + po.x, cl.y + po.y, cl.z + po.z, cl.w + po.w);
+    } else {
+      const float4 v = reinterpret_cast<const float4*>(pe)[((long long)b * np + (n - 1)) * nv + c];
+      float s = 1.0f;
+      if (pscale) s *= __ldg(pscale + (n - 1));
+      if (tmask) s *= __ldg(tmask + (long long)b * np + (n - 1));
+      o = make_float4(v.x * s + po.x, v.y * s + po.y, v.z * s + po.z, v.w * s + po.w);
+    }
+    reinterpret_cast<float4*>(tok)[i] = o;
+  }
+}
+// backward of assemble: d_pe = g[b,1+p,:] * s ; dscale[p] += sum_{b,c} g * pe ; (dpos, dcls via colsum-style kernel below)
+__global__ void __launch_bounds__(128) assemble_tokens_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, const float* __restrict__ pscale,
+                                                                 const float* __restrict__ tmask, float* __restrict__ dpe, float* __restrict__ dscale,
+                                                                 int B, int np, int C) {
+  // one warp per (b, p) row
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * np) return;
+  const int p = (int)(row % np);
+  const int b = (int)(row / np);
+  const int nv = C >> 2;
+  const float4* gr = reinterpret_cast<const float4*>(g) + ((long long)b * (np + 1) + 1 + p) * nv;
+  const float4* pr = reinterpret_cast<const float4*>(pe) + row * nv;
+  float4* dr = reinterpret_cast<float4*>(dpe) + row * nv;
+  float s = 1.0f, sm = 1.0f;
+  if (pscale) s *= __ldg(pscale + p);
+  if (tmask) { sm = __ldg(tmask + row); s *= sm; }
+  float dot = 0.f;
+  for (int c = lane; c < nv; c += 32) {
+    const float4 gg = gr[c];
+    if (dscale) { const float4 v = pr[c]; dot += (gg.x * v.x + gg.y * v.y) + (gg.z * v.z + gg.w * v.w); }
+    dr[c] = make_float4(gg.x * s, gg.y * s, gg.z * s, gg.w * s);
+  }
+  if (dscale) {
+    dot = warp_sum(dot);
+    if (lane == 0) atomicAdd(dscale + p, dot * sm);
+  }
+}
+// dpos[n,:] += sum_b g[b,n,:] ; dcls[:] += sum_b g[b,0,:]
+__global__ void __launch_bounds__(128) pos_cls_grad_kernel(const float* __restrict__ g, float* __restrict__ dpos, float* __restrict__ dcls, int B, int ntok, int C) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int b = 0; b < B; ++b) a += g[((long long)b * ntok + n) * C + c];
+    dpos[(long long)n * C + c] += a;
+    if (n == 0 && dcls) dcls[c] += a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ generic small helpers
+__global__ void scale_add_kernel(float4* __restrict__ y, const float4* __restrict__ x, const float* __restrict__ s_dev, float s, long long n4) {
+  const float sc = s * (s_dev ? __ldg(s_dev) : 1.0f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = x[i]; float4 b = y[i];
+    b.x += sc * a.x; b.y += sc * a.y; b.z += sc * a.z; b.w += sc * a.w;
+    y[i] = b;
+  }
+}
+
+static inline int grid_for(long long n, int threads, int max_blocks = 148 * 8) {
+  long long b = (n + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
+                  float* rstd, int M, int C, cudaStream_t st) {
+  UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kMaxVec * 128);
+  UVC_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm: row strides must be multiples of 4");
+  if (M <= 0) return UVC_OK;
+  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C);
+  return check_launch("layernorm_fwd");
+}
+
+int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
+                  const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
+                  cudaStream_t st) {
+  UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
+  UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
+  if (M <= 0) return UVC_OK;
+  int blocks = 148 * 4;
+  int rpb = (M + blocks - 1) / blocks;
+  if (rpb < 8) rpb = 8;
+  blocks = (M + rpb - 1) / rpb;
+  layernorm_bwd_kernel<<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, rpb);
+  return check_launch("layernorm_bwd");
+}
+
+int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st) {
+  UVC_REQUIRE(n > 0 && n <= 256, UVC_ERR_BAD_SHAPE, "softmax: n=%d must be in [1,256]", n);
+  if (rows <= 0) return UVC_OK;
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S, ld, rows, n);
+  return check_launch("softmax_fwd");
+}
+int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st) {
+  UVC_REQUIRE(n > 0 && n <= 256, UVC_ERR_BAD_SHAPE, "softmax_bwd: n=%d must be in [1,256]", n);
+  if (rows <= 0) return UVC_OK;
+  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(P, dP, ld, rows, n, scale);
+  return check_launch("softmax_bwd");
+}
+int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return UVC_OK;
+  int chunks = 148 * 4 / ((N + 127) / 128);
+  if (chunks < 1) chunks = 1;
+  int rpb = (M + chunks - 1) / chunks;
+  if (rpb < 16) rpb = 16;
+  chunks = (M + rpb - 1) / rpb;
+  colsum_kernel<<<dim3((N + 127) / 128, chunks), 128, 0, st>>>(X, ld, M, N, scale_dev, out, rpb);
+  return check_launch("colsum");
+}
+int blend_fwd(const float* t, const float* x, const float* d, float* out, long long n, cudaStream_t st) {
+  UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "blend: element count must be a multiple of 4");
+  blend_fwd_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), d, reinterpret_cast<float4*>(out), n / 4);
+  return check_launch("blend_fwd");
+}
+int blend_dots(const float* g, const float* t, const float* x, float* dots, long long n, cudaStream_t st) {
+  UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "blend_dots: element count must be a multiple of 4");
+  blend_dots_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, st>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), dots, n / 4);
+  return check_launch("blend_dots");
+}
+int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st) {
+  UVC_REQUIRE(P % 4 == 0 && HW % P == 0, UVC_ERR_BAD_SHAPE, "im2col: patch %d must divide image %d and be a multiple of 4", P, HW);
+  const long long total4 = (long long)B * Cin * HW * HW / 4;
+  im2col16_kernel<<<grid_for(total4, 256, 148 * 16), 256, 0, st>>>(x, out, B, Cin, HW, P);
+  return check_launch("im2col16");
+}
+int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
+                    cudaStream_t st) {
+  UVC_REQUIRE((C & 3) == 0, UVC_ERR_BAD_SHAPE, "assemble_tokens: C must be a multiple of 4");
+  assemble_tokens_kernel<<<grid_for((long long)B * (np + 1) * (C / 4), 256, 148 * 16), 256, 0, st>>>(pe, cls, pos, pscale, tmask, tok, B, np, C);
+  return check_launch("assemble_tokens");
+}
+int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dpos, float* dcls,
+                        int B, int np, int C, cudaStream_t st) {
+  UVC_REQUIRE((C & 3) == 0, UVC_ERR_BAD_SHAPE, "assemble_tokens_bwd: C must be a multiple of 4");
+  const long long rows = (long long)B * np;
+  assemble_tokens_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(g, pe, pscale, tmask, dpe, dscale, B, np, C);
+  int rc = check_launch("assemble_tokens_bwd");
+  if (rc) return rc;
+  if (dpos) {
+    pos_cls_grad_kernel<<<np + 1, 128, 0, st>>>(g, dpos, dcls, B, np + 1, C);
+    rc = check_launch("pos_cls_grad");
+  }
+  return rc;
+}
+int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st) {
+  UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "scale_add: element count must be a multiple of 4");
+  scale_add_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), s_dev, s, n / 4);
+  return check_launch("scale_add");
+}
+
+}  // namespace uvc
