@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 1
+#define UVC_ABI_VERSION 2
+#define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
 #define UVC_API __attribute__((visibility("default")))
@@ -92,6 +93,136 @@ typedef struct {
 } uvc_gemm_args;
 
 UVC_API int uvc_gemm_tf32(const uvc_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise bandwidth-bound kernels (warp per row, float4 accesses).  `ld*` are row strides in
+ * elements (multiples of 4).  Every function is asynchronous on `stream`.
+ */
+
+/* y = (x - mean) * rstd * gamma + beta per row; mean/rstd (optional) are saved for the backward.
+ * Replaces nn.LayerNorm at models/model_distilled.py:199,204,288,507 (eps 1e-6) and
+ * T2TViT/models/transformer_block.py:84,88 (eps 1e-5). */
+UVC_API int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
+                              float* y, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t C, void* stream);
+/* dx = r1 + s2 * r2 + LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy.  r1, r2 (same ld as dx), s2_dev,
+ * dgamma/dbeta may be NULL.  The two residual inputs fuse the skip connection and the block-gate blend. */
+UVC_API int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                              const float* gamma, const float* r1, const float* r2, const float* s2_dev,
+                              float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
+/* in-place row softmax over the first n (<= 256) columns of S[rows][ld] (models/model_distilled.py:180) */
+UVC_API int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, void* stream);
+/* dP <- scale * P .* (dP - rowsum(dP .* P)) */
+UVC_API int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, void* stream);
+/* out[col] += scale * sum_rows X[row, col]  (bias gradients); scale_dev may be NULL (= 1) */
+UVC_API int uvc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, const float* scale_dev, float* out, void* stream);
+/* out = d[1] * t + d[0] * x   -- block gate blend, models/model_distilled.py:493 */
+UVC_API int uvc_blend_fwd(const float* t, const float* x, const float* d, float* out, int64_t n, void* stream);
+/* dots[0] += <g, x>, dots[1] += <g, t>  -- gradient of the blend weights */
+UVC_API int uvc_blend_dots(const float* g, const float* t, const float* x, float* dots, int64_t n, void* stream);
+/* im2col of the patch x patch / stride patch conv: out[(b, py, px), (c, ky, kx)]  (models/model_distilled.py:149) */
+UVC_API int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, void* stream);
+/* tok[b,0,:] = cls + pos[0]; tok[b,1+p,:] = pe[b,p,:] * pscale[p] * tmask[b,p] + pos[1+p]
+ * (models/model_distilled.py:434-471; pscale / tmask may be NULL) */
+UVC_API int uvc_assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask,
+                                float* tok, int32_t B, int32_t np, int32_t C, void* stream);
+/* backward of uvc_assemble_tokens: dpe = g * scale; dscale[p] += ..., dtmask[b,p] = ..., dpos += sum_b g, dcls += sum_b g[:,0] */
+UVC_API int uvc_assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe,
+                                    float* dscale, float* dtmask, float* dpos, float* dcls, int32_t B, int32_t np, int32_t C, void* stream);
+/* y += s * (*s_dev) * x */
+UVC_API int uvc_scale_add(float* y, const float* x, const float* s_dev, float s, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention core  softmax(Q K^T * scale) V  per (image, head)   (models/model_distilled.py:175-185)
+ * qkv: [B*N, 3*H*d] exactly as nn.Linear(dim, 3*dim) writes it (q | k | v, head-major inside each).
+ * P:   [B, H, N, ldp] attention probabilities, saved for the backward (ldp = uvc_attn_ldp(N)); may be
+ *      workspace in inference.  ctx: [B*N, H*d] (already "transposed back", ready for the proj GEMM).
+ */
+UVC_API int32_t uvc_attn_ldp(int32_t N);
+UVC_API int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+/* dqkv [B*N, 3*H*d] from dctx [B*N, H*d]; dP is scratch of the same size as P */
+UVC_API int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv,
+                              int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss: soft-target cross entropy + soft distillation KL, forward and d(loss)/d(logits) in one pass
+ * (utils/losses.py:38-64 with timm SoftTargetCrossEntropy as base criterion, outputs_kd is outputs):
+ *   loss = (1-alpha) * mean_b sum_c -y log_softmax(s) + alpha * T^2 / (B*NC) * sum exp(lt) (lt - ls),
+ *   ls = log_softmax(s/T), lt = log_softmax(t/T).   t may be NULL (distillation 'none', alpha ignored).
+ * loss_out[0] = loss, loss_out[1] = base, loss_out[2] = kd (zeroed by the call).  dlogits is scaled by grad_scale.
+ */
+UVC_API int uvc_distill_loss(const float* logits, const float* teacher_logits, const float* targets, int32_t B, int32_t NC,
+                             float alpha, float T, float grad_scale, float* loss_out, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: global-norm clip + AdamW   (joint_train.py:428-429, torch.optim.AdamW semantics)
+ *   uvc_sqnorm_accum : acc[0] += sum g^2                       (call once per gradient buffer)
+ *   uvc_clip_adamw   : coef = min(1, max_norm / (sqrt(acc[0]) + 1e-6)) (1 if max_norm <= 0); g *= coef;
+ *                      p *= 1 - lr*wd; m,v updated; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+ * `step` is the 1-based step count; hyper-parameters are host scalars.  mask (optional, same size as p)
+ * multiplies the update so masked weights stay exactly 0 (Stage 2, post_train.py:357-360).
+ */
+UVC_API int uvc_sqnorm_accum(const float* g, int64_t n, float* acc, void* stream);
+UVC_API int uvc_clip_adamw(float* p, float* g, float* m, float* v, const float* mask, int64_t n, const float* sqnorm_acc, float max_norm,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-model engine: DistilledVisionTransformer forward / backward as one call each
+ * (models/model_distilled.py:429-531).  Tensors are passed by pointer; `blocks` is a HOST array.
+ * The same struct shape is used for parameters and for gradients.
+ */
+typedef struct {
+  float *norm1_w, *norm1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} uvc_block_tensors;
+
+typedef struct {
+  float *patch_w, *patch_b;      /* [C, in_chans*patch*patch], [C] */
+  float *cls_token, *pos_embed;  /* [C], [ntok, C] */
+  float *norm_w, *norm_b;        /* final LayerNorm */
+  float *head_w, *head_b;        /* [num_classes, C], [num_classes] */
+  const uvc_block_tensors* blocks;   /* host array, L entries */
+} uvc_vit_tensors;
+
+typedef struct {
+  int32_t B, img, patch, in_chans;
+  int32_t C, H, Fh, L, num_classes;
+  float ln_eps;
+} uvc_vit_dims;
+
+typedef struct {
+  uvc_vit_dims dims;
+  uvc_vit_tensors w;
+  const float* x;                /* [B, in_chans, img, img] */
+  const float* blend;            /* device [L,2] = (d0, d1) per block: x <- d1*blk(x) + d0*x; NULL = plain blocks */
+  const uint8_t* skip_host;      /* host [L] or NULL; nonzero = block is not executed (hard skip, :496-500) */
+  const float* patch_scale;      /* device [np] or NULL (patch gate mode 1, :434-444) */
+  const float* token_mask;       /* device [B, np] or NULL (token gate, :446-456) */
+  int32_t save_for_backward;     /* 1: keep activations in the workspace for uvc_vit_backward */
+  int32_t enable_jumping;        /* final norm sees the sum of all block outputs (:503-506) */
+  float* logits;                 /* [B, num_classes] */
+  float* pe_out;                 /* optional [B*np, C]: raw patch embeddings (before gates), may be NULL */
+  void* workspace; uint64_t workspace_bytes;
+} uvc_vit_forward_args;
+
+typedef struct {
+  uvc_vit_dims dims;
+  uvc_vit_tensors w;
+  uvc_vit_tensors g;             /* gradients, ACCUMULATED into (caller zeroes) */
+  const float* dlogits;          /* [B, num_classes] */
+  const float* blend;
+  const uint8_t* skip_host;
+  const float* patch_scale;
+  const float* token_mask;
+  int32_t enable_jumping;
+  int32_t _pad;
+  float* d_blend;                /* [L,2], accumulated; NULL if blend == NULL */
+  float* d_patch_scale;          /* [np] accumulated, or NULL */
+  float* d_token_mask;           /* [B, np] written, or NULL */
+  void* workspace; uint64_t workspace_bytes;   /* the workspace the forward ran with */
+} uvc_vit_backward_args;
+
+UVC_API uint64_t uvc_vit_workspace_bytes(const uvc_vit_dims* dims, int32_t save_for_backward);
+UVC_API int uvc_vit_forward(const uvc_vit_forward_args* args, void* stream);
+UVC_API int uvc_vit_backward(const uvc_vit_backward_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,140 @@
+"""ORACLE (test infrastructure only) — plain-PyTorch CPU restatement of the reference's hot path.
+
+Only `tests/`, `__graft_entry__.smoke()`, `oracle/gen_golden.py` and `bench.py`'s reference / cpu_baseline
+legs may import this file; the product (`uvc_b200/`) never does.
+
+Every function restates, op for op, a span of the reference (paths under /root/reference/UVC) and cites
+it.  The restatement is PINNED against the unmodified reference modules imported in place
+(`oracle/ref_shim.py`): `tests/test_oracle_vs_reference.py` (runs where /root/reference exists) checks
+logits, losses, gradients and MAC lists bit-for-bit on CPU, and `tests/golden/*.pt` (written by
+`oracle/gen_golden.py` FROM THE REFERENCE) pins it again on the GPU box where the reference is absent.
+
+Everything works on a state dict with the reference's key names, in whatever dtype the tensors have
+(fp32 for parity with the reference; the GPU tests also evaluate it in fp64 to measure which of
+{reference fp32, CUDA TF32} is closer to exact arithmetic).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------- model forward
+def patch_embed(sd, x, patch=16):
+    """models/model_distilled.py:145-153 — Conv2d(k=stride=patch) -> flatten(2).transpose(1,2)."""
+    y = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch)
+    return y.flatten(2).transpose(1, 2)
+
+
+def attention(sd, pre, x, num_heads):
+    """models/model_distilled.py:168-191."""
+    B, N, C = x.shape
+    qkv = F.linear(x, sd[pre + "attn.qkv.weight"], sd.get(pre + "attn.qkv.bias"))
+    qkv = qkv.reshape(B, N, 3, num_heads, C // num_heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * ((C // num_heads) ** -0.5)
+    attn = attn.softmax(dim=-1)
+    x = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    return F.linear(x, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
+
+
+def mlp(sd, pre, x):
+    """models/model_distilled.py:112-126 (nn.GELU() = erf form)."""
+    x = F.linear(x, sd[pre + "mlp.fc1.weight"], sd[pre + "mlp.fc1.bias"])
+    x = F.gelu(x)
+    return F.linear(x, sd[pre + "mlp.fc2.weight"], sd[pre + "mlp.fc2.bias"])
+
+
+def block(sd, i, x, num_heads, eps):
+    """models/model_distilled.py:238-244 (enable_part_gating == 0 branch)."""
+    pre = f"blocks.{i}."
+    C = x.shape[-1]
+    x = x + attention(sd, pre, F.layer_norm(x, (C,), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], eps), num_heads)
+    x = x + mlp(sd, pre, F.layer_norm(x, (C,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], eps))
+    return x
+
+
+def block_macs(B, N, C, H, Fh):
+    """MAC bookkeeping of Attention.forward / Mlp.forward (models/model_distilled.py:115,121,177,182,185,189)."""
+    d = C // H
+    return [B * 3 * C * N * C, N * B * H * N * d, N * B * H * N * d, B * N * C * C, Fh * B * N * C, C * B * N * Fh]
+
+
+def forward(sd, x, depth, num_heads, eps=1e-6, blend=None, skip=None, patch_scale=None, token_mask=None, enable_jumping=False, patch=16):
+    """DistilledVisionTransformer.forward_features + forward, enable_dist == 0 (models/model_distilled.py:429-531).
+
+    blend: [L,2] tensor of (d0, d1) = the `distrib` of :480-493 (already sampled), or None
+    skip:  list[bool] of hard-skipped blocks (:496-500), or None
+    patch_scale: [196] multiplier (:434-444); token_mask: [B,196] multiplier (:446-456)
+    returns logits [B, num_classes]
+    """
+    x = patch_embed(sd, x, patch)
+    if patch_scale is not None:
+        x = x * patch_scale.view(1, -1, 1)
+    if token_mask is not None:
+        x = x * token_mask.unsqueeze(-1)
+    B = x.shape[0]
+    x = torch.cat((sd["cls_token"].expand(B, -1, -1), x), dim=1)
+    x = x + sd["pos_embed"]
+    accum = 0
+    for i in range(depth):
+        if blend is not None:
+            tmp = block(sd, i, x, num_heads, eps)
+            x = blend[i, 1] * tmp + blend[i, 0] * x
+        elif skip is None or not skip[i]:
+            x = block(sd, i, x, num_heads, eps)
+        accum = accum + x
+    if enable_jumping:
+        x = accum
+    x = F.layer_norm(x, (x.shape[-1],), sd["norm.weight"], sd["norm.bias"], eps)
+    return F.linear(x[:, 0], sd["head.weight"], sd["head.bias"])
+
+
+# --------------------------------------------------------------------------------------------- losses
+def soft_target_cross_entropy(logits, target):
+    """timm.loss.SoftTargetCrossEntropy (un-vendored dependency; joint_train.py:940-942):
+    mean_b sum_c -target * log_softmax(logits)."""
+    return torch.sum(-target * F.log_softmax(logits, dim=-1), dim=-1).mean()
+
+
+def distillation_loss(logits, teacher_logits, target, alpha, T, distillation_type="soft"):
+    """utils/losses.py:25-65 with outputs_kd is outputs (enable_deit == 0, models/model_distilled.py:523-524).
+    returns (loss, base, kd)."""
+    base = soft_target_cross_entropy(logits, target)
+    if distillation_type == "none":
+        return base, base, torch.zeros_like(base)
+    kd = F.kl_div(F.log_softmax(logits / T, dim=1), F.log_softmax(teacher_logits / T, dim=1), reduction="sum", log_target=True) \
+        * (T * T) / logits.numel()
+    return base * (1 - alpha) + kd * alpha, base, kd
+
+
+# --------------------------------------------------------------------------------------------- mixup (timm.data.Mixup, batch mode)
+def one_hot_smooth(y, num_classes, smoothing):
+    """timm.data.mixup.one_hot / mixup_target: off = smoothing / K, on = 1 - smoothing + off."""
+    off = smoothing / num_classes
+    on = 1.0 - smoothing + off
+    return torch.full((y.shape[0], num_classes), off, dtype=torch.float32, device=y.device).scatter_(1, y.view(-1, 1), on)
+
+
+def mixup_target(y, num_classes, lam, smoothing):
+    y1 = one_hot_smooth(y, num_classes, smoothing)
+    y2 = one_hot_smooth(y.flip(0), num_classes, smoothing)
+    return y1 * lam + y2 * (1.0 - lam)
+
+
+# --------------------------------------------------------------------------------------------- optimiser
+def clip_adamw_step(params, grads, ms, vs, step, lr, max_norm=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05):
+    """torch.nn.utils.clip_grad_norm_(., max_norm) + torch.optim.AdamW.step() (joint_train.py:271,428-429), single-tensor form."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    b1, b2 = betas
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    for p, g, m, v in zip(params, grads, ms, vs):
+        g = g * coef
+        p.mul_(1 - lr * weight_decay)
+        m.lerp_(g, 1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / bc1)
+    return total

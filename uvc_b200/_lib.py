@@ -31,7 +31,52 @@ class GemmArgs(C.Structure):
                 ("flags", C.c_int32), ("_pad", C.c_int32)]
 
 
-_ABI_STRUCTS = {"uvc_operand": Operand, "uvc_gemm_args": GemmArgs}
+_F = C.c_void_p   # device float*
+
+
+class BlockTensors(C.Structure):
+    NAMES = ("norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+    _fields_ = [(n, _F) for n in NAMES]
+
+
+class VitTensors(C.Structure):
+    NAMES = ("patch_w", "patch_b", "cls_token", "pos_embed", "norm_w", "norm_b", "head_w", "head_b")
+    _fields_ = [(n, _F) for n in NAMES] + [("blocks", C.POINTER(BlockTensors))]
+
+
+class VitDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("img", C.c_int32), ("patch", C.c_int32), ("in_chans", C.c_int32),
+                ("C", C.c_int32), ("H", C.c_int32), ("Fh", C.c_int32), ("L", C.c_int32), ("num_classes", C.c_int32),
+                ("ln_eps", C.c_float)]
+
+
+class VitForwardArgs(C.Structure):
+    _fields_ = [("dims", VitDims), ("w", VitTensors), ("x", _F), ("blend", _F), ("skip_host", C.c_void_p),
+                ("patch_scale", _F), ("token_mask", _F), ("save_for_backward", C.c_int32), ("enable_jumping", C.c_int32),
+                ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class VitBackwardArgs(C.Structure):
+    _fields_ = [("dims", VitDims), ("w", VitTensors), ("g", VitTensors), ("dlogits", _F), ("blend", _F),
+                ("skip_host", C.c_void_p), ("patch_scale", _F), ("token_mask", _F), ("enable_jumping", C.c_int32),
+                ("_pad", C.c_int32), ("d_blend", _F), ("d_patch_scale", _F), ("d_token_mask", _F),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+_ABI_STRUCTS = {"uvc_operand": Operand, "uvc_gemm_args": GemmArgs, "uvc_block_tensors": BlockTensors,
+                "uvc_vit_tensors": VitTensors, "uvc_vit_dims": VitDims, "uvc_vit_forward_args": VitForwardArgs,
+                "uvc_vit_backward_args": VitBackwardArgs}
+
+UVC_MAX_DEPTH = 32
+
+# every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_gemm_tf32",
+    "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
+    "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_scale_add",
+    "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
+    "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
+]
 
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC = 1, 2, 4, 8, 16
 
@@ -66,6 +111,34 @@ def load():
         n = lib.uvc_abi_sizeof(name.encode())
         if n != C.sizeof(st):
             raise UvcError(f"ABI mismatch for {name}: library {n} bytes, binding {C.sizeof(st)} bytes")
+    i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+    protos = {
+        "uvc_gemm_tf32": [C.POINTER(GemmArgs), vp],
+        "uvc_layernorm_fwd": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, vp],
+        "uvc_layernorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp],
+        "uvc_softmax_fwd": [vp, i64, i64, i32, vp],
+        "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, vp],
+        "uvc_colsum": [vp, i64, i32, i32, vp, vp, vp],
+        "uvc_blend_fwd": [vp, vp, vp, vp, i64, vp],
+        "uvc_blend_dots": [vp, vp, vp, vp, i64, vp],
+        "uvc_im2col16": [vp, vp, i32, i32, i32, i32, vp],
+        "uvc_assemble_tokens": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "uvc_assemble_tokens_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
+        "uvc_scale_add": [vp, vp, vp, f32, i64, vp],
+        "uvc_attention_fwd": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_attention_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_distill_loss": [vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp],
+        "uvc_sqnorm_accum": [vp, i64, vp, vp],
+        "uvc_clip_adamw": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],
+        "uvc_vit_forward": [C.POINTER(VitForwardArgs), vp],
+        "uvc_vit_backward": [C.POINTER(VitBackwardArgs), vp],
+    }
+    for name, argtypes in protos.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    lib.uvc_attn_ldp.argtypes = [i32]; lib.uvc_attn_ldp.restype = i32
+    lib.uvc_vit_workspace_bytes.argtypes = [C.POINTER(VitDims), i32]; lib.uvc_vit_workspace_bytes.restype = C.c_uint64
     _lib = lib
     return lib
 

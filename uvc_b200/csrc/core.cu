@@ -31,6 +31,11 @@ extern "C" int uvc_abi_sizeof(const char* name) {
 #define UVC_SZ(T) if (strcmp(name, #T) == 0) return (int)sizeof(T)
   UVC_SZ(uvc_operand);
   UVC_SZ(uvc_gemm_args);
+  UVC_SZ(uvc_block_tensors);
+  UVC_SZ(uvc_vit_tensors);
+  UVC_SZ(uvc_vit_dims);
+  UVC_SZ(uvc_vit_forward_args);
+  UVC_SZ(uvc_vit_backward_args);
 #undef UVC_SZ
   return -1;
 }

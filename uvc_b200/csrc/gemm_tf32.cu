@@ -13,7 +13,7 @@
 // other's main loop.  Split-K (red.global.add) covers the long-K / few-tile weight-gradient GEMMs.
 //
 // Replaces: models/model_distilled.py:116,122,149,175,179,184,187,522 and their autograd backward.
-#include "common.cuh"
+#include "kernels.h"
 
 namespace uvc {
 

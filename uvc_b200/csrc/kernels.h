@@ -1,0 +1,53 @@
+// Internal (C++) launch functions shared between the .cu files of libuvc_sm100.so.  Each one validates
+// its arguments, enqueues on `st` and returns a uvc_status; the extern "C" entry points in
+// include/uvc_b200.h are thin wrappers over these, and vit_engine.cu composes them into the model.
+#pragma once
+#include "common.cuh"
+
+namespace uvc {
+
+int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st);
+
+int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
+                  float* rstd, int M, int C, cudaStream_t st);
+int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
+                  const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
+                  cudaStream_t st);
+int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st);
+int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st);
+int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);
+int blend_fwd(const float* t, const float* x, const float* d, float* out, long long n, cudaStream_t st);
+int blend_dots(const float* g, const float* t, const float* x, float* dots, long long n, cudaStream_t st);
+int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st);
+int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
+                    cudaStream_t st);
+int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,
+                        float* dpos, float* dcls, int B, int np, int C, cudaStream_t st);
+int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st);
+
+int attn_ldp(int N);
+int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st);
+int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int B, int H, int N, int d, float scale,
+                  cudaStream_t st);
+
+// ---- helpers to describe GEMM operands tersely
+inline uvc_operand op_k(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 0, 0}; }
+inline uvc_operand op_mn(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 1, 0}; }
+inline uvc_gemm_args gemm_args(int M, int N, int K, uvc_operand A, uvc_operand B, float* D, long long ldd) {
+  uvc_gemm_args a{};
+  a.M = M; a.N = N; a.K = K; a.nb1 = 1; a.nb2 = 1; a.splits = 1;
+  a.A = A; a.B = B; a.D = D; a.ldd = ldd;
+  a.alpha = 1.0f; a.beta = 1.0f;
+  return a;
+}
+// split-K factor for a weight-gradient GEMM (few output tiles, very long K): fill ~2 waves of 148 SMs
+inline int wgrad_splits(int M, int N, int K) {
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int s = (2 * 148 + tiles - 1) / tiles;
+  const int nkb = (K + 31) / 32;
+  if (s > nkb / 4) s = nkb / 4;
+  if (s < 1) s = 1;
+  return s;
+}
+
+}  // namespace uvc

@@ -5,7 +5,7 @@
 //
 // Reference spans: models/model_distilled.py:199,204,288,507 (LayerNorm), :179-181 (softmax),
 // :433-471 (patch embed, gates, cls/pos), :477-503 (block gate blend).
-#include "common.cuh"
+#include "kernels.h"
 
 namespace uvc {
 
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
 // backward of assemble: d_pe = g[b,1+p,:] * s ; dscale[p] += sum_{b,c} g * pe ; (dpos, dcls via colsum-style kernel below)
 __global__ void __launch_bounds__(128) assemble_tokens_bwd_kernel(const float* __restrict__ g, const float* __restrict__ pe, const float* __restrict__ pscale,
                                                                  const float* __restrict__ tmask, float* __restrict__ dpe, float* __restrict__ dscale,
-                                                                 int B, int np, int C) {
+                                                                 float* __restrict__ dtmask, int B, int np, int C) {
   // one warp per (b, p) row
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -284,18 +284,22 @@ __global__ void __launch_bounds__(128) assemble_tokens_bwd_kernel(const float* _
   const float4* gr = reinterpret_cast<const float4*>(g) + ((long long)b * (np + 1) + 1 + p) * nv;
   const float4* pr = reinterpret_cast<const float4*>(pe) + row * nv;
   float4* dr = reinterpret_cast<float4*>(dpe) + row * nv;
-  float s = 1.0f, sm = 1.0f;
-  if (pscale) s *= __ldg(pscale + p);
+  float s = 1.0f, sm = 1.0f, sp = 1.0f;
+  if (pscale) { sp = __ldg(pscale + p); s *= sp; }
   if (tmask) { sm = __ldg(tmask + row); s *= sm; }
   float dot = 0.f;
+  const bool need_dot = (dscale != nullptr) || (dtmask != nullptr);
   for (int c = lane; c < nv; c += 32) {
     const float4 gg = gr[c];
-    if (dscale) { const float4 v = pr[c]; dot += (gg.x * v.x + gg.y * v.y) + (gg.z * v.z + gg.w * v.w); }
+    if (need_dot) { const float4 v = pr[c]; dot += (gg.x * v.x + gg.y * v.y) + (gg.z * v.z + gg.w * v.w); }
     dr[c] = make_float4(gg.x * s, gg.y * s, gg.z * s, gg.w * s);
   }
-  if (dscale) {
+  if (need_dot) {
     dot = warp_sum(dot);
-    if (lane == 0) atomicAdd(dscale + p, dot * sm);
+    if (lane == 0) {
+      if (dscale) atomicAdd(dscale + p, dot * sm);
+      if (dtmask) dtmask[row] = dot * sp;
+    }
   }
 }
 // dpos[n,:] += sum_b g[b,n,:] ; dcls[:] += sum_b g[b,0,:]
@@ -393,11 +397,11 @@ int assemble_tokens(const float* pe, const float* cls, const float* pos, const f
   assemble_tokens_kernel<<<grid_for((long long)B * (np + 1) * (C / 4), 256, 148 * 16), 256, 0, st>>>(pe, cls, pos, pscale, tmask, tok, B, np, C);
   return check_launch("assemble_tokens");
 }
-int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dpos, float* dcls,
-                        int B, int np, int C, cudaStream_t st) {
+int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,
+                        float* dpos, float* dcls, int B, int np, int C, cudaStream_t st) {
   UVC_REQUIRE((C & 3) == 0, UVC_ERR_BAD_SHAPE, "assemble_tokens_bwd: C must be a multiple of 4");
   const long long rows = (long long)B * np;
-  assemble_tokens_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(g, pe, pscale, tmask, dpe, dscale, B, np, C);
+  assemble_tokens_bwd_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, st>>>(g, pe, pscale, tmask, dpe, dscale, dtmask, B, np, C);
   int rc = check_launch("assemble_tokens_bwd");
   if (rc) return rc;
   if (dpos) {
@@ -413,3 +417,58 @@ int scale_add(float* y, const float* x, const float* s_dev, float s, long long n
 }
 
 }  // namespace uvc
+
+// ------------------------------------------------------------------------------------------ C ABI
+#define UVC_ST static_cast<cudaStream_t>(stream)
+extern "C" {
+int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y, int64_t ldy, float* mean,
+                      float* rstd, int32_t M, int32_t C, void* stream) {
+  UVC_REQUIRE(x && gamma && beta && y, UVC_ERR_BAD_ARG, "uvc_layernorm_fwd: NULL pointer");
+  return uvc::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, UVC_ST);
+}
+int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                      const float* r1, const float* r2, const float* s2_dev, float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M,
+                      int32_t C, void* stream) {
+  UVC_REQUIRE(dy && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd: NULL pointer");
+  UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd: dgamma and dbeta must both be given or both NULL");
+  return uvc::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST);
+}
+int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, void* stream) {
+  UVC_REQUIRE(S, UVC_ERR_BAD_ARG, "uvc_softmax_fwd: NULL pointer");
+  return uvc::softmax_fwd(S, ld, rows, n, UVC_ST);
+}
+int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, void* stream) {
+  UVC_REQUIRE(P && dP, UVC_ERR_BAD_ARG, "uvc_softmax_bwd: NULL pointer");
+  return uvc::softmax_bwd(P, dP, ld, rows, n, scale, UVC_ST);
+}
+int uvc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, const float* scale_dev, float* out, void* stream) {
+  UVC_REQUIRE(X && out, UVC_ERR_BAD_ARG, "uvc_colsum: NULL pointer");
+  return uvc::colsum(X, ld, M, N, scale_dev, out, UVC_ST);
+}
+int uvc_blend_fwd(const float* t, const float* x, const float* d, float* out, int64_t n, void* stream) {
+  UVC_REQUIRE(t && x && d && out, UVC_ERR_BAD_ARG, "uvc_blend_fwd: NULL pointer");
+  return uvc::blend_fwd(t, x, d, out, n, UVC_ST);
+}
+int uvc_blend_dots(const float* g, const float* t, const float* x, float* dots, int64_t n, void* stream) {
+  UVC_REQUIRE(g && t && x && dots, UVC_ERR_BAD_ARG, "uvc_blend_dots: NULL pointer");
+  return uvc::blend_dots(g, t, x, dots, n, UVC_ST);
+}
+int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, void* stream) {
+  UVC_REQUIRE(x && out, UVC_ERR_BAD_ARG, "uvc_im2col16: NULL pointer");
+  return uvc::im2col16(x, out, B, Cin, HW, P, UVC_ST);
+}
+int uvc_assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int32_t B,
+                        int32_t np, int32_t C, void* stream) {
+  UVC_REQUIRE(pe && cls && pos && tok, UVC_ERR_BAD_ARG, "uvc_assemble_tokens: NULL pointer");
+  return uvc::assemble_tokens(pe, cls, pos, pscale, tmask, tok, B, np, C, UVC_ST);
+}
+int uvc_assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,
+                            float* dpos, float* dcls, int32_t B, int32_t np, int32_t C, void* stream) {
+  UVC_REQUIRE(g && pe && dpe, UVC_ERR_BAD_ARG, "uvc_assemble_tokens_bwd: NULL pointer");
+  return uvc::assemble_tokens_bwd(g, pe, pscale, tmask, dpe, dscale, dtmask, dpos, dcls, B, np, C, UVC_ST);
+}
+int uvc_scale_add(float* y, const float* x, const float* s_dev, float s, int64_t n, void* stream) {
+  UVC_REQUIRE(y && x, UVC_ERR_BAD_ARG, "uvc_scale_add: NULL pointer");
+  return uvc::scale_add(y, x, s_dev, s, n, UVC_ST);
+}
+}  // extern "C"

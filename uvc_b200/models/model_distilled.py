@@ -1,0 +1,457 @@
+"""DeiT / ViT operator surface of UVC, backed by the sm_100a engine (libuvc_sm100.so).
+
+Mirror of the reference's `UVC/models/model_distilled.py` (class names, constructor arguments, attribute
+names, parameter names/shapes and state-dict keys are the reference's, so DeiT checkpoints and the
+Stage-1 -> Stage-2 state dicts load unchanged and `joint_train.py` / `post_train.py` /
+`uvc_optimizer.py` can poke the same attributes):
+
+    DistilledVisionTransformer(enable_dist, enable_jumping=0, enable_block_gating=0, enable_part_gating=0,
+                               enable_patch_gating=0, gumbel_hard=True, use_gumbel=False, eps=0.1,
+                               enable_warmup=False, patch_hard=False, *, patch_size, embed_dim, depth,
+                               num_heads, mlp_ratio, qkv_bias, norm_layer, drop_rate)        (reference :391)
+    forward(x, tau=-1, number=0.9) -> train: ((logits, logits_dist), (macs_embed, macs_list))
+                                      eval : ((logits + logits_dist) / 2, (macs_embed, macs_list))   (:510-531)
+
+The nn.Modules only HOLD parameters.  The whole forward (patch embed, gates, L blocks, final norm, head)
+is one call into `uvc_vit_forward`, the whole backward one call into `uvc_vit_backward`; the only torch
+ops on the path are the 2-element Gumbel draws for the block gates (kept in torch so the random
+stream is the reference's) and, in token-gating mode, the [B,196] score/top-k arithmetic.
+There is no fallback: on a machine without a GPU / without the library the forward raises.
+"""
+import ctypes as C
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import _lib
+from .._lib import BlockTensors, VitBackwardArgs, VitDims, VitForwardArgs, VitTensors
+
+__all__ = ["DistilledVisionTransformer", "VisionTransformer", "Block", "Attention", "Mlp", "PatchEmbed", "gumbel_softmax", "scatter",
+           "deit_tiny_patch16_224", "deit_small_patch16_224", "deit_base_patch16_224"]
+
+
+def _to_2tuple(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+def scatter(logits, index, k):
+    """One-hot rows from top-k indices (reference :21-33) without the host round trip."""
+    out = torch.zeros_like(logits)
+    out.scatter_(1, index.reshape(logits.shape[0], k), 1.0)
+    return out
+
+
+def gumbel_softmax(logits, k=0.9, tau=1, hard=False, eps=1e-10, dim=-1):
+    """Token-gate Gumbel top-k straight-through estimator (reference :36-63), same RNG consumption."""
+    gumbels = -torch.empty_like(logits).exponential_().log()
+    gumbels = (logits + gumbels) / tau
+    y_soft = gumbels.softmax(dim)
+    if hard:
+        index = y_soft.topk(k, dim=dim)[1]
+        y_hard = scatter(logits, index, k)
+        return y_hard - y_soft.detach() + y_soft
+    return y_soft
+
+
+class _OpContainer(nn.Module):
+    """Sub-modules exist for their parameters and names; compute happens in the fused engine."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError(f"{type(self).__name__} is a parameter container: run the enclosing DistilledVisionTransformer "
+                           "(the sm_100a engine executes the whole model in one call)")
+
+
+class Mlp(_OpContainer):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        assert drop == 0., "the sm_100a engine implements drop_rate == 0 (every shipped UVC config)"
+        assert act_layer is nn.GELU, "the sm_100a engine implements erf-GELU"
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+
+class PatchEmbed(_OpContainer):
+    def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, norm_layer=None, flatten=True):
+        super().__init__()
+        img_size, patch_size = _to_2tuple(img_size), _to_2tuple(patch_size)
+        assert norm_layer is None and flatten
+        self.img_size, self.patch_size = img_size, patch_size
+        self.grid_size = (img_size[0] // patch_size[0], img_size[1] // patch_size[1])
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.flatten = flatten
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+        self.norm = nn.Identity()
+
+
+class Attention(_OpContainer):
+    def __init__(self, dim, num_heads=8, qkv_bias=False, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        assert attn_drop == 0. and proj_drop == 0.
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+
+class Block(_OpContainer):
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=False, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU,
+                 norm_layer=nn.LayerNorm, enable_part_gating=0, gumbel_hard=True):
+        super().__init__()
+        assert drop_path == 0., "the sm_100a engine implements drop_path == 0 (every shipped UVC config)"
+        self.norm1 = norm_layer(dim)
+        self.gumbel_hard = gumbel_hard
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.enable_part_gating = enable_part_gating
+        self.attn_skip_gating = nn.Parameter(torch.Tensor([-1, 1]))
+        self.mlp_skip_gating = nn.Parameter(torch.Tensor([-1, 1]))
+
+
+def _init_vit_weights(module):
+    """timm's default (non-jax) ViT init, as the reference applies it (:65-97)."""
+    if isinstance(module, nn.Linear):
+        nn.init.trunc_normal_(module.weight, std=.02)
+        if module.bias is not None:
+            nn.init.zeros_(module.bias)
+    elif isinstance(module, nn.LayerNorm):
+        nn.init.zeros_(module.bias)
+        nn.init.ones_(module.weight)
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, gumbel_hard=True, enable_part_gating=0, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768,
+                 depth=12, num_heads=12, mlp_ratio=4., qkv_bias=True, representation_size=None, distilled=False, drop_rate=0.,
+                 attn_drop_rate=0., drop_path_rate=0., embed_layer=PatchEmbed, norm_layer=None, act_layer=None, weight_init=''):
+        super().__init__()
+        assert representation_size is None and weight_init == '' and drop_path_rate == 0. and attn_drop_rate == 0.
+        self.num_classes = num_classes
+        self.num_features = self.embed_dim = embed_dim
+        self.num_tokens = 2 if distilled else 1
+        norm_layer = norm_layer or partial(nn.LayerNorm, eps=1e-6)
+        act_layer = act_layer or nn.GELU
+        self.gumbel_hard = gumbel_hard
+        self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim)
+        num_patches = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim)) if distilled else None
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + self.num_tokens, embed_dim))
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        self.blocks = nn.Sequential(*[
+            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop_rate, attn_drop=attn_drop_rate,
+                  drop_path=0., norm_layer=norm_layer, act_layer=act_layer, enable_part_gating=enable_part_gating,
+                  gumbel_hard=self.gumbel_hard) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        self.pre_logits = nn.Identity()
+        self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
+        self.head_dist = None
+        if distilled:
+            self.head_dist = nn.Linear(self.embed_dim, self.num_classes) if num_classes > 0 else nn.Identity()
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        if self.dist_token is not None:
+            nn.init.trunc_normal_(self.dist_token, std=.02)
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        self.apply(_init_vit_weights)
+
+    def _init_weights(self, m):
+        _init_vit_weights(m)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'pos_embed', 'cls_token', 'dist_token'}
+
+
+# --------------------------------------------------------------------------------------------------------- engine glue
+class _EngineState:
+    """Per-model cache: ctypes parameter tables, workspaces, flat gradient arena."""
+
+    def __init__(self):
+        self.sig = None
+        self.w = self.g = None
+        self.keep = None
+        self.ws = {}
+        self.grad_arena = None
+        self.grad_views = None
+
+
+def _engine_param_list(model):
+    """(name, Parameter) in the fixed order the autograd Function receives them."""
+    out = [("patch_w", model.patch_embed.proj.weight), ("patch_b", model.patch_embed.proj.bias), ("cls_token", model.cls_token),
+           ("pos_embed", model.pos_embed), ("norm_w", model.norm.weight), ("norm_b", model.norm.bias),
+           ("head_w", model.head.weight), ("head_b", model.head.bias)]
+    for i, blk in enumerate(model.blocks):
+        out += [(f"b{i}.norm1_w", blk.norm1.weight), (f"b{i}.norm1_b", blk.norm1.bias), (f"b{i}.qkv_w", blk.attn.qkv.weight),
+                (f"b{i}.qkv_b", blk.attn.qkv.bias), (f"b{i}.proj_w", blk.attn.proj.weight), (f"b{i}.proj_b", blk.attn.proj.bias),
+                (f"b{i}.norm2_w", blk.norm2.weight), (f"b{i}.norm2_b", blk.norm2.bias), (f"b{i}.fc1_w", blk.mlp.fc1.weight),
+                (f"b{i}.fc1_b", blk.mlp.fc1.bias), (f"b{i}.fc2_w", blk.mlp.fc2.weight), (f"b{i}.fc2_b", blk.mlp.fc2.bias)]
+    return out
+
+
+def _fill_tables(named_tensors, L):
+    """Build a uvc_vit_tensors (+ its host block array) from [(name, tensor-or-None)]."""
+    vt = VitTensors()
+    blocks = (BlockTensors * L)()
+    for name, t in named_tensors:
+        ptr = None if t is None else t.data_ptr()
+        if name.startswith("b"):
+            head, field = name.split(".")
+            setattr(blocks[int(head[1:])], field, ptr)
+        else:
+            setattr(vt, name, ptr)
+    vt.blocks = C.cast(blocks, C.POINTER(BlockTensors))
+    return vt, blocks
+
+
+class _VitFunction(torch.autograd.Function):
+    """One autograd node for the whole model: forward = uvc_vit_forward, backward = uvc_vit_backward."""
+
+    @staticmethod
+    def forward(ctx, model, x, blend, patch_scale, token_mask, skip, *params):
+        need_grad = torch.is_grad_enabled() and (any(p is not None and p.requires_grad for p in params) or
+                                                 (blend is not None and blend.requires_grad) or
+                                                 (patch_scale is not None and patch_scale.requires_grad) or
+                                                 (token_mask is not None and token_mask.requires_grad))
+        logits = model._engine_forward(x, blend, patch_scale, token_mask, skip, save=need_grad)
+        ctx.model, ctx.skip, ctx.B = model, skip, x.shape[0]
+        ctx.save_for_backward(blend, patch_scale, token_mask)
+        ctx.param_requires = [p is not None and p.requires_grad for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        blend, patch_scale, token_mask = ctx.saved_tensors
+        grads, d_blend, d_ps, d_tm = ctx.model._engine_backward(ctx.B, dlogits.contiguous(), blend, patch_scale, token_mask, ctx.skip)
+        out = [g if (g is not None and req) else None for g, req in zip(grads, ctx.param_requires)]
+        return (None, None, d_blend, d_ps, d_tm, None, *out)
+
+
+class DistilledVisionTransformer(VisionTransformer):
+    def __init__(self, enable_dist, enable_jumping=0, enable_block_gating=0, enable_part_gating=0, enable_patch_gating=0, gumbel_hard=True,
+                 use_gumbel=False, eps=0.1, enable_warmup=False, patch_hard=False, *args, **kwargs):
+        super().__init__(gumbel_hard, *args, **kwargs)
+        if enable_dist:
+            raise NotImplementedError("enable_dist=1 (distillation token) is outside the sm_100a hot path; every shipped UVC run uses enable_deit=0")
+        self.dist_token = None
+        self.num_tokens = 1
+        num_patches = self.patch_embed.num_patches
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + self.num_tokens, self.embed_dim))
+        self.head_dist = None
+        self.enable_block_gating = enable_block_gating
+        self.enable_jumping = enable_jumping
+        self.enable_patch_gating = enable_patch_gating
+        self.enable_part_gating = enable_part_gating
+        self.use_gumbel = use_gumbel
+        self.eps = eps
+        self.gumbel = nn.Linear(self.embed_dim, 1)
+        self.enable_warmup = enable_warmup
+        if self.enable_block_gating:
+            print("=====> Block gating enabled <=====")
+        self.block_skip_gating = nn.Parameter(torch.Tensor([-1, 1]).expand(len(self.blocks), 2).contiguous())
+        self.patch_gating = nn.Parameter(torch.zeros(1, self.patch_embed.grid_size[0] * self.patch_embed.grid_size[1], 1)) \
+            if self.enable_patch_gating == 1 else None
+        self.gumbel_hard = gumbel_hard
+        self.patch_hard = patch_hard
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+        self._es = _EngineState()
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _dims(self, B):
+        pe = self.patch_embed
+        d = VitDims()
+        d.B, d.img, d.patch, d.in_chans = int(B), int(pe.img_size[0]), int(pe.patch_size[0]), int(pe.proj.in_channels)
+        d.C, d.H, d.Fh, d.L = self.embed_dim, self.blocks[0].attn.num_heads, self.blocks[0].mlp.fc1.out_features, len(self.blocks)
+        d.num_classes = self.num_classes
+        d.ln_eps = float(self.norm.eps)
+        return d
+
+    def _tables(self):
+        es = self._es
+        plist = _engine_param_list(self)
+        sig = tuple(-1 if p is None else p.data_ptr() for _, p in plist)
+        if es.sig != sig:
+            dev = self.cls_token.device
+            for name, p in plist:
+                if p is not None and not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise _lib.UvcError(f"parameter {name} must be a contiguous CUDA fp32 tensor (got {p.device}, {p.dtype}); "
+                                        "the sm_100a engine has no CPU path")
+            es.w, keep_w = _fill_tables(plist, len(self.blocks))
+            # flat gradient arena in the same order; every slot padded to 4 floats (16 B) for vector access
+            offs, total = [], 0
+            for _, p in plist:
+                n = 0 if p is None else p.numel()
+                offs.append(total)
+                total += (n + 3) // 4 * 4
+            es.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
+            es.grad_views = [None if p is None else es.grad_arena[o:o + p.numel()].view(p.shape) for (_, p), o in zip(plist, offs)]
+            es.g, keep_g = _fill_tables([(n, v) for (n, _), v in zip(plist, es.grad_views)], len(self.blocks))
+            es.keep = (keep_w, keep_g)
+            es.sig = sig
+        return es
+
+    def _workspace(self, B, save):
+        es = self._es
+        key = (int(B), bool(save))
+        ws = es.ws.get(key)
+        if ws is None:
+            lib = _lib.load()
+            d = self._dims(B)
+            nbytes = int(lib.uvc_vit_workspace_bytes(C.byref(d), 1 if save else 0))
+            if nbytes == 0:
+                raise _lib.UvcError("uvc_vit_workspace_bytes: " + lib.uvc_last_error().decode())
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.cls_token.device)
+            es.ws = {k: v for k, v in es.ws.items() if k[1] != key[1]}   # one workspace per mode; batch-size changes re-allocate
+            es.ws[key] = ws
+        return ws
+
+    def _engine_forward(self, x, blend, patch_scale, token_mask, skip, save):
+        if not x.is_cuda:
+            raise _lib.UvcError("uvc_b200 runs on CUDA tensors only (no CPU fallback): move the model and the batch to a B200")
+        lib = _lib.load()
+        es = self._tables()
+        B = x.shape[0]
+        x = x.contiguous().float()
+        a = VitForwardArgs()
+        a.dims = self._dims(B)
+        a.w = es.w
+        a.x = x.data_ptr()
+        a.blend = None if blend is None else blend.data_ptr()
+        skip_arr = None
+        if skip is not None:
+            skip_arr = (C.c_uint8 * len(skip))(*[1 if s else 0 for s in skip])
+            a.skip_host = C.cast(skip_arr, C.c_void_p)
+        a.patch_scale = None if patch_scale is None else patch_scale.data_ptr()
+        a.token_mask = None if token_mask is None else token_mask.data_ptr()
+        a.save_for_backward = 1 if save else 0
+        a.enable_jumping = 1 if self.enable_jumping else 0
+        logits = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
+        a.logits = logits.data_ptr()
+        ws = self._workspace(B, save)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.uvc_vit_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_forward")
+        return logits
+
+    def _engine_backward(self, B, dlogits, blend, patch_scale, token_mask, skip):
+        lib = _lib.load()
+        es = self._tables()
+        dev = dlogits.device
+        plist = _engine_param_list(self)
+        first = plist[0][1]
+        accumulate = first.grad is not None and first.grad.data_ptr() == es.grad_views[0].data_ptr()
+        if not accumulate:
+            es.grad_arena.zero_()
+        a = VitBackwardArgs()
+        a.dims = self._dims(B)
+        a.w, a.g = es.w, es.g
+        a.dlogits = dlogits.data_ptr()
+        d_blend = d_ps = d_tm = None
+        if blend is not None:
+            a.blend = blend.data_ptr()
+            d_blend = torch.zeros_like(blend)
+            a.d_blend = d_blend.data_ptr()
+        skip_arr = None
+        if skip is not None:
+            skip_arr = (C.c_uint8 * len(skip))(*[1 if s else 0 for s in skip])
+            a.skip_host = C.cast(skip_arr, C.c_void_p)
+        if patch_scale is not None:
+            a.patch_scale = patch_scale.data_ptr()
+            d_ps = torch.zeros_like(patch_scale)
+            a.d_patch_scale = d_ps.data_ptr()
+        if token_mask is not None:
+            a.token_mask = token_mask.data_ptr()
+            d_tm = torch.empty_like(token_mask)
+            a.d_token_mask = d_tm.data_ptr()
+        a.enable_jumping = 1 if self.enable_jumping else 0
+        ws = self._workspace(B, True)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(lib.uvc_vit_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_backward")
+        grads = [None] * len(plist) if accumulate else list(es.grad_views)
+        return grads, d_blend, d_ps, d_tm
+
+    @property
+    def flat_grad(self):
+        """The flat fp32 gradient arena the backward writes (one all-reduce / one optimiser sweep)."""
+        return self._tables().grad_arena
+
+    # ------------------------------------------------------------------ MAC accounting (reference :115,121,177,182,185,189,460)
+    def _macs(self, B, executed):
+        C_, N = self.embed_dim, self.patch_embed.num_patches + self.num_tokens
+        H = self.blocks[0].attn.num_heads
+        d = C_ // H
+        Fh = self.blocks[0].mlp.fc1.out_features
+        k = self.patch_embed.proj.kernel_size
+        macs_embed = np.prod((B, self.patch_embed.num_patches, C_)) * np.prod(k) * self.patch_embed.proj.in_channels
+        per_block = [B * 3 * C_ * N * C_, N * B * H * N * d, N * B * H * N * d, B * N * C_ * C_, Fh * B * N * C_, C_ * B * N * Fh]
+        return macs_embed, [list(per_block) if e else [] for e in executed]
+
+    # ------------------------------------------------------------------ forward
+    def _block_gates(self):
+        """blend weights [L,2] (d0, d1) per block, or the hard-skip list (reference :477-500)."""
+        L = len(self.blocks)
+        dev = self.block_skip_gating.device
+        if self.enable_block_gating:
+            if self.enable_warmup:
+                return torch.full((L, 2), 0.5, device=dev), None
+            if self.use_gumbel == 1:
+                # one 2-element draw per block, in block order: the reference's RNG consumption
+                rows = [F.gumbel_softmax(self.block_skip_gating[i], tau=0.5, hard=self.gumbel_hard, eps=1e-10, dim=-1) for i in range(L)]
+                return torch.stack(rows).contiguous(), None
+            g1 = self.block_skip_gating[:, 1] ** 2
+            d1 = g1 / (g1 + self.eps)
+            return torch.stack([1 - d1, d1], dim=1).contiguous(), None
+        gate = self.block_skip_gating.detach().tolist()     # one host read: the skip decision shapes the launch sequence
+        return None, [not (g[1] > g[0]) for g in gate]
+
+    def forward_logits(self, x, tau=-1, ratio=0.9):
+        B = x.shape[0]
+        np_ = self.patch_embed.num_patches
+        patch_scale = token_mask = None
+        if self.enable_patch_gating == 1:
+            pg = torch.sigmoid(self.patch_gating).reshape(np_)
+            if self.patch_hard:
+                pg = (pg.detach() >= 0.5).float()
+                pg[0] = 1
+            patch_scale = pg.contiguous()
+        if tau > 0:
+            from .token_gate import token_gate_mask
+            token_mask = token_gate_mask(self, x, patch_scale, tau, int(ratio * np_))
+        blend, skip = self._block_gates()
+        params = [p for _, p in _engine_param_list(self)]
+        logits = _VitFunction.apply(self, x, blend, patch_scale, token_mask, skip, *params)
+        executed = [True] * len(self.blocks) if skip is None else [not s for s in skip]
+        return logits, self._macs(B, executed)
+
+    def forward(self, x, tau=-1, number=0.9):
+        if self.enable_part_gating:
+            raise NotImplementedError("enable_part_gating=1 is outside the sm_100a hot path (no shipped UVC run uses it)")
+        x, macs_list = self.forward_logits(x, tau, number)
+        x_dist = x      # head_dist is None (reference :523-524)
+        if self.training:
+            return (x, x_dist), macs_list
+        return (x + x_dist) / 2, macs_list
+
+
+def _deit(embed_dim, depth, num_heads, **kw):
+    return DistilledVisionTransformer(enable_dist=0, patch_size=16, embed_dim=embed_dim, depth=depth, num_heads=num_heads, mlp_ratio=4,
+                                      qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), drop_rate=0, **kw)
+
+
+def deit_tiny_patch16_224(**kw):
+    return _deit(192, 12, 3, **kw)
+
+
+def deit_small_patch16_224(**kw):
+    return _deit(384, 12, 6, **kw)
+
+
+def deit_base_patch16_224(**kw):
+    return _deit(768, 12, 12, **kw)

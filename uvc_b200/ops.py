@@ -65,3 +65,145 @@ def linear(x, w, bias=None, out=None, **kw):
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
     return gemm(x, w, out, M, N, K, bias=bias, **kw)
+
+
+# ------------------------------------------------------------------------------------------ row-wise ops
+def _p(t):
+    """device pointer of a CUDA fp32 tensor (or None)"""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise _lib.UvcError("uvc_b200 ops take CUDA fp32 tensors (there is no CPU path)")
+    return t.data_ptr()
+
+
+def _call(name, *args):
+    lib = _lib.load()
+    _lib.check(getattr(lib, name)(*args, _stream()), name)
+
+
+def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True):
+    """x:[M,C] rows (row stride ldx) -> y:[M,C], (mean, rstd)."""
+    C_ = gamma.numel()
+    M = x.numel() // C_ if M is None else M
+    ldx = C_ if ldx is None else ldx
+    if y is None:
+        y = torch.empty(M, C_, device=x.device)
+    mean = torch.empty(M, device=x.device) if save_stats else None
+    rstd = torch.empty(M, device=x.device) if save_stats else None
+    _call("uvc_layernorm_fwd", _p(x), ldx, _p(gamma), _p(beta), float(eps), _p(y), C_, _p(mean), _p(rstd), M, C_)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=None, dbeta=None, ldx=None, lddx=None, dx=None):
+    C_ = gamma.numel()
+    M = mean.numel()
+    ldx = C_ if ldx is None else ldx
+    lddx = C_ if lddx is None else lddx
+    if dx is None:
+        dx = torch.empty(M, C_, device=dy.device)
+    _call("uvc_layernorm_bwd", _p(dy), C_, _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), lddx,
+          _p(dgamma), _p(dbeta), M, C_)
+    return dx
+
+
+def softmax_fwd_(S, n):
+    ld = S.shape[-1]
+    _call("uvc_softmax_fwd", _p(S), ld, S.numel() // ld, n)
+    return S
+
+
+def softmax_bwd_(P, dP, n, scale):
+    ld = P.shape[-1]
+    _call("uvc_softmax_bwd", _p(P), _p(dP), ld, P.numel() // ld, n, float(scale))
+    return dP
+
+
+def colsum_(X, out, scale_dev=None):
+    M, N = X.shape
+    _call("uvc_colsum", _p(X), X.stride(0), M, N, _p(scale_dev), _p(out))
+    return out
+
+
+def blend_fwd(t, x, d, out=None):
+    out = torch.empty_like(x) if out is None else out
+    _call("uvc_blend_fwd", _p(t), _p(x), _p(d), _p(out), x.numel())
+    return out
+
+
+def blend_dots_(g, t, x, dots):
+    _call("uvc_blend_dots", _p(g), _p(t), _p(x), _p(dots), x.numel())
+    return dots
+
+
+def im2col16(x, patch=16):
+    B, Cin, HW, _ = x.shape
+    g = HW // patch
+    out = torch.empty(B * g * g, Cin * patch * patch, device=x.device)
+    _call("uvc_im2col16", _p(x), _p(out), B, Cin, HW, patch)
+    return out
+
+
+def assemble_tokens(pe, cls, pos, pscale=None, tmask=None):
+    B, np_, C_ = pe.shape
+    tok = torch.empty(B, np_ + 1, C_, device=pe.device)
+    _call("uvc_assemble_tokens", _p(pe), _p(cls), _p(pos), _p(pscale), _p(tmask), _p(tok), B, np_, C_)
+    return tok
+
+
+def assemble_tokens_bwd(g, pe, pscale=None, tmask=None, want_dpos=True):
+    B, np_, C_ = pe.shape
+    dpe = torch.empty_like(pe)
+    dscale = torch.zeros(np_, device=pe.device) if pscale is not None else None
+    dtmask = torch.empty(B, np_, device=pe.device) if tmask is not None else None
+    dpos = torch.zeros(np_ + 1, C_, device=pe.device) if want_dpos else None
+    dcls = torch.zeros(C_, device=pe.device) if want_dpos else None
+    _call("uvc_assemble_tokens_bwd", _p(g), _p(pe), _p(pscale), _p(tmask), _p(dpe), _p(dscale), _p(dtmask), _p(dpos), _p(dcls), B, np_, C_)
+    return dpe, dscale, dtmask, dpos, dcls
+
+
+def scale_add_(y, x, s=1.0, s_dev=None):
+    _call("uvc_scale_add", _p(y), _p(x), _p(s_dev), float(s), y.numel())
+    return y
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_ldp(N):
+    return int(_lib.load().uvc_attn_ldp(int(N)))
+
+
+def attention_fwd(qkv, B, H, N, d, scale=None):
+    """qkv:[B*N, 3*H*d] -> (ctx:[B*N, H*d], P:[B,H,N,ldp])"""
+    scale = d ** -0.5 if scale is None else scale
+    P = torch.empty(B, H, N, attn_ldp(N), device=qkv.device)
+    ctx = torch.empty(B * N, H * d, device=qkv.device)
+    _call("uvc_attention_fwd", _p(qkv), _p(P), _p(ctx), B, H, N, d, float(scale))
+    return ctx, P
+
+
+def attention_bwd(qkv, P, dctx, B, H, N, d, scale=None):
+    scale = d ** -0.5 if scale is None else scale
+    dP = torch.empty_like(P)
+    dqkv = torch.empty_like(qkv)
+    _call("uvc_attention_bwd", _p(qkv), _p(P), _p(dctx), _p(dP), _p(dqkv), B, H, N, d, float(scale))
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------ loss / optimiser
+def distill_loss(logits, teacher_logits, targets, alpha, T, grad_scale=1.0, want_grad=True):
+    """returns (loss_out[3] = (loss, base, kd), dlogits)"""
+    B, NC = logits.shape
+    out = torch.empty(3, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    _call("uvc_distill_loss", _p(logits), _p(teacher_logits), _p(targets), B, NC, float(alpha), float(T), float(grad_scale), _p(out), _p(dl))
+    return out, dl
+
+
+def sqnorm_accum_(g, acc):
+    _call("uvc_sqnorm_accum", _p(g), g.numel(), _p(acc))
+    return acc
+
+
+def clip_adamw_(p, g, m, v, sqnorm_acc, max_norm, lr, beta1, beta2, eps, weight_decay, step, mask=None):
+    _call("uvc_clip_adamw", _p(p), _p(g), _p(m), _p(v), _p(mask), p.numel(), _p(sqnorm_acc), float(max_norm), float(lr),
+          float(beta1), float(beta2), float(eps), float(weight_decay), int(step))
