@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the UVC hot path: images/sec of the Stage-1 (joint_train) step, DeiT-Small, 50 % FLOPs budget.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one full iteration of the reference's hot loop (joint_train.py:395-450) through this repo's public API
+(`uvc_b200.joint_train.Stage1Step`): mixup -> student forward (soft Gumbel block gates, patch gate) -> dense teacher forward
++ soft-target CE + soft KD loss -> backward -> (N>1: flat NCCL all-reduce) -> global-norm clip + AdamW -> LR schedule ->
+ADMM primal-dual update (`uvc_optimizer`, non-warm-up) -> zero_grad.  Workload: BASELINE.json configs[2] at its per-GPU size
+(DeiT-Small patch16 224, 128 images per GPU, weak scaling), synthetic 224x224 batch, random-init weights, seed 730.
+
+Prints ONE JSON line (rank 0).  `value`: device-resident inputs.  `e2e`: the same step fed from pinned HOST memory each step
+(H2D copy on a side stream, double-buffered, inside the timed region) with the loss / ADMM results read back each step.
+`roofline`: the dominant kernel (the tcgen05 TF32 GEMM), per-launch CUDA-event timing of every GEMM launch of instrumented
+steps run right after the timed region (uvc_gemm_profile).  `cpu_baseline` / `--impl reference`: the oracle port (plain
+PyTorch CPU restatement of the same step, oracle/) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "deit_small_patch16_224"
+PER_GPU_BATCH = 128
+DENSE_FWD_FLOPS = {"deit_tiny_patch16_224": 2.507e9, "deit_small_patch16_224": 9.198e9, "deit_base_patch16_224": 35.128e9}
+
+
+def uvc_args_namespace(H, **over):
+    """flags of run_uvc_train.sh (the shipped Stage-1 recipe) that the step reads"""
+    a = types.SimpleNamespace(
+        head_size=64, num_heads=H, flops_with_mhsa=1, use_gumbel=1, enable_block_gating=1, enable_part_gating=0, enable_patch_gating=1,
+        enable_jumping=0, enable_pruning=1, eps=0.1, eps_decay=0.92, enable_warmup=0, soptim="sgd", roptim="sgd", slr=0.02, rlr=0.02,
+        glr=0.1, ylr=1e-4, plr=1e-4, zlr_schedule_list=[1, 5, 9, 13, 17], budget=0.5, sl2wd=0.0, gating_weight=5e-4, z_grad_clip=0.5,
+        gating_interval=50, patch_ratio=0.9, uvc_train=True, max_grad_norm=1.0, learning_rate=1e-4, weight_decay=0.05,
+        distillation_alpha=0.1, distillation_tau=1.0, smoothing=0.1, mixup=0.8, cutmix=1.0, mixup_prob=0.8, mixup_switch_prob=0.5)
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"bf16_sustained": float(p["bf16_tflops_sustained"]), "bf16_burst": float(p["bf16_tflops"]), "hbm": float(p["hbm_gbs"]), "src": "measured"}
+    except Exception:
+        return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ the GPU arm
+def build_gpu_step(device, world, B):
+    import torch
+    from functools import partial
+    from uvc_b200.joint_train import Stage1Step, get_uvc_layers, make_optimizer
+    from uvc_b200.models import CONFIGS, DistilledVisionTransformer
+    from uvc_b200.utils.ddp import DistributedDataParallel as DDP
+    from uvc_b200.utils.losses import DistillationLoss
+    from uvc_b200.utils.mixup import Mixup, SoftTargetCrossEntropy
+    from uvc_b200.utils.scheduler import WarmupCosineSchedule
+    from uvc_b200.uvc_optimizer import build_minimax_model
+    from uvc_b200.uvc_utils import prune_w_mask
+    cfg = CONFIGS[MODEL]
+    args = uvc_args_namespace(cfg.num_heads, device=device, local_rank=0 if world > 1 else -1)
+
+    def make(gumbel_hard):
+        return DistilledVisionTransformer(enable_dist=0, patch_size=16, embed_dim=cfg.embed_dim, depth=cfg.depth, num_heads=cfg.num_heads, mlp_ratio=4,
+                                          qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), drop_rate=0, gumbel_hard=gumbel_hard)
+    torch.manual_seed(730)
+    model = make(False).to(device)
+    teacher = make(True).to(device).eval()
+    teacher.load_state_dict(model.state_dict(), strict=False)        # teacher = copy of the initial student (no checkpoints offline)
+    for _, m in model.named_modules():
+        if hasattr(m, "weight"):
+            m.register_buffer("mask", torch.ones_like(m.weight))
+    layer_names, uvc_layers, uvc_dict = get_uvc_layers(model)
+    model.eval()
+    with torch.no_grad():
+        _, flops_list = model(torch.ones(1, 3, 224, 224, device=device))
+    uvc = list(build_minimax_model(model, layer_names, uvc_layers, uvc_dict, args, flops_list))
+    mm = uvc[0]
+    with torch.no_grad():           # mid-training ADMM state: the selections / prox / dual updates all do real work
+        mm.s[:, 0] = 1.3; mm.s[:, 1] = 400.5; mm.r.fill_(9.2)
+    prune_w_mask(mm, None)
+    model.train()
+    model.enable_warmup = 0
+    model.block_skip_gating.requires_grad = True
+    model.flatten_parameters()
+    optimizer = make_optimizer(args, model, args.learning_rate, args.weight_decay)
+    scheduler = WarmupCosineSchedule(optimizer, warmup_steps=500, t_total=100000)
+    ddp = DDP(model, gradient_predivide_factor=world, delay_allreduce=True) if world > 1 else model
+    mixup = Mixup(mixup_alpha=args.mixup, cutmix_alpha=args.cutmix, prob=args.mixup_prob, switch_prob=args.mixup_switch_prob,
+                  label_smoothing=args.smoothing, num_classes=1000)
+    crit = DistillationLoss(SoftTargetCrossEntropy(), teacher, "soft", args.distillation_alpha, args.distillation_tau)
+    step = Stage1Step(args, model, ddp, optimizer, scheduler, crit, mixup, uvc)
+    return step, model
+
+
+def run_gpu(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from uvc_b200 import _lib
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+    np.random.seed(730)
+    B = PER_GPU_BATCH
+    step, model = build_gpu_step(device, world, B)
+    g = torch.Generator().manual_seed(730 + rank)
+    x_host = [torch.randn(B, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
+    y_host = [torch.randint(0, 1000, (B,), generator=g).pin_memory() for _ in range(2)]
+    x_dev, y_dev = x_host[0].to(device), y_host[0].to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm (inputs already in HBM; the step's own 77 MB clone + mixup happen inside)
+    def dev_step(i):
+        step(x_dev.clone(), y_dev)
+    for i in range(a.warmup):
+        dev_step(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = lib.uvc_launch_count()
+    ms = timed(dev_step, a.steps)
+    launches = int(lib.uvc_launch_count() - n0)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- end-to-end arm: pinned host -> device every step (double-buffered on a copy stream), results read back every step
+    copy_stream = torch.cuda.Stream(device)
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h = [0]
+
+    done = [None, None]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            if done[i % 2] is not None:
+                copy_stream.wait_event(done[i % 2])        # the step that last consumed this buffer has finished
+            bx, by = bufs[i % 2]
+            bx.copy_(x_host[i % 2], non_blocking=True); by.copy_(y_host[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_step(i):
+        if i == 0:
+            prefetch(0)
+        prefetch(i + 1)                         # next batch's H2D copy overlaps this step's compute
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[i % 2])
+        bx, by = bufs[i % 2]
+        out = step(bx, by)                      # consumes bx in place (mixup)
+        done[i % 2] = torch.cuda.Event(); done[i % 2].record(cur)
+        loss = float(out["loss"].item())        # device -> host read of the step's result (the ADMM state came back inside step())
+        d2h[0] = 4 + 4 * (1 + out["s"].size + out["r"].size + (out["gating"].size if out["gating"] is not None else 0))
+        return loss
+    for i in range(min(3, a.warmup)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, a.steps)
+
+    # ---- roofline leg: every GEMM launch of 2 instrumented steps timed with a CUDA-event pair on the launching stream
+    lib.uvc_gemm_profile(1)
+    for i in range(2):
+        dev_step(i)
+    torch.cuda.synchronize()
+    import ctypes
+    t_ms, t_fl, n_l = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.uvc_gemm_profile_read(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(n_l))
+    lib.uvc_gemm_profile(0)
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    imgs = B * world * a.steps
+    value = imgs / (ms / 1e3)
+    step_flops = 4 * DENSE_FWD_FLOPS[MODEL] * B          # student fwd + bwd (2x) + dense teacher fwd, reference MAC accounting
+    gemm_tflops = (t_fl.value / max(t_ms.value, 1e-9)) / 1e9
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    out = {
+        "metric": "images/sec DeiT-Small UVC@50%FLOPs (Stage-1 joint_train step)", "value": round(value, 1), "unit": "images/sec",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[2] at per-GPU size: DeiT-Small patch16 224 UVC joint_train (ADMM active), budget 0.5, "
+                               "soft-distill alpha=0.1, 128 images/GPU, DDP over N GPUs", "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush"},
+        "clocks": clk,
+        "e2e": {"value": round(imgs / (ms_e2e / 1e3), 1), "unit": "images/sec", "ms_per_step": round(ms_e2e / a.steps, 3),
+                "h2d_bytes_per_step": int(x_host[0].numel() * 4 + y_host[0].numel() * 8), "d2h_bytes_per_step": int(d2h[0])},
+        "gpu_launches": launches,
+        "step_tflops_per_gpu": round(step_flops / (ms / a.steps / 1e3) / 1e12, 1),
+        "roofline": {"bound": "tensor", "kernel": "uvc::gemm_tf32_kernel (tcgen05.mma kind::tf32)", "achieved": round(gemm_tflops, 1),
+                     "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_tflops / tf32_peak, 3), "traffic": None,
+                     "peak_source": f"TF32 dense = 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}); bf16 sustained {peaks['bf16_sustained']}",
+                     "launches_per_step": int(n_l.value // 2), "gemm_ms_per_step": round(t_ms.value / 2, 3),
+                     "how": "CUDA-event pair around every GEMM launch of 2 instrumented steps run right after the timed region",
+                     "step_frac_of_tf32_peak": round(step_flops / (ms / a.steps / 1e3) / 1e12 / tf32_peak, 3)},
+    }
+    out["cpu_baseline"] = run_cpu_sample(steps=2, warmup=1) if world == 1 and not a.no_cpu_baseline else None
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ the CPU (reference) arm
+def build_cpu_step(B):
+    """The same Stage-1 step as the oracle states it: plain PyTorch fp32 on the host cores (oracle/vit_oracle.py,
+    oracle/admm_oracle.py).  TEST/BASELINE infrastructure: this is the thing being compared against, never shipped."""
+    import numpy as np
+    import torch
+    from oracle import admm_oracle as ao, fixtures as fx, vit_oracle as vo
+    dims = fx.MODEL_DIMS[MODEL]
+    C, H, L = dims["embed_dim"], dims["num_heads"], dims["depth"]
+    sd, _ = fx.make_state_dict(MODEL, None, seed=730)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    teacher = {k: v.clone() for k, v in sd.items()}
+    patch_gating = (3 * torch.ones(196)).requires_grad_(True)
+    names = [k for k in params if k not in ("gumbel.weight", "gumbel.bias") and "attn_skip" not in k and "mlp_skip" not in k]
+    ms = {k: torch.zeros_like(params[k]) for k in names}; vs = {k: torch.zeros_like(params[k]) for k in names}
+    st = dict(s=torch.stack([torch.full((L,), 1.3), torch.full((L,), 400.5)], 1), r=torch.full((L, H), 9.2), y=torch.full((L, 2), 1e-3),
+              p=torch.full((L, H), 1e-3), z=torch.tensor(1e-3), gate=params["block_skip_gating"], gate_buf=[])
+    macs = torch.tensor([vo.block_macs(1, 197, C, H, 4 * C)] * L, dtype=torch.float32)
+    embed = 196 * C * 768
+    hp = dict(lr=1e-4, slr=0.02, rlr=0.02, ylr=1e-4, plr=1e-4, zlr=1.0, budget=0.5, z_grad_clip=0.5, sl2wd=0.0, gating_weight=5e-4, d=64, Fh=4 * C,
+              macs=macs, embed_macs=embed, full=float((embed + macs.sum()) * 2), use_gumbel=True, eps=0.1, gating_interval=50, global_step=0)
+    x0, y0 = fx.make_batch(B, seed=730)
+    state = {"step": 0}
+
+    def step():
+        x = x0.clone()
+        lam = float(np.random.beta(0.8, 0.8))
+        x = x * lam + x.flip(0) * (1 - lam)
+        tgt = vo.mixup_target(y0, 1000, lam, 0.1)
+        blend = torch.stack([torch.nn.functional.gumbel_softmax(params["block_skip_gating"][i], tau=0.5, hard=False, eps=1e-10, dim=-1) for i in range(L)])
+        logits = vo.forward(params, x, L, H, blend=blend, patch_scale=torch.sigmoid(patch_gating))
+        with torch.no_grad():
+            t_logits = vo.forward(teacher, x, L, H, skip=[False] * L)
+        loss, _, _ = vo.distillation_loss(logits, t_logits, tgt, 0.1, 1.0)
+        for p in params.values():
+            p.grad = None
+        loss.backward()
+        state["step"] += 1
+        with torch.no_grad():
+            vo.clip_adamw_step([params[k] for k in names], [params[k].grad for k in names], [ms[k] for k in names], [vs[k] for k in names],
+                               state["step"], 1e-4)
+            W1 = [params[f"blocks.{i}.attn.proj.weight"] for i in range(L)]
+            W3 = [params[f"blocks.{i}.mlp.fc2.weight"] for i in range(L)]
+            n1, n2 = [-torch.empty(L, 2).exponential_().log() for _ in range(2)]
+            hp["global_step"] = state["step"]
+            ao.step(st, W1, W3, hp, n1, n2, gate_grad=params["block_skip_gating"].grad, gate_sgd=lambda g: None)
+        return float(loss)
+    return step
+
+
+def run_cpu_sample(steps, warmup, B=16):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = build_cpu_step(B)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(B * steps / dt, 2), "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"{steps} full Stage-1 steps (student fwd+bwd, dense teacher fwd, CE+KD loss, clip+AdamW, ADMM step) of DeiT-Small at batch {B} "
+                      f"through the oracle port (plain PyTorch fp32, {cores} threads) after {warmup} warm-up"}
+
+
+def run_reference(a):
+    """`--impl reference`: the reference's CPU path = the oracle port (the reference itself is Python that cannot travel to the
+    GPU box; oracle/ is pinned to it bit-for-bit by tests/test_oracle.py and oracle/gen_golden*.py).  Rank 0 only."""
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    steps, warm = max(1, min(a.steps, 3)), max(1, min(a.warmup, 1))
+    cb = run_cpu_sample(steps, warm)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    out = {"impl": "reference", "metric": "images/sec DeiT-Small UVC@50%FLOPs (Stage-1 joint_train step)", "value": cb["value"], "unit": "images/sec",
+           "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": round(16 / cb["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE.json configs[2] step on the host CPU: bounded sample of 16 images per step (same step, same model)"},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="uvc_b200", choices=["uvc_b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    if a.impl == "reference":
+        return run_reference(a)
+    run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

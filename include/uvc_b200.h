@@ -45,6 +45,12 @@ typedef enum {
 UVC_API int uvc_version(void);                 /* ABI version, bumped on any signature change */
 UVC_API const char* uvc_last_error(void);      /* thread-local text of the last failure */
 UVC_API int uvc_abi_sizeof(const char* struct_name);   /* sizeof() of an ABI struct, for binding self-checks */
+UVC_API long long uvc_launch_count(void);      /* kernels this library has launched so far in this process */
+/* Optional timing of every uvc GEMM launch with a CUDA-event pair on the launching stream (bench.py's roofline leg).
+ * uvc_gemm_profile(1) clears the records and starts recording, (0) stops; _read synchronises the recorded events and
+ * returns the summed kernel time, the summed algorithmic FLOPs (2*M*N*K*batch) and the number of launches. */
+UVC_API int uvc_gemm_profile(int enable);
+UVC_API int uvc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Batched TF32 tensor-core GEMM (tcgen05.mma + TMEM accumulator + TMA operand staging)
@@ -72,7 +78,9 @@ enum {
   UVC_EPI_GELU = 2,        /* aux[row,col] = v (pre-activation, if aux != NULL); v = gelu_erf(v) */
   UVC_EPI_GELU_BWD = 4,    /* v *= gelu'(aux[row,col]) */
   UVC_EPI_RESIDUAL = 8,    /* v += beta * R[row,col] */
-  UVC_EPI_ATOMIC = 16      /* D += v with red.global.add (required when splits > 1) */
+  UVC_EPI_ATOMIC = 16,     /* D += v with red.global.add (required when splits > 1) */
+  UVC_EPI_ROUND_TF32 = 32  /* round v to nearest TF32 before the store: for outputs that only feed other GEMMs (the
+                              tensor core truncates its inputs, rounding here keeps the error unbiased) */
 };
 
 typedef struct {
@@ -97,22 +105,23 @@ UVC_API int uvc_gemm_tf32(const uvc_gemm_args* args, void* stream);
 /* ------------------------------------------------------------------------------------------
  * Row-wise bandwidth-bound kernels (warp per row, float4 accesses).  `ld*` are row strides in
  * elements (multiples of 4).  Every function is asynchronous on `stream`.
+ * `round_tf32` != 0 rounds the output to the nearest TF32 value (use it when the output only feeds tensor-core GEMMs).
  */
 
 /* y = (x - mean) * rstd * gamma + beta per row; mean/rstd (optional) are saved for the backward.
  * Replaces nn.LayerNorm at models/model_distilled.py:199,204,288,507 (eps 1e-6) and
  * T2TViT/models/transformer_block.py:84,88 (eps 1e-5). */
 UVC_API int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps,
-                              float* y, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t C, void* stream);
+                              float* y, int64_t ldy, float* mean, float* rstd, int32_t M, int32_t C, int32_t round_tf32, void* stream);
 /* dx = r1 + s2 * r2 + LN'(dy); dgamma += sum dy*xhat; dbeta += sum dy.  r1, r2 (same ld as dx), s2_dev,
  * dgamma/dbeta may be NULL.  The two residual inputs fuse the skip connection and the block-gate blend. */
 UVC_API int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                               const float* gamma, const float* r1, const float* r2, const float* s2_dev,
                               float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
 /* in-place row softmax over the first n (<= 256) columns of S[rows][ld] (models/model_distilled.py:180) */
-UVC_API int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, void* stream);
+UVC_API int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream);
 /* dP <- scale * P .* (dP - rowsum(dP .* P)) */
-UVC_API int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, void* stream);
+UVC_API int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, int32_t round_tf32, void* stream);
 /* out[col] += scale * sum_rows X[row, col]  (bias gradients); scale_dev may be NULL (= 1) */
 UVC_API int uvc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, const float* scale_dev, float* out, void* stream);
 /* out = d[1] * t + d[0] * x   -- block gate blend, models/model_distilled.py:493 */
@@ -120,7 +129,7 @@ UVC_API int uvc_blend_fwd(const float* t, const float* x, const float* d, float*
 /* dots[0] += <g, x>, dots[1] += <g, t>  -- gradient of the blend weights */
 UVC_API int uvc_blend_dots(const float* g, const float* t, const float* x, float* dots, int64_t n, void* stream);
 /* im2col of the patch x patch / stride patch conv: out[(b, py, px), (c, ky, kx)]  (models/model_distilled.py:149) */
-UVC_API int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, void* stream);
+UVC_API int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, int32_t round_tf32, void* stream);
 /* tok[b,0,:] = cls + pos[0]; tok[b,1+p,:] = pe[b,p,:] * pscale[p] * tmask[b,p] + pos[1+p]
  * (models/model_distilled.py:434-471; pscale / tmask may be NULL) */
 UVC_API int uvc_assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask,
@@ -128,6 +137,8 @@ UVC_API int uvc_assemble_tokens(const float* pe, const float* cls, const float* 
 /* backward of uvc_assemble_tokens: dpe = g * scale; dscale[p] += ..., dtmask[b,p] = ..., dpos += sum_b g, dcls += sum_b g[:,0] */
 UVC_API int uvc_assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe,
                                     float* dscale, float* dtmask, float* dpos, float* dcls, int32_t B, int32_t np, int32_t C, void* stream);
+/* dst[i] = round_to_nearest_tf32(src[i])  (weights are rounded once per forward into the workspace) */
+UVC_API int uvc_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 /* y += s * (*s_dev) * x */
 UVC_API int uvc_scale_add(float* y, const float* x, const float* s_dev, float s, int64_t n, void* stream);
 
@@ -223,6 +234,41 @@ typedef struct {
 UVC_API uint64_t uvc_vit_workspace_bytes(const uvc_vit_dims* dims, int32_t save_for_backward);
 UVC_API int uvc_vit_forward(const uvc_vit_forward_args* args, void* stream);
 UVC_API int uvc_vit_backward(const uvc_vit_backward_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ADMM primal-dual update (uvc_optimizer.py:37-144 + uvc_utils.py:54-73,177-269,315-471) on the device.
+ * One argument block for all six entry points; each reads the fields it needs.
+ *   W1[l] = blocks[l].attn.proj.weight [C, C] (prunable input columns, grouped in H heads of d),
+ *   W3[l] = blocks[l].mlp.fc2.weight  [C, Fh] (prunable input columns), W2[l] = mlp.fc1.weight [Fh, C] (rows follow W3).
+ * Call order of one step (uvc_optimizer):  scores -> prox -> scores -> primal -> [host: gate SGD every
+ * `gating_interval` steps] -> dual.  A "k smallest" selection is rank < k (ties: lower index first).
+ */
+typedef struct {
+  int32_t L, H, d, Fh;                 /* C = H * d */
+  float* const* w1; float* const* w3;  /* HOST arrays [L] of device pointers to the weights */
+  float* const* m1; float* const* m3; float* const* m2;   /* HOST arrays [L] of device pointers to the .mask buffers (uvc_admm_masks) */
+  float *c1, *c2, *c3;                 /* device workspace: [L,C] column norms, [L,H] head norms, [L,Fh] neuron norms */
+  int32_t *rank1, *rank2, *rank3;      /* device workspace: rank inside head [L,C], across heads [L,H], across neurons [L,Fh] */
+  float *s, *r, *y, *p, *z;            /* ADMM variables: [L,2], [L,H], [L,2], [L,H], [1] */
+  const float* gate;                   /* block_skip_gating [L,2] or NULL */
+  const float* gate_grad;              /* its task-loss gradient [L,2] or NULL */
+  const float* noise;                  /* Gumbel noise [L,2] for this evaluation of the resource model (use_gumbel) */
+  const float* macs;                   /* [L,6] per-block MACs at batch 1, as fp32 (joint_train.py:1010-1012) */
+  double embed_macs, full_flops;       /* patch-embed MACs; dense model FLOPs (resource_ub, uvc_optimizer.py:178-188) */
+  double lr;                           /* prox: the weight optimiser's current learning rate */
+  float budget, z_grad_clip, slr, rlr, ylr, plr, zlr, sl2wd, gating_weight, eps;
+  int32_t use_gumbel, gumbel_hard, warmup;
+  float gate_mult;                     /* (global_step % gating_interval): weight of this step in the gate-gradient buffer */
+  float* gate_grad_acc;                /* [L,2] running sum of the weighted gate gradients, or NULL */
+  float* out;                          /* [1]: resource (FLOPs fraction of the dense model) of this evaluation */
+} uvc_admm_args;
+
+UVC_API int uvc_admm_scores(const uvc_admm_args* args, void* stream);    /* uvc_utils.py:54-73 for every layer + ranks */
+UVC_API int uvc_admm_prox(const uvc_admm_args* args, void* stream);      /* uvc_utils.py:315-345 */
+UVC_API int uvc_admm_masks(const uvc_admm_args* args, void* stream);     /* uvc_utils.py:376-401 */
+UVC_API int uvc_admm_primal(const uvc_admm_args* args, void* stream);    /* uvc_optimizer.py:46-123 */
+UVC_API int uvc_admm_dual(const uvc_admm_args* args, void* stream);      /* uvc_optimizer.py:126-135 */
+UVC_API int uvc_admm_resource(const uvc_admm_args* args, void* stream);  /* uvc_utils.py:409-471 */
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,11 @@ m.enable_block_gating, m.enable_warmup = 1, 1
 x = torch.randn(B, 3, 224, 224, device="cuda")
 
 
-def timeit(fn, n=10, w=3):
+N_IT, W_IT = int(os.environ.get('PROBE_N', 10)), int(os.environ.get('PROBE_W', 3))
+
+
+def timeit(fn, n=None, w=None):
+    n = N_IT if n is None else n; w = W_IT if w is None else w
     for _ in range(w): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -38,7 +38,7 @@ def test_errors_do_not_cross_the_boundary():
     assert rc == -2 and b"NULL" in lib.uvc_last_error()
     d = _lib.VitDims()          # all zero -> bad shape, reported through the return value of the size query
     assert lib.uvc_vit_workspace_bytes(ctypes.byref(d), 1) == 0
-    assert lib.uvc_layernorm_fwd(None, 0, None, None, 1e-6, None, 0, None, None, 1, 4, None) == -2
+    assert lib.uvc_layernorm_fwd(None, 0, None, None, 1e-6, None, 0, None, None, 1, 4, 0, None) == -2
 
 
 def test_workspace_size_query_runs_on_cpu():
@@ -54,7 +54,6 @@ def test_no_cpu_fallback():
     import pytest
     import torch
     from uvc_b200.models import deit_tiny_patch16_224
-    m = deit_tiny_patch16_224(depth=1) if False else None
     from uvc_b200.models.model_distilled import DistilledVisionTransformer
     from functools import partial
     m = DistilledVisionTransformer(enable_dist=0, patch_size=16, embed_dim=192, depth=1, num_heads=3, mlp_ratio=4, qkv_bias=True,

@@ -93,16 +93,18 @@ def test_train_step_loss_and_gradients_match_reference_golden(golden_dir):
     lo = vo.forward(sdr, x, sp["depth"], dims["num_heads"], blend=br)
     loss, _, _ = vo.distillation_loss(lo, g["teacher_logits"], tgt.cpu(), sp["alpha"], sp["T"])
     loss.backward()
-    worst = 0.0
+    worst, bad = 0.0, []
     for k, p in m.named_parameters():
         if p.grad is None:
             assert sdr[k].grad is None or k in ("block_skip_gating",) or float(sdr[k].grad.abs().max()) == 0.0, k
             continue
         e = rel(p.grad, sdr[k].grad)
         worst = max(worst, e)
-        assert e < GRAD_TOL, (k, e)
+        if not e < GRAD_TOL:
+            bad.append((k, e, float(p.grad.abs().max()), float(sdr[k].grad.abs().max())))
         if k in g["grads_full"]:
-            assert rel(p.grad, g["grads_full"][k]) < GRAD_TOL, k
+            assert rel(sdr[k].grad, g["grads_full"][k]) < 1e-4, k        # oracle on this box == reference golden
+    assert not bad, bad
     assert rel(blend.grad, br.grad) < GRAD_TOL
     print(f"train step: worst gradient rel err {worst:.3e}")
     # gradient norm as the reference's clip_grad_norm_ would see it (gate gradient excluded: it needs the Gumbel draw)
@@ -118,6 +120,7 @@ def test_backward_accumulates_like_autograd():
     x = x.cuda()
     (o, _), _ = m(x); o.square().mean().backward()
     g1 = m.blocks[0].mlp.fc1.weight.grad.clone()
+    assert float(g1.abs().max()) > 0
     (o, _), _ = m(x); o.square().mean().backward()          # second backward without zero_grad: gradients add up
     assert rel(m.blocks[0].mlp.fc1.weight.grad, 2 * g1) < 1e-3
     m.zero_grad(set_to_none=True)

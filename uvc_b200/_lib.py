@@ -63,7 +63,21 @@ class VitBackwardArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
 
 
-_ABI_STRUCTS = {"uvc_operand": Operand, "uvc_gemm_args": GemmArgs, "uvc_block_tensors": BlockTensors,
+class AdmmArgs(C.Structure):
+    _PP = C.POINTER(C.c_void_p)
+    _fields_ = [("L", C.c_int32), ("H", C.c_int32), ("d", C.c_int32), ("Fh", C.c_int32),
+                ("w1", _PP), ("w3", _PP), ("m1", _PP), ("m3", _PP), ("m2", _PP),
+                ("c1", _F), ("c2", _F), ("c3", _F), ("rank1", _F), ("rank2", _F), ("rank3", _F),
+                ("s", _F), ("r", _F), ("y", _F), ("p", _F), ("z", _F),
+                ("gate", _F), ("gate_grad", _F), ("noise", _F), ("macs", _F),
+                ("embed_macs", C.c_double), ("full_flops", C.c_double), ("lr", C.c_double),
+                ("budget", C.c_float), ("z_grad_clip", C.c_float), ("slr", C.c_float), ("rlr", C.c_float), ("ylr", C.c_float),
+                ("plr", C.c_float), ("zlr", C.c_float), ("sl2wd", C.c_float), ("gating_weight", C.c_float), ("eps", C.c_float),
+                ("use_gumbel", C.c_int32), ("gumbel_hard", C.c_int32), ("warmup", C.c_int32), ("gate_mult", C.c_float),
+                ("gate_grad_acc", _F), ("out", _F)]
+
+
+_ABI_STRUCTS = {"uvc_admm_args": AdmmArgs, "uvc_operand": Operand, "uvc_gemm_args": GemmArgs, "uvc_block_tensors": BlockTensors,
                 "uvc_vit_tensors": VitTensors, "uvc_vit_dims": VitDims, "uvc_vit_forward_args": VitForwardArgs,
                 "uvc_vit_backward_args": VitBackwardArgs}
 
@@ -71,14 +85,15 @@ UVC_MAX_DEPTH = 32
 
 # every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_gemm_tf32",
+    "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_tf32",
     "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
-    "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_scale_add",
+    "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
     "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
+    "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
-EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32 = 1, 2, 4, 8, 16, 32
 
 _lib = None
 
@@ -114,14 +129,15 @@ def load():
     i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
     protos = {
         "uvc_gemm_tf32": [C.POINTER(GemmArgs), vp],
-        "uvc_layernorm_fwd": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, vp],
+        "uvc_layernorm_fwd": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, i32, vp],
         "uvc_layernorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp],
-        "uvc_softmax_fwd": [vp, i64, i64, i32, vp],
-        "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, vp],
+        "uvc_softmax_fwd": [vp, i64, i64, i32, i32, vp],
+        "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, i32, vp],
         "uvc_colsum": [vp, i64, i32, i32, vp, vp, vp],
         "uvc_blend_fwd": [vp, vp, vp, vp, i64, vp],
         "uvc_blend_dots": [vp, vp, vp, vp, i64, vp],
-        "uvc_im2col16": [vp, vp, i32, i32, i32, i32, vp],
+        "uvc_im2col16": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "uvc_round_tf32": [vp, vp, i64, vp],
         "uvc_assemble_tokens": [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "uvc_assemble_tokens_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp],
         "uvc_scale_add": [vp, vp, vp, f32, i64, vp],
@@ -133,10 +149,16 @@ def load():
         "uvc_vit_forward": [C.POINTER(VitForwardArgs), vp],
         "uvc_vit_backward": [C.POINTER(VitBackwardArgs), vp],
     }
+    for name in ("scores", "prox", "masks", "primal", "dual", "resource"):
+        protos["uvc_admm_" + name] = [C.POINTER(AdmmArgs), vp]
     for name, argtypes in protos.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.uvc_launch_count.argtypes = []; lib.uvc_launch_count.restype = C.c_longlong
+    lib.uvc_gemm_profile.argtypes = [C.c_int]; lib.uvc_gemm_profile.restype = C.c_int
+    lib.uvc_gemm_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.uvc_gemm_profile_read.restype = C.c_int
     lib.uvc_attn_ldp.argtypes = [i32]; lib.uvc_attn_ldp.restype = i32
     lib.uvc_vit_workspace_bytes.argtypes = [C.POINTER(VitDims), i32]; lib.uvc_vit_workspace_bytes.restype = C.c_uint64
     _lib = lib

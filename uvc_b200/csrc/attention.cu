@@ -27,10 +27,11 @@ int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, i
   uvc_gemm_args a = gemm_args(N, N, d, op_k(q, ld3, d, (long long)N * ld3), op_k(k, ld3, d, (long long)N * ld3), P, ldp);
   a.nb1 = H; a.nb2 = B; a.d_bs1 = (long long)N * ldp; a.d_bs2 = (long long)H * N * ldp; a.alpha = scale;
   if ((rc = gemm_tf32(a, st))) return rc;
-  if ((rc = softmax_fwd(P, ldp, (long long)B * H * N, N, st))) return rc;
+  if ((rc = softmax_fwd(P, ldp, (long long)B * H * N, N, st, 1))) return rc;     // P only feeds GEMMs: rounded to TF32
   // ctx[b, :, h*d:(h+1)*d] = P[b,h] V[b,h]        (V is [k=N rows][n=d cols] in memory -> MN-major B operand)
   uvc_gemm_args c = gemm_args(N, d, N, op_k(P, ldp, (long long)N * ldp, (long long)H * N * ldp), op_mn(v, ld3, d, (long long)N * ld3), ctx, C);
   c.nb1 = H; c.nb2 = B; c.d_bs1 = d; c.d_bs2 = (long long)N * C;
+  c.flags = UVC_EPI_ROUND_TF32;
   return gemm_tf32(c, st);
 }
 
@@ -48,17 +49,17 @@ int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP
   if ((rc = gemm_tf32(a, st))) return rc;
   // dV = P^T dctx    (A = P^T: memory rows index K -> MN-major; B = dctx^T likewise)
   uvc_gemm_args b = gemm_args(N, d, N, op_mn(P, ldp, pb1, pb2), op_mn(dctx, C, d, cb2), dv, ld3);
-  b.nb1 = H; b.nb2 = B; b.d_bs1 = d; b.d_bs2 = qb2;
+  b.nb1 = H; b.nb2 = B; b.d_bs1 = d; b.d_bs2 = qb2; b.flags = UVC_EPI_ROUND_TF32;
   if ((rc = gemm_tf32(b, st))) return rc;
   // dS = scale * P .* (dP - rowsum(dP .* P))
-  if ((rc = softmax_bwd(P, dP, ldp, (long long)B * H * N, N, scale, st))) return rc;
+  if ((rc = softmax_bwd(P, dP, ldp, (long long)B * H * N, N, scale, st, 1))) return rc;
   // dQ = dS K
   uvc_gemm_args c = gemm_args(N, d, N, op_k(dP, ldp, pb1, pb2), op_mn(k, ld3, d, qb2), dq, ld3);
-  c.nb1 = H; c.nb2 = B; c.d_bs1 = d; c.d_bs2 = qb2;
+  c.nb1 = H; c.nb2 = B; c.d_bs1 = d; c.d_bs2 = qb2; c.flags = UVC_EPI_ROUND_TF32;
   if ((rc = gemm_tf32(c, st))) return rc;
   // dK = dS^T Q
   uvc_gemm_args e = gemm_args(N, d, N, op_mn(dP, ldp, pb1, pb2), op_mn(q, ld3, d, qb2), dk, ld3);
-  e.nb1 = H; e.nb2 = B; e.d_bs1 = d; e.d_bs2 = qb2;
+  e.nb1 = H; e.nb2 = B; e.d_bs1 = d; e.d_bs2 = qb2; e.flags = UVC_EPI_ROUND_TF32;
   return gemm_tf32(e, st);
 }
 

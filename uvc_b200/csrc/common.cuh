@@ -12,7 +12,11 @@ namespace uvc {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);   // cudaGetLastError -> UVC_ERR_CUDA
+int check_launch(const char* what);   // counts the launch; cudaGetLastError -> UVC_ERR_CUDA
+long long launch_count();
+bool prof_enabled();
+void prof_begin(cudaStream_t st, double flops);
+void prof_end(cudaStream_t st);
 
 #define UVC_REQUIRE(cond, code, ...)                                   \
   do { if (!(cond)) { ::uvc::set_error(__VA_ARGS__); return (code); } } while (0)
@@ -35,6 +39,14 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
+}
+// round-to-nearest fp32 -> TF32 (10-bit mantissa kept in an fp32 container).  tcgen05.mma kind::tf32 TRUNCATES
+// the low 13 mantissa bits of whatever it reads, which is a biased error (-2^-11 relative on average per
+// operand); every tensor that is only ever a GEMM operand is therefore rounded here by its producer.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
 }
 // exact (erf) GELU, as torch.nn.GELU() default
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -221,6 +221,10 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
             for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] += beta * Rrow[col0 + j];
           }
         }
+        if (flags & UVC_EPI_ROUND_TF32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
         if (flags & UVC_EPI_ATOMIC) {
           if (full && vec_ok) {
 #pragma unroll
@@ -311,6 +315,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   UVC_REQUIRE(a.D != nullptr, UVC_ERR_BAD_ARG, "gemm: D is NULL");
   UVC_REQUIRE(a.splits == 1 || (a.flags & UVC_EPI_ATOMIC), UVC_ERR_BAD_ARG, "gemm: splits > 1 requires UVC_EPI_ATOMIC");
   UVC_REQUIRE(!(a.flags & UVC_EPI_ATOMIC) || !(a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)), UVC_ERR_BAD_ARG, "gemm: GELU epilogues cannot be combined with split-K accumulation");
+  UVC_REQUIRE(!(a.flags & UVC_EPI_ATOMIC) || !(a.flags & UVC_EPI_ROUND_TF32), UVC_ERR_BAD_ARG, "gemm: UVC_EPI_ROUND_TF32 cannot be combined with atomic accumulation");
   UVC_REQUIRE(!(a.flags & UVC_EPI_BIAS) || a.bias, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_BIAS without bias");
   UVC_REQUIRE(!(a.flags & UVC_EPI_RESIDUAL) || a.R, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_RESIDUAL without R");
   UVC_REQUIRE(!(a.flags & UVC_EPI_GELU_BWD) || a.aux, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_GELU_BWD without aux");
@@ -338,7 +343,11 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const long long gy = (a.M + BM - 1) / BM;
   UVC_REQUIRE(gz <= 65535 && gy <= 65535, UVC_ERR_BAD_SHAPE, "gemm: grid too large (m tiles %lld, batch*splits %lld)", gy, gz);
   dim3 grid((a.N + BN - 1) / BN, (unsigned)gy, (unsigned)gz);
-  return launch<BN, 3>(kp, grid, st);
+  const bool prof = prof_enabled();
+  if (prof) prof_begin(st, 2.0 * a.M * a.N * (double)a.K * a.nb1 * a.nb2);
+  rc = launch<BN, 3>(kp, grid, st);
+  if (prof) prof_end(st);
+  return rc;
 }
 
 }  // namespace uvc

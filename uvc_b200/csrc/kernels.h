@@ -9,16 +9,18 @@ namespace uvc {
 int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st);
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
-                  float* rstd, int M, int C, cudaStream_t st);
+                  float* rstd, int M, int C, cudaStream_t st, int round_out = 0);
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
                   cudaStream_t st);
-int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st);
-int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st);
+int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int round_out = 0);
+int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int round_out = 0);
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);
 int blend_fwd(const float* t, const float* x, const float* d, float* out, long long n, cudaStream_t st);
 int blend_dots(const float* g, const float* t, const float* x, float* dots, long long n, cudaStream_t st);
-int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st);
+int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st, int round_out = 0);
+constexpr int kMaxRoundSegs = 96;
+int round_tf32_segs(const float* const* src, float* const* dst, const long long* n, int nseg, cudaStream_t st);
 int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
                     cudaStream_t st);
 int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,

@@ -15,7 +15,7 @@ constexpr int kMaxVec = 8;   // float4 per lane -> C <= 1024
 // one warp per row; two-pass moments in registers (mean, then centred variance) like ATen's RowwiseMoments.
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float* __restrict__ y, long long ldy,
-                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C) {
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C, int rnd) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (rnd) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       yr[c] = o;
     }
   }
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 
 // ------------------------------------------------------------------------------------------ softmax over attention rows
 // in place on S[rows][ld], n valid columns (<= 256); one warp per row
-__global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S, long long ld, long long rows, int n) {
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S, long long ld, long long rows, int n, int rnd) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -153,11 +154,11 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S,
   for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; v[i] = (c < n) ? expf(v[i] - mx) : 0.f; sum += v[i]; }
   const float inv = 1.0f / warp_sum(sum);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; if (c < n) s[c] = v[i] * inv; }
+  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; if (c < n) s[c] = rnd ? round_tf32(v[i] * inv) : v[i] * inv; }
 }
 
 // dS = scale * P .* (dP - sum_j dP_j P_j), written over dP
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, long long ld, long long rows, int n, float scale) {
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, long long ld, long long rows, int n, float scale, int rnd) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -173,7 +174,10 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const int c = lane + i * 32; if (c < n) d[c] = scale * pv[i] * (dv[i] - dot); }
+  for (int i = 0; i < 8; ++i) {
+    const int c = lane + i * 32;
+    if (c < n) { const float o = scale * pv[i] * (dv[i] - dot); d[c] = rnd ? round_tf32(o) : o; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ column sums (bias grads)
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(256) blend_dots_kernel(const float4* __restric
 
 // ------------------------------------------------------------------------------------------ patch embed glue
 // im2col of the 16x16 stride-16 conv: out[(b*196 + py*14 + px), c*256 + ky*16 + kx] = x[b, c, py*16+ky, px*16+kx]
-__global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Cin, int HW, int P) {
+__global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Cin, int HW, int P, int rnd) {
   const int G = HW / P;                       // patches per side
   const long long total4 = (long long)B * G * G * Cin * P * (P / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -238,7 +242,8 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__
     const int px = (int)(t % G); t /= G;
     const int py = (int)(t % G); t /= G;
     const int b = (int)t;
-    const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * Cin + c) * HW + (py * P + ky)) * HW + px * P + kx4 * 4);
+    float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * Cin + c) * HW + (py * P + ky)) * HW + px * P + kx4 * 4);
+    if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     reinterpret_cast<float4*>(out)[i] = v;
   }
 }
@@ -323,6 +328,20 @@ __global__ void scale_add_kernel(float4* __restrict__ y, const float4* __restric
   }
 }
 
+// dst = rna_tf32(src) over up to kMaxSeg tensors in one launch (all GEMM weights of the model)
+struct RoundSegs { const float* src[kMaxRoundSegs]; float* dst[kMaxRoundSegs]; long long n4[kMaxRoundSegs]; int nseg; };
+__global__ void __launch_bounds__(256) round_segs_kernel(const __grid_constant__ RoundSegs segs) {
+  const int seg = blockIdx.y;
+  const float4* s = reinterpret_cast<const float4*>(segs.src[seg]);
+  float4* d = reinterpret_cast<float4*>(segs.dst[seg]);
+  const long long n4 = segs.n4[seg];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = s[i];
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    d[i] = v;
+  }
+}
+
 static inline int grid_for(long long n, int threads, int max_blocks = 148 * 8) {
   long long b = (n + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -331,11 +350,11 @@ static inline int grid_for(long long n, int threads, int max_blocks = 148 * 8) {
 }
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
-                  float* rstd, int M, int C, cudaStream_t st) {
+                  float* rstd, int M, int C, cudaStream_t st, int rnd) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kMaxVec * 128);
   UVC_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm: row strides must be multiples of 4");
   if (M <= 0) return UVC_OK;
-  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C);
+  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd);
   return check_launch("layernorm_fwd");
 }
 
@@ -353,16 +372,16 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
   return check_launch("layernorm_bwd");
 }
 
-int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st) {
+int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int rnd) {
   UVC_REQUIRE(n > 0 && n <= 256, UVC_ERR_BAD_SHAPE, "softmax: n=%d must be in [1,256]", n);
   if (rows <= 0) return UVC_OK;
-  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S, ld, rows, n);
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S, ld, rows, n, rnd);
   return check_launch("softmax_fwd");
 }
-int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st) {
+int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int rnd) {
   UVC_REQUIRE(n > 0 && n <= 256, UVC_ERR_BAD_SHAPE, "softmax_bwd: n=%d must be in [1,256]", n);
   if (rows <= 0) return UVC_OK;
-  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(P, dP, ld, rows, n, scale);
+  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(P, dP, ld, rows, n, scale, rnd);
   return check_launch("softmax_bwd");
 }
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st) {
@@ -385,10 +404,10 @@ int blend_dots(const float* g, const float* t, const float* x, float* dots, long
   blend_dots_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, st>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), dots, n / 4);
   return check_launch("blend_dots");
 }
-int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st) {
+int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st, int rnd) {
   UVC_REQUIRE(P % 4 == 0 && HW % P == 0, UVC_ERR_BAD_SHAPE, "im2col: patch %d must divide image %d and be a multiple of 4", P, HW);
   const long long total4 = (long long)B * Cin * HW * HW / 4;
-  im2col16_kernel<<<grid_for(total4, 256, 148 * 16), 256, 0, st>>>(x, out, B, Cin, HW, P);
+  im2col16_kernel<<<grid_for(total4, 256, 148 * 16), 256, 0, st>>>(x, out, B, Cin, HW, P, rnd);
   return check_launch("im2col16");
 }
 int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
@@ -410,6 +429,23 @@ int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, co
   }
   return rc;
 }
+int round_tf32_segs(const float* const* src, float* const* dst, const long long* n, int nseg, cudaStream_t st) {
+  for (int base = 0; base < nseg; base += kMaxRoundSegs) {
+    RoundSegs segs;
+    segs.nseg = (nseg - base < kMaxRoundSegs) ? nseg - base : kMaxRoundSegs;
+    long long mx = 0;
+    for (int i = 0; i < segs.nseg; ++i) {
+      UVC_REQUIRE((n[base + i] & 3) == 0, UVC_ERR_BAD_SHAPE, "round_tf32: element count must be a multiple of 4");
+      segs.src[i] = src[base + i]; segs.dst[i] = dst[base + i]; segs.n4[i] = n[base + i] / 4;
+      if (segs.n4[i] > mx) mx = segs.n4[i];
+    }
+    if (mx == 0) continue;
+    round_segs_kernel<<<dim3(grid_for(mx, 256, 32), segs.nseg), 256, 0, st>>>(segs);
+    int rc = check_launch("round_tf32");
+    if (rc) return rc;
+  }
+  return UVC_OK;
+}
 int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st) {
   UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "scale_add: element count must be a multiple of 4");
   scale_add_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), s_dev, s, n / 4);
@@ -422,9 +458,9 @@ int scale_add(float* y, const float* x, const float* s_dev, float s, long long n
 #define UVC_ST static_cast<cudaStream_t>(stream)
 extern "C" {
 int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y, int64_t ldy, float* mean,
-                      float* rstd, int32_t M, int32_t C, void* stream) {
+                      float* rstd, int32_t M, int32_t C, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(x && gamma && beta && y, UVC_ERR_BAD_ARG, "uvc_layernorm_fwd: NULL pointer");
-  return uvc::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, UVC_ST);
+  return uvc::layernorm_fwd(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, UVC_ST, round_tf32);
 }
 int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
                       const float* r1, const float* r2, const float* s2_dev, float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M,
@@ -433,13 +469,13 @@ int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx
   UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd: dgamma and dbeta must both be given or both NULL");
   return uvc::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST);
 }
-int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, void* stream) {
+int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(S, UVC_ERR_BAD_ARG, "uvc_softmax_fwd: NULL pointer");
-  return uvc::softmax_fwd(S, ld, rows, n, UVC_ST);
+  return uvc::softmax_fwd(S, ld, rows, n, UVC_ST, round_tf32);
 }
-int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, void* stream) {
+int uvc_softmax_bwd(const float* P, float* dP, int64_t ld, int64_t rows, int32_t n, float scale, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(P && dP, UVC_ERR_BAD_ARG, "uvc_softmax_bwd: NULL pointer");
-  return uvc::softmax_bwd(P, dP, ld, rows, n, scale, UVC_ST);
+  return uvc::softmax_bwd(P, dP, ld, rows, n, scale, UVC_ST, round_tf32);
 }
 int uvc_colsum(const float* X, int64_t ld, int32_t M, int32_t N, const float* scale_dev, float* out, void* stream) {
   UVC_REQUIRE(X && out, UVC_ERR_BAD_ARG, "uvc_colsum: NULL pointer");
@@ -453,9 +489,9 @@ int uvc_blend_dots(const float* g, const float* t, const float* x, float* dots, 
   UVC_REQUIRE(g && t && x && dots, UVC_ERR_BAD_ARG, "uvc_blend_dots: NULL pointer");
   return uvc::blend_dots(g, t, x, dots, n, UVC_ST);
 }
-int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, void* stream) {
+int uvc_im2col16(const float* x, float* out, int32_t B, int32_t Cin, int32_t HW, int32_t P, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(x && out, UVC_ERR_BAD_ARG, "uvc_im2col16: NULL pointer");
-  return uvc::im2col16(x, out, B, Cin, HW, P, UVC_ST);
+  return uvc::im2col16(x, out, B, Cin, HW, P, UVC_ST, round_tf32);
 }
 int uvc_assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int32_t B,
                         int32_t np, int32_t C, void* stream) {
@@ -466,6 +502,11 @@ int uvc_assemble_tokens_bwd(const float* g, const float* pe, const float* pscale
                             float* dpos, float* dcls, int32_t B, int32_t np, int32_t C, void* stream) {
   UVC_REQUIRE(g && pe && dpe, UVC_ERR_BAD_ARG, "uvc_assemble_tokens_bwd: NULL pointer");
   return uvc::assemble_tokens_bwd(g, pe, pscale, tmask, dpe, dscale, dtmask, dpos, dcls, B, np, C, UVC_ST);
+}
+int uvc_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
+  UVC_REQUIRE(src && dst, UVC_ERR_BAD_ARG, "uvc_round_tf32: NULL pointer");
+  const long long nn = n;
+  return uvc::round_tf32_segs(&src, &dst, &nn, 1, UVC_ST);
 }
 int uvc_scale_add(float* y, const float* x, const float* s_dev, float s, int64_t n, void* stream) {
   UVC_REQUIRE(y && x, UVC_ERR_BAD_ARG, "uvc_scale_add: NULL pointer");

@@ -31,7 +31,13 @@ struct LayerWs {
   float *ln1, *qkv, *P, *ctx, *x1, *ln2, *hpre, *h, *t, *xout;
 };
 
+struct WeightsR {   // TF32-rounded copies of every GEMM weight (refreshed at the start of each forward)
+  float *patch_w, *head_w;
+  float *qkv_w[UVC_MAX_DEPTH], *proj_w[UVC_MAX_DEPTH], *fc1_w[UVC_MAX_DEPTH], *fc2_w[UVC_MAX_DEPTH];
+};
+
 struct Ws {
+  WeightsR wr;
   // persistent (saved for backward)
   float *cols, *pe, *tok, *mean_f, *rstd_f, *cls_ln, *accum;
   LayerWs layer[UVC_MAX_DEPTH];
@@ -67,6 +73,10 @@ void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
   Bump b(base, cap);
   const size_t M = (size_t)D.M, C = D.C, Fh = D.Fh;
   const size_t psz = (size_t)D.B * D.H * D.ntok * attn_ldp(D.ntok);
+  w->wr.patch_w = b.f(C * (size_t)D.Kp); w->wr.head_w = b.f((size_t)D.NC * C);
+  for (int l = 0; l < D.L; ++l) {
+    w->wr.qkv_w[l] = b.f(3 * C * C); w->wr.proj_w[l] = b.f(C * C); w->wr.fc1_w[l] = b.f(Fh * C); w->wr.fc2_w[l] = b.f(C * Fh);
+  }
   w->cols = b.f((size_t)D.B * D.np * D.Kp);
   w->pe = b.f((size_t)D.B * D.np * C);
   w->tok = b.f(M * C);
@@ -127,6 +137,23 @@ int linear_wgrad(const float* dY, long long lddy, const float* X, long long ldx,
   return UVC_OK;
 }
 
+// weights -> TF32-rounded copies in the workspace (one launch per <= 96 tensors)
+int round_weights(const uvc_vit_tensors& p, const Dims& D, const WeightsR& wr, cudaStream_t st) {
+  const float* src[2 + 4 * UVC_MAX_DEPTH]; float* dst[2 + 4 * UVC_MAX_DEPTH]; long long n[2 + 4 * UVC_MAX_DEPTH];
+  int k = 0;
+  const long long C = D.C, Fh = D.Fh;
+  src[k] = p.patch_w; dst[k] = wr.patch_w; n[k++] = C * D.Kp;
+  src[k] = p.head_w; dst[k] = wr.head_w; n[k++] = (long long)D.NC * C;
+  for (int l = 0; l < D.L; ++l) {
+    const uvc_block_tensors& b = p.blocks[l];
+    src[k] = b.qkv_w; dst[k] = wr.qkv_w[l]; n[k++] = 3 * C * C;
+    src[k] = b.proj_w; dst[k] = wr.proj_w[l]; n[k++] = C * C;
+    src[k] = b.fc1_w; dst[k] = wr.fc1_w[l]; n[k++] = Fh * C;
+    src[k] = b.fc2_w; dst[k] = wr.fc2_w[l]; n[k++] = C * Fh;
+  }
+  return round_tf32_segs(src, dst, n, k, st);
+}
+
 int check_tensors(const uvc_vit_tensors& w, int L, const char* what) {
   UVC_REQUIRE(w.patch_w && w.patch_b && w.cls_token && w.pos_embed && w.norm_w && w.norm_b && w.head_w && w.head_b && w.blocks, UVC_ERR_BAD_ARG,
               "vit: %s has a NULL tensor", what);
@@ -163,9 +190,10 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   const float scale = 1.0f / sqrtf((float)D.d);
 
   // patch embed: 16x16/16 conv == GEMM over im2col rows
-  UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st));
+  UVC_TRY(round_weights(a.w, D, w.wr, st));
+  UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
   float* pe = a.pe_out ? a.pe_out : w.pe;
-  UVC_TRY(linear_fwd(w.cols, D.Kp, a.w.patch_w, a.w.patch_b, pe, C, D.B * D.np, C, D.Kp, st));
+  UVC_TRY(linear_fwd(w.cols, D.Kp, w.wr.patch_w, a.w.patch_b, pe, C, D.B * D.np, C, D.Kp, st));
   UVC_TRY(assemble_tokens(pe, a.w.cls_token, a.w.pos_embed, a.patch_scale, a.token_mask, w.tok, D.B, D.np, C, st));
   if (a.pe_out && save) {
     cudaError_t e = cudaMemcpyAsync(w.pe, pe, (size_t)D.B * D.np * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -182,17 +210,17 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
     if (!skipped) {
       const uvc_block_tensors& p = a.w.blocks[l];
       LayerWs& L = w.layer[l];
-      UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, L.ln1, C, L.mean1, L.rstd1, M, C, st));
-      UVC_TRY(linear_fwd(L.ln1, C, p.qkv_w, p.qkv_b, L.qkv, 3 * C, M, 3 * C, C, st));
+      UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, L.ln1, C, L.mean1, L.rstd1, M, C, st, 1));
+      UVC_TRY(linear_fwd(L.ln1, C, w.wr.qkv_w[l], p.qkv_b, L.qkv, 3 * C, M, 3 * C, C, st, UVC_EPI_ROUND_TF32));
       UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st));
-      UVC_TRY(linear_fwd(L.ctx, C, p.proj_w, p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));           // x1 = x + proj(ctx)
-      UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st));
-      UVC_TRY(linear_fwd(L.ln2, C, p.fc1_w, p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU, L.hpre));          // h = gelu(fc1), hpre kept
+      UVC_TRY(linear_fwd(L.ctx, C, w.wr.proj_w[l], p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));     // x1 = x + proj(ctx)
+      UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st, 1));
+      UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1), hpre kept
       if (a.blend) {
-        UVC_TRY(linear_fwd(L.h, Fh, p.fc2_w, p.fc2_b, L.t, C, M, C, Fh, st, 0, nullptr, L.x1, C));          // t = x1 + fc2(h)
+        UVC_TRY(linear_fwd(L.h, Fh, w.wr.fc2_w[l], p.fc2_b, L.t, C, M, C, Fh, st, 0, nullptr, L.x1, C));    // t = x1 + fc2(h)
         UVC_TRY(blend_fwd(L.t, x, a.blend + 2 * l, L.xout, (long long)M * C, st));                            // x <- d1 t + d0 x
       } else {
-        UVC_TRY(linear_fwd(L.h, Fh, p.fc2_w, p.fc2_b, L.xout, C, M, C, Fh, st, 0, nullptr, L.x1, C));
+        UVC_TRY(linear_fwd(L.h, Fh, w.wr.fc2_w[l], p.fc2_b, L.xout, C, M, C, Fh, st, 0, nullptr, L.x1, C));
       }
       x = L.xout;
     }
@@ -200,8 +228,8 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   }
   const float* xf = a.enable_jumping ? w.accum : x;
   // final LayerNorm only on the cls rows (row stride ntok*C), then the classifier head
-  UVC_TRY(layernorm_fwd(xf, (long long)D.ntok * C, a.w.norm_w, a.w.norm_b, eps, w.cls_ln, C, w.mean_f, w.rstd_f, D.B, C, st));
-  UVC_TRY(linear_fwd(w.cls_ln, C, a.w.head_w, a.w.head_b, a.logits, D.NC, D.B, D.NC, C, st));
+  UVC_TRY(layernorm_fwd(xf, (long long)D.ntok * C, a.w.norm_w, a.w.norm_b, eps, w.cls_ln, C, w.mean_f, w.rstd_f, D.B, C, st, 1));
+  UVC_TRY(linear_fwd(w.cls_ln, C, w.wr.head_w, a.w.head_b, a.logits, D.NC, D.B, D.NC, C, st));
   return UVC_OK;
 }
 
@@ -228,7 +256,7 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
 
   // head: dW += dlogits^T cls_ln ; db += colsum ; dcls_ln = dlogits W
   UVC_TRY(linear_wgrad(a.dlogits, D.NC, w.cls_ln, C, a.g.head_w, a.g.head_b, D.B, D.NC, C, st));
-  UVC_TRY(linear_dgrad(a.dlogits, D.NC, a.w.head_w, w.dcls_ln, C, D.B, D.NC, C, st));
+  UVC_TRY(linear_dgrad(a.dlogits, D.NC, w.wr.head_w, w.dcls_ln, C, D.B, D.NC, C, st));
   // final LN backward on the cls rows; every other row of the stream gradient is zero
   float* g = w.g_a;         // gradient wrt the current residual stream
   float* g_jump = nullptr;  // with jumping connections the final-norm gradient reaches every block output
@@ -264,19 +292,19 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
       }
       // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2)))
       UVC_TRY(linear_wgrad(dt, C, L.h, Fh, gp.fc2_w, gp.fc2_b, M, C, Fh, st));
-      UVC_TRY(linear_dgrad(dt, C, p.fc2_w, w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD, L.hpre, Fh));               // dhpre
+      UVC_TRY(linear_dgrad(dt, C, w.wr.fc2_w[l], w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD | UVC_EPI_ROUND_TF32, L.hpre, Fh));               // dhpre
       UVC_TRY(linear_wgrad(w.dh, Fh, L.ln2, C, gp.fc1_w, gp.fc1_b, M, Fh, C, st));
-      UVC_TRY(linear_dgrad(w.dh, Fh, p.fc1_w, spare2, C, M, Fh, C, st));                                          // dln2
+      UVC_TRY(linear_dgrad(w.dh, Fh, w.wr.fc1_w[l], spare2, C, M, Fh, C, st));                                          // dln2
       // dx1 = dt + LN2'(dln2)
       UVC_TRY(layernorm_bwd(spare2, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, dt, nullptr, nullptr, spare2, C, gp.norm2_w, gp.norm2_b, M, C, st));
       float* dx1 = spare2;
       // ---- attention:  x1 = x + proj(ctx)
       UVC_TRY(linear_wgrad(dx1, C, L.ctx, C, gp.proj_w, gp.proj_b, M, C, C, st));
       float* dctx = spare1;                                        // dt is dead after the LN2 backward
-      UVC_TRY(linear_dgrad(dx1, C, p.proj_w, dctx, C, M, C, C, st));
+      UVC_TRY(linear_dgrad(dx1, C, w.wr.proj_w[l], dctx, C, M, C, C, st, UVC_EPI_ROUND_TF32));
       UVC_TRY(attention_bwd(L.qkv, L.P, dctx, w.dP, w.dqkv, D.B, D.H, D.ntok, D.d, scale, st));
       UVC_TRY(linear_wgrad(w.dqkv, 3 * C, L.ln1, C, gp.qkv_w, gp.qkv_b, M, 3 * C, C, st));
-      UVC_TRY(linear_dgrad(w.dqkv, 3 * C, p.qkv_w, spare1, C, M, 3 * C, C, st));                                  // dln1
+      UVC_TRY(linear_dgrad(w.dqkv, 3 * C, w.wr.qkv_w[l], spare1, C, M, 3 * C, C, st));                                  // dln1
       // dx = dx1 + LN1'(dln1) + d0 g        (written over spare1)
       UVC_TRY(layernorm_bwd(spare1, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st));
       // rotate buffers: new stream gradient is spare1

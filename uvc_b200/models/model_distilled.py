@@ -182,6 +182,7 @@ class _EngineState:
         self.ws = {}
         self.grad_arena = None
         self.grad_views = None
+        self.grad_offs = None
 
 
 def _engine_param_list(model):
@@ -217,10 +218,8 @@ class _VitFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, blend, patch_scale, token_mask, skip, *params):
-        need_grad = torch.is_grad_enabled() and (any(p is not None and p.requires_grad for p in params) or
-                                                 (blend is not None and blend.requires_grad) or
-                                                 (patch_scale is not None and patch_scale.requires_grad) or
-                                                 (token_mask is not None and token_mask.requires_grad))
+        # (grad mode is always off inside Function.forward; ctx.needs_input_grad says whether a backward can follow)
+        need_grad = any(ctx.needs_input_grad)
         logits = model._engine_forward(x, blend, patch_scale, token_mask, skip, save=need_grad)
         ctx.model, ctx.skip, ctx.B = model, skip, x.shape[0]
         ctx.save_for_backward(blend, patch_scale, token_mask)
@@ -292,6 +291,7 @@ class DistilledVisionTransformer(VisionTransformer):
                 offs.append(total)
                 total += (n + 3) // 4 * 4
             es.grad_arena = torch.zeros(total, device=dev, dtype=torch.float32)
+            es.grad_offs = offs
             es.grad_views = [None if p is None else es.grad_arena[o:o + p.numel()].view(p.shape) for (_, p), o in zip(plist, offs)]
             es.g, keep_g = _fill_tables([(n, v) for (n, _), v in zip(plist, es.grad_views)], len(self.blocks))
             es.keep = (keep_w, keep_g)
@@ -374,8 +374,44 @@ class DistilledVisionTransformer(VisionTransformer):
         ws = self._workspace(B, True)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.uvc_vit_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_backward")
-        grads = [None] * len(plist) if accumulate else list(es.grad_views)
+        # fresh view objects: autograd's AccumulateGrad only adopts a gradient it holds the sole reference to, and
+        # adopting (not copying) is what makes every .grad a window of the flat arena
+        grads = [None] * len(plist) if accumulate else \
+            [None if p is None else es.grad_arena[o:o + p.numel()].view(p.shape) for (_, p), o in zip(plist, es.grad_offs)]
         return grads, d_blend, d_ps, d_tm
+
+    def flatten_parameters(self):
+        """Move every engine parameter into ONE flat fp32 arena laid out exactly like the gradient arena (same order, same
+        16-byte padded offsets).  `flat_param`, `flat_grad` (and an optimiser's flat moment buffers) then line up element
+        for element: the gradient all-reduce is one collective and clip + AdamW is one sweep.  Parameters stay ordinary
+        nn.Parameters (views of the arena), so state dicts / torch optimisers keep working."""
+        plist = _engine_param_list(self)
+        offs, total = [], 0
+        for _, p in plist:
+            offs.append(total)
+            total += ((0 if p is None else p.numel()) + 3) // 4 * 4
+        dev = self.cls_token.device
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for (_, p), o in zip(plist, offs):
+                if p is None:
+                    continue
+                flat[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                p.data = flat[o:o + p.numel()].view(p.shape)
+        self._flat_param = flat
+        self._es.sig = None          # pointer tables are rebuilt on the next call
+        return flat
+
+    @property
+    def flat_param(self):
+        fp = getattr(self, "_flat_param", None)
+        if fp is None or _engine_param_list(self)[0][1].data_ptr() != fp.data_ptr():
+            return None              # never flattened, or re-materialised by .to() / load with assign
+        return fp
+
+    def engine_parameters(self):
+        """Parameters that live in the flat arenas, in arena order (offsets: 16-byte padded running sum)."""
+        return [p for _, p in _engine_param_list(self) if p is not None]
 
     @property
     def flat_grad(self):

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, GemmArgs, Operand  # noqa: F401
+from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GemmArgs, Operand  # noqa: F401
 
 
 def _stream():
@@ -82,7 +82,7 @@ def _call(name, *args):
     _lib.check(getattr(lib, name)(*args, _stream()), name)
 
 
-def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True):
+def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True, round_tf32=False):
     """x:[M,C] rows (row stride ldx) -> y:[M,C], (mean, rstd)."""
     C_ = gamma.numel()
     M = x.numel() // C_ if M is None else M
@@ -91,7 +91,7 @@ def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True
         y = torch.empty(M, C_, device=x.device)
     mean = torch.empty(M, device=x.device) if save_stats else None
     rstd = torch.empty(M, device=x.device) if save_stats else None
-    _call("uvc_layernorm_fwd", _p(x), ldx, _p(gamma), _p(beta), float(eps), _p(y), C_, _p(mean), _p(rstd), M, C_)
+    _call("uvc_layernorm_fwd", _p(x), ldx, _p(gamma), _p(beta), float(eps), _p(y), C_, _p(mean), _p(rstd), M, C_, int(round_tf32))
     return y, mean, rstd
 
 
@@ -107,15 +107,15 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=No
     return dx
 
 
-def softmax_fwd_(S, n):
+def softmax_fwd_(S, n, round_tf32=False):
     ld = S.shape[-1]
-    _call("uvc_softmax_fwd", _p(S), ld, S.numel() // ld, n)
+    _call("uvc_softmax_fwd", _p(S), ld, S.numel() // ld, n, int(round_tf32))
     return S
 
 
-def softmax_bwd_(P, dP, n, scale):
+def softmax_bwd_(P, dP, n, scale, round_tf32=False):
     ld = P.shape[-1]
-    _call("uvc_softmax_bwd", _p(P), _p(dP), ld, P.numel() // ld, n, float(scale))
+    _call("uvc_softmax_bwd", _p(P), _p(dP), ld, P.numel() // ld, n, float(scale), int(round_tf32))
     return dP
 
 
@@ -136,11 +136,18 @@ def blend_dots_(g, t, x, dots):
     return dots
 
 
-def im2col16(x, patch=16):
+def round_tf32(src, dst=None):
+    """dst = src rounded to the nearest TF32 value (10-bit mantissa)."""
+    dst = torch.empty_like(src) if dst is None else dst
+    _call("uvc_round_tf32", _p(src), _p(dst), src.numel())
+    return dst
+
+
+def im2col16(x, patch=16, round_tf32=False):
     B, Cin, HW, _ = x.shape
     g = HW // patch
     out = torch.empty(B * g * g, Cin * patch * patch, device=x.device)
-    _call("uvc_im2col16", _p(x), _p(out), B, Cin, HW, patch)
+    _call("uvc_im2col16", _p(x), _p(out), B, Cin, HW, patch, int(round_tf32))
     return out
 
 

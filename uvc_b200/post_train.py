@@ -1,0 +1,172 @@
+"""Stage 2 of UVC — post-training of the weights under the FIXED layout found by Stage 1 — on the sm_100a engine.
+
+Mirror of the reference's `UVC/post_train.py`: load a Stage-1 checkpoint (weights + `.mask` buffers + gates, strict), hard-skip
+blocks whose gate prefers "skip" (models/model_distilled.py:496-500), keep every masked weight at zero, AdamW + per-epoch cosine
+schedule (timm `create_optimizer` / `create_scheduler`, re-stated: timm is an un-vendored dependency), soft distillation from the
+dense teacher, evaluate every epoch and keep the best checkpoint.
+
+The reference re-multiplies every weight by its mask before every step (:357-360, ~150 launches); here the mask rides inside the
+fused clip+AdamW sweep (the update is multiplied by the mask), so masked weights are exactly 0 at every forward, identically.
+"""
+import math
+import os
+import time
+
+import torch
+
+from . import joint_train as jt
+from .utils.data_utils import get_loader
+from .utils.ddp import DistributedDataParallel as DDP
+from .utils.dist_util import get_world_size
+from .utils.optim import FusedClipAdamW
+
+
+def apply_masks(model):
+    """weight *= mask for every module that carries one (post_train.py:228-231,357-360)"""
+    with torch.no_grad():
+        for _, m in model.named_modules():
+            if hasattr(m, "mask"):
+                m.weight.mul_(m.mask)
+
+
+def param_groups_weight_decay(model, weight_decay):
+    """timm.optim.optim_factory.add_weight_decay: no decay for 1-d tensors, biases and model.no_weight_decay() names"""
+    skip = model.no_weight_decay() if hasattr(model, "no_weight_decay") else set()
+    decay, no_decay = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (no_decay if (p.ndim <= 1 or name.endswith(".bias") or name in skip) else decay).append(p)
+    return [{"params": no_decay, "weight_decay": 0.0}, {"params": decay, "weight_decay": weight_decay}]
+
+
+class CosineEpochSchedule:
+    """timm CosineLRScheduler stepped per epoch with linear warm-up (create_scheduler defaults of the DeiT recipe:
+    warmup_epochs 5 from warmup_lr 1e-6, min_lr 1e-5)."""
+
+    def __init__(self, optimizer, epochs, base_lr, warmup_epochs=5, warmup_lr=1e-6, min_lr=1e-5):
+        self.opt, self.epochs, self.base_lr = optimizer, epochs, base_lr
+        self.warmup_epochs, self.warmup_lr, self.min_lr = warmup_epochs, warmup_lr, min_lr
+
+    def get_epoch_values(self, epoch):
+        if epoch < self.warmup_epochs:
+            lr = self.warmup_lr + epoch * (self.base_lr - self.warmup_lr) / self.warmup_epochs
+        else:
+            lr = self.min_lr + 0.5 * (self.base_lr - self.min_lr) * (1 + math.cos(math.pi * epoch / self.epochs))
+        return [lr]
+
+    def step(self, epoch):
+        lr = self.get_epoch_values(epoch)[0]
+        for g in self.opt.param_groups:
+            g["lr"] = lr
+
+
+def post_training(args, model, mixup_fn=None, criterion=None, lr=None, weight_decay=None, epochs=None):
+    """post_train.py:270-402"""
+    epochs = epochs if epochs is not None else args.epochs
+    lr = lr if lr is not None else args.learning_rate
+    weight_decay = weight_decay if weight_decay is not None else args.weight_decay
+    if args.local_rank in [-1, 0]:
+        os.makedirs(os.path.join(args.output_dir, args.name), exist_ok=True)
+    print("Starting post training")
+    train_loader, test_loader = get_loader(args)
+    model.enable_block_gating = 0            # hard skip by gate comparison, as the Stage-2 constructor default does
+    model.block_skip_gating.requires_grad = False
+    apply_masks(model)
+    ddp_model = DDP(model, message_size=250000000, gradient_predivide_factor=get_world_size(), delay_allreduce=True) \
+        if args.local_rank != -1 and get_world_size() > 1 else model
+    args.lr = lr * args.train_batch_size * get_world_size() / 512.0
+    masks = {m.weight: m.mask for _, m in model.named_modules() if hasattr(m, "mask")}
+    optimizer = FusedClipAdamW(param_groups_weight_decay(model, weight_decay), lr=args.lr, weight_decay=weight_decay,
+                               max_grad_norm=args.max_grad_norm, model=model, masks=masks)
+    scheduler = CosineEpochSchedule(optimizer, epochs, args.lr)
+    print("***** [Stage 2] Post Training *****")
+    print("  Instantaneous batch size per GPU = %d" % args.train_batch_size)
+    model.zero_grad()
+    jt.set_seed(args)
+    losses = jt.AverageMeter()
+    global_step, best_acc = 0, 0
+    for epoch in range(epochs):
+        model.train()
+        print("=" * 60)
+        print(f"Start training [Epoch {epoch}]")
+        scheduler.step(epoch)
+        t0 = time.time()
+        for step, (x, y) in enumerate(train_loader):
+            x, y = x.to(args.device, non_blocking=True), y.to(args.device, non_blocking=True)
+            if len(x) % 2 != 0:
+                x, y = x[:-1], y[:-1]
+            if mixup_fn is not None:
+                x, y = mixup_fn(x, y)
+            outputs, _ = ddp_model(x)
+            loss = criterion(x, outputs, y)
+            loss.backward()
+            optimizer.step()
+            global_step += 1
+            optimizer.zero_grad()
+            if (step + 1) % max(1, getattr(args, "print_every", 50)) == 0 and args.local_rank in [-1, 0]:
+                losses.update(loss.item())
+                print(f"Training [{global_step} Steps] [LR: {scheduler.get_epoch_values(epoch)[0]:.6f} | Loss: {losses.val:.3f}] "
+                      f"{(step + 1) * x.shape[0] * get_world_size() / (time.time() - t0):.1f} img/s")
+        if args.local_rank in [-1, 0]:
+            accuracy = valid(args, model, None, test_loader, global_step)
+            if best_acc < accuracy:
+                jt.save_model(args, model, None, global_step)
+                best_acc = accuracy
+    return best_acc
+
+
+def valid(args, model, writer, test_loader, global_step):
+    apply_masks(model)           # post_train.py:228-231
+    return jt.valid(args, model, writer, test_loader, global_step)
+
+
+def build_parser():
+    p = jt.build_parser()
+    p.add_argument("--checkpoint_dir", default=None, type=str, help="Stage-1 checkpoint (state dict with masks and gates)")
+    p.add_argument("--epochs", default=120, type=int)
+    return p
+
+
+def main(argv=None):
+    import torch.distributed as dist
+    from datetime import timedelta
+    from .models import CONFIGS
+    from .utils.losses import DistillationLoss
+    from .utils.mixup import Mixup, SoftTargetCrossEntropy, LabelSmoothingCrossEntropy
+    args = build_parser().parse_args(argv)
+    config = CONFIGS[args.model_type]
+    args.local_rank = int(os.environ.get("LOCAL_RANK", args.local_rank))
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        torch.cuda.set_device(args.local_rank)
+        dist.init_process_group(backend='nccl', timeout=timedelta(minutes=60))
+    else:
+        args.local_rank = -1 if "LOCAL_RANK" not in os.environ else args.local_rank
+    args.n_gpu = 1
+    args.device = torch.device("cuda", max(args.local_rank, 0))
+    jt.set_seed(args)
+    args.num_classes = {"cifar10": 10, "cifar100": 100}.get(args.dataset, 1000)
+    model = jt.make_model(args, config, gumbel_hard=True)
+    for _, m in model.named_modules():      # masks registered BEFORE the strict load so the layout is restored (post_train.py:176-186)
+        if hasattr(m, "weight"):
+            m.register_buffer("mask", torch.ones_like(m.weight))
+    if args.checkpoint_dir:
+        jt.load_checkpoint(model, args.checkpoint_dir, strict=True)
+    model.to(args.device)
+    model.flatten_parameters()
+    mixup_fn = Mixup(mixup_alpha=args.mixup, cutmix_alpha=args.cutmix, prob=args.mixup_prob, switch_prob=args.mixup_switch_prob,
+                     label_smoothing=args.smoothing, num_classes=args.num_classes) if (args.mixup > 0 or args.cutmix > 0) else None
+    base = SoftTargetCrossEntropy() if args.mixup > 0 else (LabelSmoothingCrossEntropy(args.smoothing) if args.smoothing else torch.nn.CrossEntropyLoss())
+    teacher = None
+    if args.distillation_type != 'none':
+        teacher = jt.make_model(args, config, gumbel_hard=True)
+        path = args.teacher_path or args.model_path
+        if path is not None:
+            jt.load_checkpoint(teacher, path)
+        teacher.to(args.device).eval()
+    criterion = DistillationLoss(base, teacher, args.distillation_type, args.distillation_alpha, args.distillation_tau)
+    post_training(args, model, mixup_fn, criterion)
+
+
+if __name__ == "__main__":
+    main()
