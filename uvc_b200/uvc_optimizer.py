@@ -41,7 +41,8 @@ def uvc_optimizer(optimizer, minimax_model, s_optimizer, r_optimizer, gating_opt
 
     prox_w(mm, optimizer)                                   # :42   (scores of the pre-prox weights inside)
     d.scores()                                              # :46-48 read the post-prox weights
-    a = mm.admm_args(noise=mm.gumbel_noise(), gumbel_hard=False, warmup=warmup)     # first Gumbel draw (srloss2)
+    noise1 = mm.gumbel_noise()                              # first Gumbel draw (srloss2)
+    a = mm.admm_args(noise=noise1, gumbel_hard=False, warmup=warmup)
     a.z_grad_clip = float(z_grad_clip)
     a.slr, a.rlr = _sgd_lr(s_optimizer, "soptim"), _sgd_lr(r_optimizer, "roptim")
     gate = mm.block_skip_gating
@@ -71,7 +72,8 @@ def uvc_optimizer(optimizer, minimax_model, s_optimizer, r_optimizer, gating_opt
                 buf = GateGradBuffer()
                 gating_optimizer.zero_grad()
         # dual ascent (:126-135) with the updated s, r (and gate), second Gumbel draw (zloss)
-        b = mm.admm_args(noise=mm.gumbel_noise(), gumbel_hard=False)
+        noise2 = mm.gumbel_noise()
+        b = mm.admm_args(noise=noise2, gumbel_hard=False)
         groups = dual_optimizer.param_groups
         b.zlr, b.ylr, b.plr = float(groups[0]['lr']), float(groups[1]['lr']), float(groups[2]['lr'])
         d.call("uvc_admm_dual", b)

@@ -216,6 +216,7 @@ class UVC_CP_MiniMax(nn.Module):
         gate = self.block_skip_gating
         a.gate = None if gate is None else gate.data_ptr()
         a.noise = None if noise is None else noise.data_ptr()
+        a._keepalive = (noise, self._macs_dev)      # the kernel reads these after this function returns
         a.macs = self._macs_dev.data_ptr()
         a.embed_macs, a.full_flops = self._embed_macs, self.full_flops
         ar = self.args
