@@ -139,6 +139,54 @@ def run_case(case):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         print(f"  cuBLAS tf32 8192^3: {ms*1e3:.1f} us {2*8192**3/ms/1e9:.1f} TFLOP/s")
+    elif case == "v2":
+        # CTA-pair kernel (run with UVC_GEMM_V2=2 and UVC_GEMM_V2_BN in {128,192,256}): majors, ragged edges, split-K, epilogues
+        for (M, N, K, amn, bmn, splits) in [(512, 256, 64, 0, 0, 1), (1000, 388, 100, 0, 0, 1), (300, 260, 132, 0, 1, 1), (776, 512, 96, 1, 0, 1),
+                                            (1536, 384, 2500, 1, 1, 5), (25216, 1152, 384, 0, 0, 1), (25216, 384, 1536, 0, 1, 1), (130, 36, 200, 0, 0, 1)]:
+            A = rn(K, M) if amn else rn(M, K); B = rn(K, N) if bmn else rn(N, K)
+            D = torch.zeros(M, N, device=dev)
+            fl = ops.EPI_ATOMIC if splits > 1 else 0
+            ops.gemm(ops.operand(A, mn_major=bool(amn)), ops.operand(B, mn_major=bool(bmn)), D, M, N, K, splits=splits, flags=fl); torch.cuda.synchronize()
+            ref = (A.t() if amn else A) @ (B if bmn else B.t())
+            ok &= report(f"v2 {M}x{N}x{K} a_mn={amn} b_mn={bmn} splits={splits}", D, ref)
+        M, N, K = 1000, 768, 192
+        A, B, bias, R = rn(M, K), rn(N, K) * 0.1, rn(N), rn(M, N)
+        pre = A @ B.t() + bias
+        D = torch.empty(M, N, device=dev); aux = torch.empty(M, N, device=dev)
+        ops.gemm(A, B, D, M, N, K, bias=bias, aux=aux, flags=ops.EPI_GELU); torch.cuda.synchronize()
+        ok &= report("v2 gelu", D, torch.nn.functional.gelu(pre)); ok &= report("v2 gelu_aux", aux, pre)
+        ops.gemm(A, B, D, M, N, K, bias=bias, R=R, beta=0.5); torch.cuda.synchronize()
+        ok &= report("v2 bias_residual", D, pre + 0.5 * R)
+        u = rn(M, N)
+        ops.gemm(A, B, D, M, N, K, aux=u, flags=ops.EPI_GELU_BWD | ops.EPI_ROUND_TF32); torch.cuda.synchronize()
+        uu = u.clone().requires_grad_(True); torch.nn.functional.gelu(uu).sum().backward()
+        ok &= report("v2 gelu_bwd", D, (A @ B.t()) * uu.grad)
+        D0 = rn(M, N); D1 = D0.clone()
+        ops.gemm(A, B, D1, M, N, K, R=D1); torch.cuda.synchronize()
+        ok &= report("v2 accumulate_inplace", D1, D0 + A @ B.t())
+        # many back-to-back launches (pipeline phase bookkeeping across units, TMEM alloc/free across kernels)
+        A, B = rn(4096, 384), rn(1536, 384); D = torch.empty(4096, 1536, device=dev)
+        for _ in range(20): ops.gemm(A, B, D, 4096, 1536, 384)
+        torch.cuda.synchronize()
+        ok &= report("v2 repeat", D, A @ B.t())
+    elif case == "perf2":
+        shapes = [(25216, 1152, 384, 0, 0, 1, 0, "qkv fwd"), (25216, 1536, 384, 0, 0, 1, ops.EPI_GELU, "fc1 fwd+gelu"), (25216, 384, 1536, 0, 0, 1, 0, "fc2 fwd"),
+                  (25216, 384, 384, 0, 0, 1, 0, "proj fwd"), (25216, 384, 1536, 0, 1, 1, 0, "fc1 dgrad"), (25216, 1536, 384, 0, 1, 1, 0, "fc2 dgrad"),
+                  (25216, 384, 1152, 0, 1, 1, 0, "qkv dgrad"), (1536, 384, 25216, 1, 1, 0, ops.EPI_ATOMIC, "fc1 wgrad"), (384, 1536, 25216, 1, 1, 0, ops.EPI_ATOMIC, "fc2 wgrad"),
+                  (1152, 384, 25216, 1, 1, 0, ops.EPI_ATOMIC, "qkv wgrad"), (384, 384, 25216, 1, 1, 0, ops.EPI_ATOMIC, "proj wgrad"), (8192, 8192, 8192, 0, 0, 1, 0, "square 8k")]
+        for (M, N, K, amn, bmn, splits, fl, tag) in shapes:
+            A = rn(K, M) if amn else rn(M, K); B = rn(K, N) if bmn else rn(N, K); D = torch.zeros(M, N, device=dev)
+            aux = torch.empty(M, N, device=dev) if fl & ops.EPI_GELU else None
+            bias = rn(N) if fl & ops.EPI_GELU else None
+            Ao, Bo = ops.operand(A, mn_major=bool(amn)), ops.operand(B, mn_major=bool(bmn))
+            for sp in ([1] if splits else [4, 8, 16]):
+                for _ in range(3): ops.gemm(Ao, Bo, D, M, N, K, splits=sp, flags=fl, aux=aux, bias=bias)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10): ops.gemm(Ao, Bo, D, M, N, K, splits=sp, flags=fl, aux=aux, bias=bias)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                print(f"  perf2[{os.environ.get('UVC_GEMM_V2','1')}/{os.environ.get('UVC_GEMM_V2_BN','auto')}] {tag}: {M}x{N}x{K} splits={sp} {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     print(f"CASE {case}: {'PASS' if ok else 'FAIL'}", flush=True)
     return ok
 

@@ -14,6 +14,7 @@
 //
 // Replaces: models/model_distilled.py:116,122,149,175,179,184,187,522 and their autograd backward.
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace uvc {
 
@@ -32,6 +33,8 @@ struct alignas(64) GemmKParams {
   int M, N, K, nb1, nb2, splits, flags;
   int a_mn, b_mn;
   int a_use1, a_use2, b_use1, b_use2;   // operand varies with batch index i1 / i2 (else coordinate 0)
+  int a_grp, b_grp;                     // v2: MN-major operand described by a grouped tensor map (one TMA op per stage)
+  int m_tiles, n_tiles, units;          // v2 (persistent CTA-pair kernel): 256-row x BN-column tiles, units = tiles * splits
 };
 
 template <int BN, int STAGES>
@@ -89,13 +92,13 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      const int za1 = p.a_use1 ? i1 : 0, za2 = p.a_use2 ? i2 : 0;
-      const int zb1 = p.b_use1 ? i1 : 0, zb2 = p.b_use2 ? i2 : 0;
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    // the whole warp walks the loop (uniform control flow keeps addresses in uniform registers); one elected lane issues
+    const int za1 = p.a_use1 ? i1 : 0, za2 = p.a_use2 ? i2 : 0;
+    const int zb1 = p.b_use1 ? i1 : 0, zb2 = p.b_use2 ? i2 : 0;
+    int s = 0; uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
         const int k0 = (kb0 + it) * BK;
         const uint32_t sA = smem_base + s * Cfg::STAGE_BYTES;
@@ -107,41 +110,42 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
           for (int c = 0; c < BM / 32; ++c) tma_load_4d(sA + c * 4096, &p.tmA, full_bar(s), m0 + c * 32, k0, za1, za2);
         }
         if (!p.b_mn) {
-          if (BN <= 256) {
-            // a TMA box dimension is limited to 256 rows
-            tma_load_4d(sB, &p.tmB, full_bar(s), k0, n0, zb1, zb2);
-          }
+          tma_load_4d(sB, &p.tmB, full_bar(s), k0, n0, zb1, zb2);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) tma_load_4d(sB + c * 4096, &p.tmB, full_bar(s), n0 + c * 32, k0, zb1, zb2);
         }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4  (cute/arch/mma_sm100_desc.hpp bit layout)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sA = smem_base + s * Cfg::STAGE_BYTES;
-        const uint32_t sB = sA + Cfg::A_BYTES;
+    // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4  (cute/arch/mma_sm100_desc.hpp bit layout).  The smem descriptors are
+    // split into a constant high word and a low word advanced by one add per k-slice / stage (see umma_desc_lo).
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_hi = p.a_mn ? umma_desc_hi(512, 1) : umma_desc_hi(1024, 2);
+    const uint32_t b_hi = p.b_mn ? umma_desc_hi(512, 1) : umma_desc_hi(1024, 2);
+    const uint32_t a_k = p.a_mn ? 64u : 2u, b_k = p.b_mn ? 64u : 2u;
+    const uint32_t a_lo0 = umma_desc_lo(smem_base, p.a_mn ? 4096u : 16u);
+    const uint32_t b_lo0 = umma_desc_lo(smem_base + Cfg::A_BYTES, p.b_mn ? 4096u : 16u);
+    int s = 0; uint32_t ph = 0, acc = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 8; ++k4) {
-          const uint64_t adesc = p.a_mn ? umma_smem_desc(sA + k4 * 1024, 4096, 512, 1)
-                                        : umma_smem_desc(sA + k4 * 32, 16, 1024, 2);
-          const uint64_t bdesc = p.b_mn ? umma_smem_desc(sB + k4 * 1024, 4096, 512, 1)
-                                        : umma_smem_desc(sB + k4 * 32, 16, 1024, 2);
-          umma_tf32(tmem_base, adesc, bdesc, idesc, (it | k4) != 0 ? 1u : 0u);
-        }
+        for (int k4 = 0; k4 < BK / 8; ++k4) umma_tf32_lh(tmem_base, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
         umma_commit(empty_bar(s));     // frees this smem stage once the MMAs above have read it
       }
-      umma_commit(tmem_full_bar);      // accumulator complete
+      __syncwarp();
+      acc = 1u;
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
     }
+    if (elect_one()) umma_commit(tmem_full_bar);      // accumulator complete
     __syncwarp();
   } else {
     // ===================== epilogue =====================
@@ -254,6 +258,263 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
   }
 }
 
+
+// ====================================================================================================================
+// v2: persistent CTA-PAIR kernel (tcgen05 cta_group::2).  A cluster of two CTAs (one per SM of a TPC) owns one
+// 256 x BN output tile at a time: CTA r stages rows [128 r, 128 r + 128) of A and rows [BN/2 r, BN/2 r + BN/2) of B, so
+// every operand byte is fetched from L2 once per PAIR (half the shared-memory fill traffic of the 128 x 128 kernel,
+// which on fp32 operands is what bounds it), the leader CTA's elected thread issues 256 x BN x 8 MMAs, and each CTA's
+// TMEM receives its own 128 accumulator rows.  The grid is one pair per two SMs and loops over work units
+// (tile x split-K slice, N fastest so concurrently running pairs share the same A rows in L2); the accumulator is
+// double-buffered in TMEM (2 x BN columns), so the epilogue of unit i overlaps the main loop of unit i + 1.
+//
+//   warp 0    : TMA producer (both CTAs; completion bytes land on the LEADER's full barrier)
+//   warp 1    : TMEM allocator (both CTAs) + MMA issuer (leader only; commits are multicast to both CTAs' barriers)
+//   warps 2-9 : epilogue, two warps per TMEM lane quadrant (each takes half of the BN columns):
+//               tcgen05.ld 32 lanes x 32 columns -> XOR-swizzled 4 KB shared staging (transpose) -> every global access of
+//               the fused epilogue (bias / GELU (+aux) / GELU' / residual / TF32 rounding / store or red.add) is a fully
+//               coalesced 128-bit access: 8 lanes cover 128 contiguous bytes of one output row.
+// ====================================================================================================================
+constexpr int kThreads2 = 320;
+constexpr int kEpiWarps2 = 8;
+
+template <int BN, int STAGES>
+struct Gemm2Cfg {
+  static constexpr int HALF_N = BN / 2;
+  static constexpr int A_BYTES = 128 * BK * 4;
+  static constexpr int B_BYTES = HALF_N * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STG_BYTES = kEpiWarps2 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN, STAGES>;
+  constexpr int HALF_N = Cfg::HALF_N;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * STAGES + 2 + a); };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps2); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int nkb_total = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    // The whole warp walks the loop (uniform control flow), one elected lane issues; a k-block costs a wait, an expect_tx and two TMA issues.
+    {
+      const uint32_t full0_leader = mapa_cluster(full_bar(0), 0);
+      int s = 0; uint32_t ph = 0;
+      for (int u = pair; u < p.units; u += npairs) {
+        const int tile = u % tiles, split = u / tiles;
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int m0 = mt * 256 + (int)rank * 128;
+        const int n0 = nt * BN + (int)rank * HALF_N;
+        const int kb0 = (int)(((long long)nkb_total * split) / p.splits);
+        const int kb1 = (int)(((long long)nkb_total * (split + 1)) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
+            const uint32_t fb = full0_leader + 8u * s;
+            const int k0 = kb * BK;
+            const uint32_t sA = smem_base + s * Cfg::STAGE_BYTES;
+            const uint32_t sB = sA + Cfg::A_BYTES;
+            if constexpr (!A_MN) {
+              tma_load_4d_2sm(sA, &p.tmA, fb, k0, m0, 0, 0);
+            } else {
+              if (p.a_grp) {
+                tma_load_4d_2sm(sA, &p.tmA, fb, 0, k0, m0 >> 5, 0);            // one box = 4 groups of 32 (mn) x 32 (k)
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) tma_load_4d_2sm(sA + c * 4096, &p.tmA, fb, m0 + c * 32, k0, 0, 0);
+              }
+            }
+            if constexpr (!B_MN) {
+              tma_load_4d_2sm(sB, &p.tmB, fb, k0, n0, 0, 0);
+            } else {
+              if (p.b_grp) {
+                tma_load_4d_2sm(sB, &p.tmB, fb, 0, k0, n0 >> 5, 0);
+              } else {
+#pragma unroll
+                for (int c = 0; c < HALF_N / 32; ++c) tma_load_4d_2sm(sB + c * 4096, &p.tmB, fb, n0 + c * 32, k0, 0, 0);
+              }
+            }
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    // A single thread feeds the tensor cores of both SMs; one 256 x BN x 8 MMA takes BN/2 cycles, so the loop body must
+    // stay far below 2*BN cycles per k-block: descriptors are split into a constant high word and a low word advanced by
+    // one add (stage: STAGE_BYTES/16, k-slice: 2 (K-major, 32 B) or 64 (MN-major, 8 rows of 128 B)).
+    if (rank == 0) {
+      // the whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); one elected lane issues
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t a_hi = A_MN ? ((512u >> 4) | (1u << 14) | (1u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
+      constexpr uint32_t b_hi = B_MN ? ((512u >> 4) | (1u << 14) | (1u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
+      constexpr uint32_t a_k = A_MN ? 64u : 2u, b_k = B_MN ? 64u : 2u;
+      const uint32_t a_lo0 = umma_desc_lo(smem_base, A_MN ? 4096u : 16u);
+      const uint32_t b_lo0 = umma_desc_lo(smem_base + Cfg::A_BYTES, B_MN ? 4096u : 16u);
+      int s = 0; uint32_t ph = 0, ac = 0;
+      for (int u = pair; u < p.units; u += npairs, ++ac) {
+        const int split = u / tiles;
+        const int kb0 = (int)(((long long)nkb_total * split) / p.splits);
+        const int kb1 = (int)(((long long)nkb_total * (split + 1)) / p.splits);
+        const uint32_t a = ac & 1u, aph = (ac >> 1) & 1u;
+        mbar_wait(tempty_bar(a), aph ^ 1u);            // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        uint32_t acc = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 8; ++k4) umma_tf32_2sm_lh(d_tmem, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+            umma_commit_2sm(empty_bar(s), 3);          // frees this smem stage in BOTH CTAs
+          }
+          __syncwarp();
+          acc = 1u;
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (elect_one()) umma_commit_2sm(tfull_bar(a), 3);   // accumulator stage complete: wake both CTAs' epilogues
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                            // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                          // which half of the BN columns
+    const uint32_t stg = stg_base + ew * 4096;
+    const int flags = p.flags;
+    float alpha = p.alpha, beta = p.beta;
+    if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    if (p.beta_dev) beta *= __ldg(p.beta_dev);
+    const int rl = lane >> 3, cc = lane & 7;
+    const uint32_t tempty_leader = mapa_cluster(tempty_bar(0), 0);
+    uint32_t ac = 0;
+    for (int u = pair; u < p.units; u += npairs, ++ac) {
+      const int tile = u % tiles, split = u / tiles;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int row_base = mt * 256 + (int)rank * 128 + q * 32;
+      const bool first_split = (split == 0);
+      const uint32_t a = ac & 1u, aph = (ac >> 1) & 1u;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+      if (row_base < p.M) {
+#pragma unroll 1
+        for (int c = 0; c < HALF_N / 32; ++c) {
+          const int col_t = half * HALF_N + c * 32;
+          const int col0 = nt * BN + col_t;
+          if (col0 >= p.N) break;                      // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + (uint32_t)col_t, r);
+          tmem_ld_wait();
+          // transpose through the warp's staging tile: lane = row, 16 B chunk index XOR (row & 7)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = stg + lane * 128 + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+          }
+          __syncwarp();
+          const int gcol = col0 + cc * 4;
+          const bool colok = gcol < p.N;               // N % 4 == 0: a float4 is entirely in or out
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if ((flags & UVC_EPI_BIAS) && first_split && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+          float4 rr[8], xx[8];
+          if ((flags & UVC_EPI_RESIDUAL) && first_split) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int grow = row_base + i * 4 + rl;
+              rr[i] = (colok && grow < p.M) ? *reinterpret_cast<const float4*>(p.R + (long long)grow * p.ldr + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (flags & UVC_EPI_GELU_BWD) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int grow = row_base + i * 4 + rl;
+              xx[i] = (colok && grow < p.M) ? *reinterpret_cast<const float4*>(p.aux + (long long)grow * p.ldaux + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row_l = i * 4 + rl;
+            const int grow = row_base + row_l;
+            float4 v;
+            const uint32_t addr = stg + row_l * 128 + (((uint32_t)cc ^ ((uint32_t)row_l & 7u)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+            if (!(colok && grow < p.M)) continue;
+            v.x = v.x * alpha + b4.x; v.y = v.y * alpha + b4.y; v.z = v.z * alpha + b4.z; v.w = v.w * alpha + b4.w;
+            if (flags & UVC_EPI_GELU) {
+              if (p.aux) *reinterpret_cast<float4*>(p.aux + (long long)grow * p.ldaux + gcol) = v;
+              v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+            }
+            if (flags & UVC_EPI_GELU_BWD) {
+              v.x *= gelu_grad_f(xx[i].x); v.y *= gelu_grad_f(xx[i].y); v.z *= gelu_grad_f(xx[i].z); v.w *= gelu_grad_f(xx[i].w);
+            }
+            if ((flags & UVC_EPI_RESIDUAL) && first_split) {
+              v.x += beta * rr[i].x; v.y += beta * rr[i].y; v.z += beta * rr[i].z; v.w += beta * rr[i].w;
+            }
+            if (flags & UVC_EPI_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+            float* dptr = p.D + (long long)grow * p.ldd + gcol;
+            if (flags & UVC_EPI_ATOMIC) red_add_v4(dptr, v.x, v.y, v.z, v.w);
+            else *reinterpret_cast<float4*>(dptr) = v;
+          }
+          __syncwarp();                                // staging tile is rewritten by the next chunk
+        }
+      }
+      // this warp's TMEM reads of the stage are complete (tcgen05.wait::ld above): hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                                  // nobody exits (or frees TMEM) while the pair still works
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -296,6 +557,21 @@ static int make_tmap(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K,
   return UVC_OK;
 }
 
+// MN-major operand [K rows][MN cols] viewed as (32 mn, K, MN/32 groups): ONE TMA box of 32 x 32 x `groups` lands `groups` consecutive
+// 4 KB swizzle atoms [g][k][mn] in shared memory -- the layout the MN-major UMMA descriptor walks (LBO = 4096 B between groups).
+// Returns 1 when the view is not expressible (MN % 32 != 0, or the driver rejects the overlapping strides): caller falls back to 32 x 32 boxes.
+static int make_tmap_grouped(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K, int groups) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  if (!enc || !op.mn_major || (rows_mn & 31) || op.ld <= 0 || (op.ld & 3) || (reinterpret_cast<uintptr_t>(op.ptr) & 15)) return 1;
+  cuuint64_t dims[4] = {32, (cuuint64_t)K, (cuuint64_t)(rows_mn / 32), 1};
+  cuuint64_t strides[3] = {(cuuint64_t)op.ld * 4, 128, (cuuint64_t)op.ld * 4 * (cuuint64_t)K};
+  cuuint32_t box[4] = {32, 32, (cuuint32_t)groups, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 template <int BN, int STAGES>
 static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN, STAGES>;
@@ -307,6 +583,78 @@ static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   }
   gemm_tf32_kernel<BN, STAGES><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(kp);
   return check_launch("gemm_tf32_kernel");
+}
+
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch2m(const GemmKParams& kp, int pairs, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN><<<dim3(2 * pairs), kThreads2, Cfg::SMEM_BYTES, st>>>(kp);
+  return check_launch("gemm2_tf32_kernel");
+}
+template <int BN, int STAGES>
+static int launch2(const GemmKParams& kp, int pairs, cudaStream_t st) {
+  if (kp.a_mn) return kp.b_mn ? launch2m<BN, STAGES, true, true>(kp, pairs, st) : launch2m<BN, STAGES, true, false>(kp, pairs, st);
+  return kp.b_mn ? launch2m<BN, STAGES, false, true>(kp, pairs, st) : launch2m<BN, STAGES, false, false>(kp, pairs, st);
+}
+
+static int sm_pairs() {
+  static int pairs = 0;
+  if (pairs == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+    pairs = sms / 2;
+  }
+  return pairs;
+}
+
+// 0 = always the 128 x 128 kernel, 1 = pick per shape (default), 2 = CTA-pair kernel whenever it is legal
+static int gemm_v2_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("UVC_GEMM_V2");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
+static int gemm_v2_force_bn() {
+  static int bn = -1;
+  if (bn < 0) {
+    const char* e = getenv("UVC_GEMM_V2_BN");
+    bn = e ? atoi(e) : 0;
+  }
+  return bn;
+}
+
+// the CTA-pair kernel needs unbatched operands and 16 B-aligned rows everywhere its epilogue touches
+static bool v2_legal(const uvc_gemm_args& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (a.nb1 != 1 || a.nb2 != 1 || a.K < 1) return false;
+  if ((a.N & 3) || (a.ldd & 3) || !al16(a.D)) return false;
+  if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
+  if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
+  if ((a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux && ((a.ldaux & 3) || !al16(a.aux))) return false;
+  return true;
+}
+
+// tile width minimising (waves over the SM pairs) x (tile cost ~ BN); ties go to the wider tile (fewer operand re-reads)
+static int v2_pick_bn(int M, int N, int splits, int pairs) {
+  const int mt = (M + 255) / 256;
+  int best = 0; long long best_cost = 0;
+  const int cand[3] = {256, 192, 128};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    const long long units = (long long)mt * ((N + bn - 1) / bn) * splits;
+    const long long cost = ((units + pairs - 1) / pairs) * (bn + 24);     // + fixed per-unit overhead (pipeline fill, barriers)
+    if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
@@ -325,10 +673,19 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
 
   GemmKParams kp;
   constexpr int BN = 128;
-  int rc = make_tmap(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A");
-  if (rc) return rc;
-  rc = make_tmap(&kp.tmB, a.B, a.N, a.K, a.nb1, a.nb2, BN, "B");
-  if (rc) return rc;
+  const int mode = gemm_v2_mode();
+  const int pairs = sm_pairs();
+  int bn2 = 0;
+  if (mode > 0 && v2_legal(a) && (mode == 2 || (a.M >= 512 && a.N >= 128))) {
+    bn2 = gemm_v2_force_bn() ? gemm_v2_force_bn() : v2_pick_bn(a.M, a.N, splits, pairs);
+    UVC_REQUIRE(bn2 == 128 || bn2 == 192 || bn2 == 256, UVC_ERR_BAD_ARG, "gemm: UVC_GEMM_V2_BN must be 128, 192 or 256");
+  }
+  kp.a_grp = kp.b_grp = 0;
+  int rc = UVC_OK;
+  if (bn2 && a.A.mn_major && make_tmap_grouped(&kp.tmA, a.A, a.M, a.K, 4) == 0) kp.a_grp = 1;
+  else if ((rc = make_tmap(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A"))) return rc;
+  if (bn2 && a.B.mn_major && make_tmap_grouped(&kp.tmB, a.B, a.N, a.K, bn2 / 64) == 0) kp.b_grp = 1;
+  else if ((rc = make_tmap(&kp.tmB, a.B, a.N, a.K, a.nb1, a.nb2, bn2 ? bn2 / 2 : BN, "B"))) return rc;
   kp.D = a.D; kp.ldd = a.ldd; kp.d_bs1 = a.d_bs1; kp.d_bs2 = a.d_bs2;
   kp.bias = a.bias;
   kp.R = (a.flags & UVC_EPI_RESIDUAL) ? a.R : nullptr; kp.ldr = a.ldr; kp.r_bs1 = a.r_bs1; kp.r_bs2 = a.r_bs2;
@@ -339,6 +696,21 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.a_mn = a.A.mn_major ? 1 : 0; kp.b_mn = a.B.mn_major ? 1 : 0;
   kp.a_use1 = a.A.bs1 != 0; kp.a_use2 = a.A.bs2 != 0; kp.b_use1 = a.B.bs1 != 0; kp.b_use2 = a.B.bs2 != 0;
 
+  if (bn2) {
+    kp.m_tiles = (a.M + 255) / 256; kp.n_tiles = (a.N + bn2 - 1) / bn2;
+    const long long units = (long long)kp.m_tiles * kp.n_tiles * splits;
+    UVC_REQUIRE(units < (1ll << 30), UVC_ERR_BAD_SHAPE, "gemm: too many work units (%lld)", units);
+    kp.units = (int)units;
+    const int np = units < pairs ? (int)units : pairs;
+    const bool prof2 = prof_enabled();
+    if (prof2) prof_begin(st, 2.0 * a.M * a.N * (double)a.K);
+    if (bn2 == 256) rc = launch2<256, 6>(kp, np, st);
+    else if (bn2 == 192) rc = launch2<192, 6>(kp, np, st);
+    else rc = launch2<128, 8>(kp, np, st);
+    if (prof2) prof_end(st);
+    return rc;
+  }
+  kp.m_tiles = kp.n_tiles = kp.units = 0;
   const long long gz = (long long)a.nb1 * a.nb2 * splits;
   const long long gy = (a.M + BM - 1) / BM;
   UVC_REQUIRE(gz <= 65535 && gy <= 65535, UVC_ERR_BAD_SHAPE, "gemm: grid too large (m tiles %lld, batch*splits %lld)", gy, gz);
