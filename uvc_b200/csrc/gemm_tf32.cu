@@ -289,7 +289,9 @@ struct Gemm2Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+enum { kEpiPlain = 0, kEpiGelu = 1, kEpiGeluBwd = 2 };
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
   using Cfg = Gemm2Cfg<BN, STAGES>;
@@ -419,6 +421,8 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     __syncwarp();
   } else {
     // ===================== epilogue (both CTAs) =====================
+    // MODE is a template parameter so the GELU / GELU' code only exists in the instantiations that need it: with every mode
+    // inlined the loop body was 2.5 K instructions (40 KB) and the eight epilogue warps were instruction-fetch bound.
     const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                          // which half of the BN columns
@@ -428,74 +432,77 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
     if (p.beta_dev) beta *= __ldg(p.beta_dev);
     const int rl = lane >> 3, cc = lane & 7;
+    const uint32_t st_row = stg + lane * 128;                                        // staging: this lane's TMEM row
+    const uint32_t ld_even = stg + rl * 128 + (((uint32_t)cc ^ (uint32_t)rl) << 4);  // rows i*4 + rl, i even: (row & 7) = rl
+    const uint32_t ld_odd = stg + rl * 128 + (((uint32_t)cc ^ (uint32_t)(rl + 4)) << 4);
     const uint32_t tempty_leader = mapa_cluster(tempty_bar(0), 0);
+    const bool do_round = (flags & UVC_EPI_ROUND_TF32) != 0, do_atomic = (flags & UVC_EPI_ATOMIC) != 0;
     uint32_t ac = 0;
     for (int u = pair; u < p.units; u += npairs, ++ac) {
       const int tile = u % tiles, split = u / tiles;
       const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
       const int row_base = mt * 256 + (int)rank * 128 + q * 32;
       const bool first_split = (split == 0);
+      const bool do_bias = (flags & UVC_EPI_BIAS) && first_split, do_res = (flags & UVC_EPI_RESIDUAL) && first_split;
       const uint32_t a = ac & 1u, aph = (ac >> 1) & 1u;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       if (row_base < p.M) {
+        const int rows_left = p.M - row_base - rl;     // row i*4 + rl is valid iff i*4 < rows_left
 #pragma unroll 1
         for (int c = 0; c < HALF_N / 32; ++c) {
           const int col_t = half * HALF_N + c * 32;
           const int col0 = nt * BN + col_t;
           if (col0 >= p.N) break;                      // warp-uniform
+          if (flags & (1 << 29)) break;                // bring-up: no epilogue body
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + (uint32_t)col_t, r);
           tmem_ld_wait();
           // transpose through the warp's staging tile: lane = row, 16 B chunk index XOR (row & 7)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint32_t addr = stg + lane * 128 + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4);
+            const uint32_t addr = st_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
           }
           __syncwarp();
           const int gcol = col0 + cc * 4;
           const bool colok = gcol < p.N;               // N % 4 == 0: a float4 is entirely in or out
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if ((flags & UVC_EPI_BIAS) && first_split && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-          float4 rr[8], xx[8];
-          if ((flags & UVC_EPI_RESIDUAL) && first_split) {
+          if (do_bias && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+          const long long roff = (long long)(row_base + rl);
+          float* dptr = p.D + roff * p.ldd + gcol;
+          const float* rptr = p.R + roff * p.ldr + gcol;
+          float* xptr = p.aux + roff * p.ldaux + gcol;
+          float4 rr[8];
+          if (MODE == kEpiGeluBwd) {                   // gelu'(pre-activation) factors, loaded up front (8 independent 128-bit loads in flight)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int grow = row_base + i * 4 + rl;
-              rr[i] = (colok && grow < p.M) ? *reinterpret_cast<const float4*>(p.R + (long long)grow * p.ldr + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (flags & UVC_EPI_GELU_BWD) {
+            for (int i = 0; i < 8; ++i)
+              rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(xptr + (long long)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (do_res) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int grow = row_base + i * 4 + rl;
-              xx[i] = (colok && grow < p.M) ? *reinterpret_cast<const float4*>(p.aux + (long long)grow * p.ldaux + gcol) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int i = 0; i < 8; ++i)
+              rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(rptr + (long long)i * 4 * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row_l = i * 4 + rl;
-            const int grow = row_base + row_l;
             float4 v;
-            const uint32_t addr = stg + row_l * 128 + (((uint32_t)cc ^ ((uint32_t)row_l & 7u)) << 4);
+            const uint32_t addr = ((i & 1) ? ld_odd : ld_even) + i * 512;
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-            if (!(colok && grow < p.M)) continue;
-            v.x = v.x * alpha + b4.x; v.y = v.y * alpha + b4.y; v.z = v.z * alpha + b4.z; v.w = v.w * alpha + b4.w;
-            if (flags & UVC_EPI_GELU) {
-              if (p.aux) *reinterpret_cast<float4*>(p.aux + (long long)grow * p.ldaux + gcol) = v;
+            if (!(colok && i * 4 < rows_left) || (flags & (1 << 30))) continue;   // (bit 30: bring-up, no global traffic)
+            v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y); v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
+            if (MODE == kEpiGelu) {
+              if (p.aux) *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = v;
               v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
             }
-            if (flags & UVC_EPI_GELU_BWD) {
-              v.x *= gelu_grad_f(xx[i].x); v.y *= gelu_grad_f(xx[i].y); v.z *= gelu_grad_f(xx[i].z); v.w *= gelu_grad_f(xx[i].w);
+            if (MODE == kEpiGeluBwd) {
+              v.x *= gelu_grad_f(rr[i].x); v.y *= gelu_grad_f(rr[i].y); v.z *= gelu_grad_f(rr[i].z); v.w *= gelu_grad_f(rr[i].w);
+            } else if (do_res) {
+              v.x = fmaf(beta, rr[i].x, v.x); v.y = fmaf(beta, rr[i].y, v.y); v.z = fmaf(beta, rr[i].z, v.z); v.w = fmaf(beta, rr[i].w, v.w);
             }
-            if ((flags & UVC_EPI_RESIDUAL) && first_split) {
-              v.x += beta * rr[i].x; v.y += beta * rr[i].y; v.z += beta * rr[i].z; v.w += beta * rr[i].w;
-            }
-            if (flags & UVC_EPI_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            float* dptr = p.D + (long long)grow * p.ldd + gcol;
-            if (flags & UVC_EPI_ATOMIC) red_add_v4(dptr, v.x, v.y, v.z, v.w);
-            else *reinterpret_cast<float4*>(dptr) = v;
+            if (do_round) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+            float* dp = dptr + (long long)i * 4 * p.ldd;
+            if (do_atomic) red_add_v4(dp, v.x, v.y, v.z, v.w);
+            else *reinterpret_cast<float4*>(dp) = v;
           }
           __syncwarp();                                // staging tile is rewritten by the next chunk
         }
@@ -586,17 +593,23 @@ static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
 }
 
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-static int launch2m(const GemmKParams& kp, int pairs, cudaStream_t st) {
+template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
+static int launch2k(const GemmKParams& kp, int pairs, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN><<<dim3(2 * pairs), kThreads2, Cfg::SMEM_BYTES, st>>>(kp);
+  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE><<<dim3(2 * pairs), kThreads2, Cfg::SMEM_BYTES, st>>>(kp);
   return check_launch("gemm2_tf32_kernel");
+}
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+static int launch2m(const GemmKParams& kp, int pairs, cudaStream_t st) {
+  if (kp.flags & UVC_EPI_GELU) return launch2k<BN, STAGES, A_MN, B_MN, kEpiGelu>(kp, pairs, st);
+  if (kp.flags & UVC_EPI_GELU_BWD) return launch2k<BN, STAGES, A_MN, B_MN, kEpiGeluBwd>(kp, pairs, st);
+  return launch2k<BN, STAGES, A_MN, B_MN, kEpiPlain>(kp, pairs, st);
 }
 template <int BN, int STAGES>
 static int launch2(const GemmKParams& kp, int pairs, cudaStream_t st) {
@@ -636,6 +649,8 @@ static int gemm_v2_force_bn() {
 static bool v2_legal(const uvc_gemm_args& a) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a.nb1 != 1 || a.nb2 != 1 || a.K < 1) return false;
+  if ((a.flags & UVC_EPI_GELU) && (a.flags & UVC_EPI_GELU_BWD)) return false;
+  if ((a.flags & UVC_EPI_GELU_BWD) && (a.flags & UVC_EPI_RESIDUAL)) return false;
   if ((a.N & 3) || (a.ldd & 3) || !al16(a.D)) return false;
   if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
   if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
@@ -677,7 +692,15 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const int pairs = sm_pairs();
   int bn2 = 0;
   if (mode > 0 && v2_legal(a) && (mode == 2 || (a.M >= 512 && a.N >= 128))) {
-    bn2 = gemm_v2_force_bn() ? gemm_v2_force_bn() : v2_pick_bn(a.M, a.N, splits, pairs);
+    // split-K (caller allows it by passing splits > 1 with UVC_EPI_ATOMIC): the persistent kernel wants ~2 units per SM pair
+    if (splits > 1 && !getenv("UVC_GEMM_V2_KEEP_SPLITS")) {
+      const int bn0 = gemm_v2_force_bn() ? gemm_v2_force_bn() : 128;
+      const int tiles2 = ((a.M + 255) / 256) * ((a.N + bn0 - 1) / bn0);
+      int sp = (2 * pairs + tiles2 / 2) / tiles2;
+      if (sp > nkb / 8) sp = nkb / 8;              // keep >= 8 k-blocks per slice
+      splits = sp < 1 ? 1 : sp;
+    }
+    bn2 = gemm_v2_force_bn() ? gemm_v2_force_bn() : (splits > 1 ? 128 : v2_pick_bn(a.M, a.N, splits, pairs));
     UVC_REQUIRE(bn2 == 128 || bn2 == 192 || bn2 == 256, UVC_ERR_BAD_ARG, "gemm: UVC_GEMM_V2_BN must be 128, 192 or 256");
   }
   kp.a_grp = kp.b_grp = 0;
@@ -693,6 +716,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev;
   kp.alpha = a.alpha; kp.beta = a.beta;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.nb1 = a.nb1; kp.nb2 = a.nb2; kp.splits = splits; kp.flags = a.flags;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("UVC_GEMM_DBG"); dbg = e ? atoi(e) : 0; } kp.flags |= dbg << 29; }   // bring-up experiments only
   kp.a_mn = a.A.mn_major ? 1 : 0; kp.b_mn = a.B.mn_major ? 1 : 0;
   kp.a_use1 = a.A.bs1 != 0; kp.a_use2 = a.A.bs2 != 0; kp.b_use1 = a.B.bs1 != 0; kp.b_use2 = a.B.bs2 != 0;
 
