@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 2
+#define UVC_ABI_VERSION 3
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -79,8 +79,10 @@ enum {
   UVC_EPI_GELU_BWD = 4,    /* v *= gelu'(aux[row,col]) */
   UVC_EPI_RESIDUAL = 8,    /* v += beta * R[row,col] */
   UVC_EPI_ATOMIC = 16,     /* D += v with red.global.add (required when splits > 1) */
-  UVC_EPI_ROUND_TF32 = 32  /* round v to nearest TF32 before the store: for outputs that only feed other GEMMs (the
+  UVC_EPI_ROUND_TF32 = 32, /* round v to nearest TF32 before the store: for outputs that only feed other GEMMs (the
                               tensor core truncates its inputs, rounding here keeps the error unbiased) */
+  UVC_EPI_COLSUM = 64      /* colsum[col] += sum_rows v[row,col] (before TF32 rounding): the bias gradient of the Linear whose
+                              output gradient this GEMM produces, fused so the tensor is not re-read (fp32 atomics) */
 };
 
 typedef struct {
@@ -98,6 +100,7 @@ typedef struct {
   const float* beta_dev;   /* optional device scalar multiplied into beta */
   int32_t flags;           /* UVC_EPI_* */
   int32_t _pad;
+  float* colsum;           /* [N], accumulated into when UVC_EPI_COLSUM is set */
 } uvc_gemm_args;
 
 UVC_API int uvc_gemm_tf32(const uvc_gemm_args* args, void* stream);
@@ -118,6 +121,12 @@ UVC_API int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, c
 UVC_API int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                               const float* gamma, const float* r1, const float* r2, const float* s2_dev,
                               float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
+/* Same, and additionally cs_r1[col] += sum_rows r1[row,col], cs_out[col] += sum_rows dx[row,col] (either may be NULL): the bias gradients of
+ * the Linear layers on either side of the norm are column sums of tensors this kernel streams anyway (fc2.bias <- r1 = d(block output),
+ * attn.proj.bias <- dx = d(x1) for norm2 of models/model_distilled.py:204,243). */
+UVC_API int uvc_layernorm_bwd_cs(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                                 const float* gamma, const float* r1, const float* r2, const float* s2_dev,
+                                 float* dx, int64_t lddx, float* dgamma, float* dbeta, float* cs_r1, float* cs_out, int32_t M, int32_t C, void* stream);
 /* in-place row softmax over the first n (<= 256) columns of S[rows][ld] (models/model_distilled.py:180) */
 UVC_API int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream);
 /* dP <- scale * P .* (dP - rowsum(dP .* P)) */

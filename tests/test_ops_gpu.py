@@ -206,3 +206,42 @@ def test_clip_adamw_matches_torch(ops):
         ops.clip_adamw_(flat_p, flat_g, flat_m, flat_v, acc, 1.0, 1e-3, 0.9, 0.999, 1e-8, 0.05, step)
         for r, p, o in zip(ref, ps, offs):
             assert rel(flat_p[o:o + p.numel()].view(p.shape), r.detach()) < 1e-5
+
+@pytest.mark.parametrize("M,N,K", [(1000, 768, 192), (2048, 384, 100), (130, 36, 64)])
+def test_gemm_colsum_epilogue(ops, M, N, K):
+    """UVC_EPI_COLSUM: the bias gradient (column sums of the GEMM output) accumulated by the epilogue, plain and after GELU'."""
+    A, B = rn(M, K), rn(N, K) * 0.1
+    D = torch.empty(M, N, device="cuda"); cs = torch.ones(N, device="cuda")
+    ops.gemm(A, B, D, M, N, K, colsum=cs)
+    ref = A @ B.t()
+    assert rel(D, ref) < TF32_TOL and rel(cs - 1, ref.sum(0)) < TF32_TOL
+    u = rn(M, N, seed=5)
+    cs2 = torch.zeros(N, device="cuda")
+    ops.gemm(A, B, D, M, N, K, aux=u, flags=ops.EPI_GELU_BWD | ops.EPI_ROUND_TF32, colsum=cs2)
+    uu = u.clone().requires_grad_(True); F.gelu(uu).sum().backward()
+    ref2 = ref * uu.grad
+    assert rel(D, ref2) < TF32_TOL and rel(cs2, ref2.sum(0)) < TF32_TOL
+
+
+@pytest.mark.parametrize("M,N,K,amn,bmn,splits", [(25216, 1152, 384, 0, 0, 1), (25216, 384, 1536, 0, 1, 1), (1536, 384, 5000, 1, 1, 8), (1000, 388, 100, 0, 0, 1),
+                                                   (776, 512, 96, 1, 0, 1)])
+def test_gemm_cta_pair_kernel_shapes(ops, M, N, K, amn, bmn, splits):
+    """hot-path shapes that dispatch to the persistent CTA-pair kernel (all operand majors, ragged edges, split-K)"""
+    A = rn(K, M) if amn else rn(M, K); B = rn(K, N) if bmn else rn(N, K)
+    D = torch.zeros(M, N, device="cuda")
+    ops.gemm(ops.operand(A, mn_major=bool(amn)), ops.operand(B, mn_major=bool(bmn)), D, M, N, K, splits=splits, flags=ops.EPI_ATOMIC if splits > 1 else 0)
+    ref = (A.t() if amn else A) @ (B if bmn else B.t())
+    assert rel(D, ref) < TF32_TOL
+
+
+def test_layernorm_bwd_fused_column_sums(ops):
+    """uvc_layernorm_bwd_cs also emits the bias gradients of the neighbouring Linears (column sums of r1 and of dx)"""
+    M, Cc = 1576, 384
+    x, g, dy, r1 = rn(M, Cc) * 2 + 0.3, 1 + 0.1 * rn(Cc), rn(M, Cc, seed=2), rn(M, Cc, seed=3)
+    y, mean, rstd = ops.layernorm_fwd(x, g, 0.1 * rn(Cc, seed=1), 1e-6)
+    dx0 = ops.layernorm_bwd(dy, x, mean, rstd, g, r1=r1)
+    c1, co = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    dg, db = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, mean, rstd, g, r1=r1, dgamma=dg, dbeta=db, cs_r1=c1, cs_out=co)
+    assert torch.equal(dx, dx0)
+    assert rel(c1, r1.sum(0)) < FP32_TOL and rel(co - 1, dx0.double().sum(0).float()) < 1e-4 and rel(db, dy.sum(0)) < FP32_TOL

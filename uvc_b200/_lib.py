@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ("R", C.c_void_p), ("ldr", C.c_int64), ("r_bs1", C.c_int64), ("r_bs2", C.c_int64),
                 ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_bs1", C.c_int64), ("aux_bs2", C.c_int64),
                 ("alpha", C.c_float), ("beta", C.c_float), ("alpha_dev", C.c_void_p), ("beta_dev", C.c_void_p),
-                ("flags", C.c_int32), ("_pad", C.c_int32)]
+                ("flags", C.c_int32), ("_pad", C.c_int32), ("colsum", C.c_void_p)]
 
 
 _F = C.c_void_p   # device float*
@@ -86,14 +86,14 @@ UVC_MAX_DEPTH = 32
 # every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_tf32",
-    "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
+    "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_layernorm_bwd_cs", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
     "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
     "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
-EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32 = 1, 2, 4, 8, 16, 32
+EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM = 1, 2, 4, 8, 16, 32, 64
 
 _lib = None
 
@@ -131,6 +131,7 @@ def load():
         "uvc_gemm_tf32": [C.POINTER(GemmArgs), vp],
         "uvc_layernorm_fwd": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, i32, vp],
         "uvc_layernorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp],
+        "uvc_layernorm_bwd_cs": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp],
         "uvc_softmax_fwd": [vp, i64, i64, i32, i32, vp],
         "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, i32, vp],
         "uvc_colsum": [vp, i64, i32, i32, vp, vp, vp],

@@ -29,6 +29,7 @@ struct alignas(64) GemmKParams {
   const float* R; long long ldr, r_bs1, r_bs2;
   float* aux; long long ldaux, aux_bs1, aux_bs2;
   const float* alpha_dev; const float* beta_dev;
+  float* colsum;
   float alpha, beta;
   int M, N, K, nb1, nb2, splits, flags;
   int a_mn, b_mn;
@@ -178,6 +179,16 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
       if (nkb == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (p.colsum && !(flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD | UVC_EPI_RESIDUAL))) {
+        // fused bias gradient (fallback kernel: lane = row, so a column sum is a warp reduction per column)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = (row < p.M) ? __uint_as_float(r[j]) * alpha : 0.f;
+          if ((flags & UVC_EPI_BIAS) && first_split && col0 + j < p.N) t += (row < p.M) ? __ldg(p.bias + col0 + j) : 0.f;
+          t = warp_sum(t);
+          if (lane == 0 && col0 + j < p.N) atomicAdd(p.colsum + col0 + j, t);
+        }
       }
       if (row < p.M) {
         const bool full = (col0 + 32 <= p.N);
@@ -483,6 +494,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             for (int i = 0; i < 8; ++i)
               rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(rptr + (long long)i * 4 * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);   // fused bias gradient: column sums of this warp's 32 rows
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 v;
@@ -499,10 +511,18 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             } else if (do_res) {
               v.x = fmaf(beta, rr[i].x, v.x); v.y = fmaf(beta, rr[i].y, v.y); v.z = fmaf(beta, rr[i].z, v.z); v.w = fmaf(beta, rr[i].w, v.w);
             }
+            if (p.colsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
             if (do_round) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
             float* dp = dptr + (long long)i * 4 * p.ldd;
             if (do_atomic) red_add_v4(dp, v.x, v.y, v.z, v.w);
             else *reinterpret_cast<float4*>(dp) = v;
+          }
+          if (p.colsum) {                              // lanes with the same cc hold the same 4 columns: fold the 4 row phases, one red per 4 columns
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x, cs.y, cs.z, cs.w);
           }
           __syncwarp();                                // staging tile is rewritten by the next chunk
         }
@@ -653,6 +673,7 @@ static bool v2_legal(const uvc_gemm_args& a) {
   if ((a.flags & UVC_EPI_GELU_BWD) && (a.flags & UVC_EPI_RESIDUAL)) return false;
   if ((a.N & 3) || (a.ldd & 3) || !al16(a.D)) return false;
   if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
+  if ((a.flags & UVC_EPI_COLSUM) && !al16(a.colsum)) return false;
   if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
   if ((a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux && ((a.ldaux & 3) || !al16(a.aux))) return false;
   return true;
@@ -682,8 +703,10 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   UVC_REQUIRE(!(a.flags & UVC_EPI_BIAS) || a.bias, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_BIAS without bias");
   UVC_REQUIRE(!(a.flags & UVC_EPI_RESIDUAL) || a.R, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_RESIDUAL without R");
   UVC_REQUIRE(!(a.flags & UVC_EPI_GELU_BWD) || a.aux, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_GELU_BWD without aux");
+  UVC_REQUIRE(!(a.flags & UVC_EPI_COLSUM) || a.colsum, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_COLSUM without colsum");
   const int nkb = (a.K + BK - 1) / BK;
   int splits = a.splits;
+  const bool colsum_simple = !(a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD | UVC_EPI_RESIDUAL));
   if (splits > nkb) splits = nkb > 0 ? nkb : 1;
 
   GemmKParams kp;
@@ -691,7 +714,9 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const int mode = gemm_v2_mode();
   const int pairs = sm_pairs();
   int bn2 = 0;
-  if (mode > 0 && v2_legal(a) && (mode == 2 || (a.M >= 512 && a.N >= 128))) {
+  const bool need_v2 = (a.flags & UVC_EPI_COLSUM) && !colsum_simple;   // only the CTA-pair epilogue sums columns after a non-linear epilogue
+  UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: UVC_EPI_COLSUM with GELU / residual epilogues needs unbatched, 16 B-aligned operands");
+  if ((mode > 0 || need_v2) && v2_legal(a) && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
     // split-K (caller allows it by passing splits > 1 with UVC_EPI_ATOMIC): the persistent kernel wants ~2 units per SM pair
     if (splits > 1 && !getenv("UVC_GEMM_V2_KEEP_SPLITS")) {
       const int bn0 = gemm_v2_force_bn() ? gemm_v2_force_bn() : 128;
@@ -714,6 +739,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.R = (a.flags & UVC_EPI_RESIDUAL) ? a.R : nullptr; kp.ldr = a.ldr; kp.r_bs1 = a.r_bs1; kp.r_bs2 = a.r_bs2;
   kp.aux = (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) ? a.aux : nullptr; kp.ldaux = a.ldaux; kp.aux_bs1 = a.aux_bs1; kp.aux_bs2 = a.aux_bs2;
   kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev;
+  kp.colsum = (a.flags & UVC_EPI_COLSUM) ? a.colsum : nullptr;
   kp.alpha = a.alpha; kp.beta = a.beta;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.nb1 = a.nb1; kp.nb2 = a.nb2; kp.splits = splits; kp.flags = a.flags;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("UVC_GEMM_DBG"); dbg = e ? atoi(e) : 0; } kp.flags |= dbg << 29; }   // bring-up experiments only

@@ -12,7 +12,7 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
                   float* rstd, int M, int C, cudaStream_t st, int round_out = 0);
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st);
+                  cudaStream_t st, float* cs_r1 = nullptr, float* cs_out = nullptr);   // cs_*: fused column sums of r1 / of dx (bias gradients)
 int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int round_out = 0);
 int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int round_out = 0);
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);

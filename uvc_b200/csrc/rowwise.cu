@@ -11,8 +11,20 @@ namespace uvc {
 
 constexpr int kMaxVec = 8;   // float4 per lane -> C <= 1024
 
+// The LayerNorm kernels are templated on NV = float4 per lane (2: C <= 256, 3: C <= 384, 6: C <= 768, 8: C <= 1024) so the per-row
+// register arrays are sized for the model at hand: with a fixed 8 the backward needed ~200 registers (one 256-thread block per SM) and ran
+// at a quarter of HBM bandwidth on DeiT-Small.
+#define UVC_LN_DISPATCH(C, CALL)                         \
+  do {                                                   \
+    if ((C) <= 256) { constexpr int NV = 2; CALL; }      \
+    else if ((C) <= 384) { constexpr int NV = 3; CALL; } \
+    else if ((C) <= 768) { constexpr int NV = 6; CALL; } \
+    else { constexpr int NV = 8; CALL; }                 \
+  } while (0)
+
 // ------------------------------------------------------------------------------------------ LayerNorm fwd
 // one warp per row; two-pass moments in registers (mean, then centred variance) like ATen's RowwiseMoments.
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float* __restrict__ y, long long ldy,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C, int rnd) {
@@ -21,17 +33,17 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
   const int nv = C >> 2;
-  float4 v[kMaxVec];
+  float4 v[NV];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) { v[i] = xr[c]; s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
   }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -43,7 +55,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + i * 32;
     if (c < nv) {
       const float4 g = __ldg(g4 + c), b = __ldg(b4 + c);
@@ -63,32 +75,48 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx[row] = r1[row] + s2 * r2[row] + rstd * (g - mean(g) - xhat * mean(g * xhat)),   g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (register partials per lane -> smem -> atomics)
+// Optional fused bias gradients of the neighbouring Linears (they are column sums of tensors this kernel touches anyway):
+//   cs_r1[col] += sum_rows r1[row, col]      cs_out[col] += sum_rows dx[row, col]
+template <int NV, bool CS>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ r1, const float* __restrict__ r2,
                                                             const float* __restrict__ s2_dev, float* __restrict__ dx, long long lddx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C, int rows_per_block) {
-  __shared__ float red[2][8][32 * 4 + 4];
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cs_r1,
+                                                            float* __restrict__ cs_out, int M, int C, int rows_per_block) {
+  __shared__ float red[4][8][32 * 4 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int nv = C >> 2;
   const float s2 = (r2 && s2_dev) ? __ldg(s2_dev) : 1.0f;
-  float4 ag[kMaxVec], ab[kMaxVec];
+  float4 ag[NV], ab[NV], a1[CS ? NV : 1], ao[CS ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  if (CS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { a1[i] = make_float4(0, 0, 0, 0); ao[i] = make_float4(0, 0, 0, 0); }
+  }
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(M, row0 + rows_per_block);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = row0 + warp; row < row1; row += nwarps) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * lddy);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+    const float4* r1r = r1 ? reinterpret_cast<const float4*>(r1 + (long long)row * lddx) : nullptr;
+    const float4* r2r = r2 ? reinterpret_cast<const float4*>(r2 + (long long)row * lddx) : nullptr;
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[kMaxVec], gg[kMaxVec];
+    float4 xh[NV], gg[NV], res[NV];
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {                      // every load of the row is issued before the first reduction
       const int c = lane + i * 32;
+      res[i] = make_float4(0, 0, 0, 0);
       if (c < nv) {
         const float4 d = dyr[c], xv = xr[c], gm = __ldg(g4 + c);
+        if (r1r) {
+          res[i] = r1r[c];
+          if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
+        }
+        if (r2r) { const float4 a = r2r[c]; res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w; }
         xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
         gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
         sg += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
@@ -99,39 +127,48 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
     const float mg = warp_sum(sg) / (float)C, mgx = warp_sum(sgx) / (float)C;
     float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * lddx);
-    const float4* r1r = r1 ? reinterpret_cast<const float4*>(r1 + (long long)row * lddx) : nullptr;
-    const float4* r2r = r2 ? reinterpret_cast<const float4*>(r2 + (long long)row * lddx) : nullptr;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
         float4 o;
-        o.x = rs * (gg[i].x - mg - xh[i].x * mgx); o.y = rs * (gg[i].y - mg - xh[i].y * mgx);
-        o.z = rs * (gg[i].z - mg - xh[i].z * mgx); o.w = rs * (gg[i].w - mg - xh[i].w * mgx);
-        if (r1r) { const float4 a = r1r[c]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        if (r2r) { const float4 a = r2r[c]; o.x += s2 * a.x; o.y += s2 * a.y; o.z += s2 * a.z; o.w += s2 * a.w; }
+        o.x = res[i].x + rs * (gg[i].x - mg - xh[i].x * mgx); o.y = res[i].y + rs * (gg[i].y - mg - xh[i].y * mgx);
+        o.z = res[i].z + rs * (gg[i].z - mg - xh[i].z * mgx); o.w = res[i].w + rs * (gg[i].w - mg - xh[i].w * mgx);
+        if (CS) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
         dxr[c] = o;
       }
     }
   }
-  if (!dgamma) return;
+  if (!dgamma && !(CS && (cs_r1 || cs_out))) return;
   // cross-warp reduction of the per-lane column partials, one 128-column slab (i) at a time
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     if (i * 32 >= nv) break;
     __syncthreads();
     float* rg = &red[0][warp][lane * 4];
     float* rb = &red[1][warp][lane * 4];
     rg[0] = ag[i].x; rg[1] = ag[i].y; rg[2] = ag[i].z; rg[3] = ag[i].w;
     rb[0] = ab[i].x; rb[1] = ab[i].y; rb[2] = ab[i].z; rb[3] = ab[i].w;
+    if (CS) {
+      float* q1 = &red[2][warp][lane * 4];
+      float* qo = &red[3][warp][lane * 4];
+      q1[0] = a1[i].x; q1[1] = a1[i].y; q1[2] = a1[i].z; q1[3] = a1[i].w;
+      qo[0] = ao[i].x; qo[1] = ao[i].y; qo[2] = ao[i].z; qo[3] = ao[i].w;
+    }
     __syncthreads();
     if (threadIdx.x < 128) {
       const int col = i * 128 + threadIdx.x;
       if (col < C) {
-        float sgm = 0.f, sbt = 0.f;
-        for (int w = 0; w < nwarps; ++w) { sgm += red[0][w][threadIdx.x]; sbt += red[1][w][threadIdx.x]; }
-        atomicAdd(dgamma + col, sgm);
-        atomicAdd(dbeta + col, sbt);
+        float sgm = 0.f, sbt = 0.f, s1 = 0.f, so = 0.f;
+        for (int w = 0; w < nwarps; ++w) {
+          sgm += red[0][w][threadIdx.x]; sbt += red[1][w][threadIdx.x];
+          if (CS) { s1 += red[2][w][threadIdx.x]; so += red[3][w][threadIdx.x]; }
+        }
+        if (dgamma) { atomicAdd(dgamma + col, sgm); atomicAdd(dbeta + col, sbt); }
+        if (CS) {
+          if (cs_r1) atomicAdd(cs_r1 + col, s1);
+          if (cs_out) atomicAdd(cs_out + col, so);
+        }
       }
     }
   }
@@ -181,7 +218,41 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------ column sums (bias grads)
-// out[col] += scale * sum_rows X[row, col]; thread per column, grid.y row chunks, atomics to combine
+// out[col] += scale * sum_rows X[row, col].  A block of 256 threads covers 128 columns (32 float4 lanes) x 8 row phases; each thread
+// keeps 4 independent 128-bit loads in flight, the 8 phases are combined through shared memory and one atomicAdd per column and block
+// lands in `out`.  N % 4 == 0 takes this path; ragged N falls back to the scalar kernel below.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ X, long long ld, int M, int N, const float* __restrict__ scale_dev,
+                                                      float* __restrict__ out, int rows_per_block) {
+  __shared__ float4 red[8][32];
+  const int cl = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cl) * 4;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float4 a = make_float4(0, 0, 0, 0), b = a, c = a, d = a;
+  if (col < N) {
+    const float* base = X + col;
+    int r = r0 + ph;
+    for (; r + 24 < r1; r += 32) {
+      const float4 v0 = *reinterpret_cast<const float4*>(base + (long long)r * ld), v1 = *reinterpret_cast<const float4*>(base + (long long)(r + 8) * ld);
+      const float4 v2 = *reinterpret_cast<const float4*>(base + (long long)(r + 16) * ld), v3 = *reinterpret_cast<const float4*>(base + (long long)(r + 24) * ld);
+      a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w; b.x += v1.x; b.y += v1.y; b.z += v1.z; b.w += v1.w;
+      c.x += v2.x; c.y += v2.y; c.z += v2.z; c.w += v2.w; d.x += v3.x; d.y += v3.y; d.z += v3.z; d.w += v3.w;
+    }
+    for (; r < r1; r += 8) { const float4 v0 = *reinterpret_cast<const float4*>(base + (long long)r * ld); a.x += v0.x; a.y += v0.y; a.z += v0.z; a.w += v0.w; }
+  }
+  red[ph][cl] = make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c4 = threadIdx.x >> 2, e = threadIdx.x & 3;
+    const int oc = (blockIdx.x * 32 + c4) * 4 + e;
+    if (oc < N) {
+      float sum = 0.f;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) sum += reinterpret_cast<const float*>(&red[p][c4])[e];
+      atomicAdd(out + oc, (scale_dev ? __ldg(scale_dev) : 1.0f) * sum);
+    }
+  }
+}
+// scalar fallback: thread per column, grid.y row chunks, atomics to combine
 __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X, long long ld, int M, int N, const float* __restrict__ scale_dev,
                                                      float* __restrict__ out, int rows_per_block) {
   const int col = blockIdx.x * 128 + threadIdx.x;
@@ -354,21 +425,25 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kMaxVec * 128);
   UVC_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm: row strides must be multiples of 4");
   if (M <= 0) return UVC_OK;
-  layernorm_fwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd);
+  UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd)));
   return check_launch("layernorm_fwd");
 }
 
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st) {
+                  cudaStream_t st, float* cs_r1, float* cs_out) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
   UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
+  UVC_REQUIRE(!cs_r1 || r1, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without r1");
   if (M <= 0) return UVC_OK;
-  int blocks = 148 * 4;
+  int blocks = 148 * 6;
   int rpb = (M + blocks - 1) / blocks;
   if (rpb < 8) rpb = 8;
   blocks = (M + rpb - 1) / rpb;
-  layernorm_bwd_kernel<<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, rpb);
+  if (cs_r1 || cs_out)
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb)));
+  else
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb)));
   return check_launch("layernorm_bwd");
 }
 
@@ -386,6 +461,16 @@ int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, 
 }
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st) {
   if (M <= 0 || N <= 0) return UVC_OK;
+  if ((N & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int cb = (N + 127) / 128;
+    int chunks = 148 * 4 / cb;
+    if (chunks < 1) chunks = 1;
+    int rpb = (M + chunks - 1) / chunks;
+    if (rpb < 64) rpb = 64;
+    chunks = (M + rpb - 1) / rpb;
+    colsum4_kernel<<<dim3(cb, chunks), 256, 0, st>>>(X, ld, M, N, scale_dev, out, rpb);
+    return check_launch("colsum");
+  }
   int chunks = 148 * 4 / ((N + 127) / 128);
   if (chunks < 1) chunks = 1;
   int rpb = (M + chunks - 1) / chunks;
@@ -468,6 +553,13 @@ int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx
   UVC_REQUIRE(dy && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd: NULL pointer");
   UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd: dgamma and dbeta must both be given or both NULL");
   return uvc::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST);
+}
+int uvc_layernorm_bwd_cs(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd, const float* gamma,
+                         const float* r1, const float* r2, const float* s2_dev, float* dx, int64_t lddx, float* dgamma, float* dbeta, float* cs_r1,
+                         float* cs_out, int32_t M, int32_t C, void* stream) {
+  UVC_REQUIRE(dy && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_cs: NULL pointer");
+  UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_cs: dgamma and dbeta must both be given or both NULL");
+  return uvc::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST, cs_r1, cs_out);
 }
 int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(S, UVC_ERR_BAD_ARG, "uvc_softmax_fwd: NULL pointer");

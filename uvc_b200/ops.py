@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GemmArgs, Operand  # noqa: F401
+from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GemmArgs, Operand  # noqa: F401
 
 
 def _stream():
@@ -31,7 +31,7 @@ def operand(t, ld=None, bs1=0, bs2=0, mn_major=False):
 
 
 def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=None, ldr=None, r_bs=(0, 0),
-         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1):
+         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T) with A:[M,K], B:[N,K] (see include/uvc_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
@@ -53,6 +53,8 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
     a.alpha, a.beta = float(alpha), float(beta)
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     a.beta_dev = beta_dev.data_ptr() if beta_dev is not None else None
+    if colsum is not None:
+        a.colsum = colsum.data_ptr(); flags |= EPI_COLSUM
     a.flags = int(flags)
     _lib.check(lib.uvc_gemm_tf32(C.byref(a), _stream()), "uvc_gemm_tf32")
     return D
@@ -95,15 +97,19 @@ def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=None, dbeta=None, ldx=None, lddx=None, dx=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=None, dbeta=None, ldx=None, lddx=None, dx=None, cs_r1=None, cs_out=None):
     C_ = gamma.numel()
     M = mean.numel()
     ldx = C_ if ldx is None else ldx
     lddx = C_ if lddx is None else lddx
     if dx is None:
         dx = torch.empty(M, C_, device=dy.device)
-    _call("uvc_layernorm_bwd", _p(dy), C_, _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), lddx,
-          _p(dgamma), _p(dbeta), M, C_)
+    if cs_r1 is not None or cs_out is not None:
+        _call("uvc_layernorm_bwd_cs", _p(dy), C_, _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), lddx,
+              _p(dgamma), _p(dbeta), _p(cs_r1), _p(cs_out), M, C_)
+    else:
+        _call("uvc_layernorm_bwd", _p(dy), C_, _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), lddx,
+              _p(dgamma), _p(dbeta), M, C_)
     return dx
 
 
