@@ -154,8 +154,9 @@ UVC_API int uvc_scale_add(float* y, const float* x, const float* s_dev, float s,
 /* ------------------------------------------------------------------------------------------
  * Attention core  softmax(Q K^T * scale) V  per (image, head)   (models/model_distilled.py:175-185)
  * qkv: [B*N, 3*H*d] exactly as nn.Linear(dim, 3*dim) writes it (q | k | v, head-major inside each).
- * P:   [B, H, N, ldp] attention probabilities, saved for the backward (ldp = uvc_attn_ldp(N)); may be
- *      workspace in inference.  ctx: [B*N, H*d] (already "transposed back", ready for the proj GEMM).
+ * P:   [B, H, N, ldp] attention probabilities, saved for the backward (ldp = uvc_attn_ldp(N)).  May be NULL when d == 64 and
+ *      N <= 208 (inference / teacher forward): the fused kernel keeps scores and probabilities in tensor memory and only qkv -> ctx
+ *      touches HBM.  ctx: [B*N, H*d] (already "transposed back", ready for the proj GEMM).
  */
 UVC_API int32_t uvc_attn_ldp(int32_t N);
 UVC_API int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);

@@ -245,3 +245,21 @@ def test_layernorm_bwd_fused_column_sums(ops):
     dx = ops.layernorm_bwd(dy, x, mean, rstd, g, r1=r1, dgamma=dg, dbeta=db, cs_r1=c1, cs_out=co)
     assert torch.equal(dx, dx0)
     assert rel(c1, r1.sum(0)) < FP32_TOL and rel(co - 1, dx0.double().sum(0).float()) < 1e-4 and rel(db, dy.sum(0)) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,H,N", [(64, 6, 197), (3, 3, 50), (5, 2, 130), (2, 4, 208), (40, 12, 197)])
+def test_attention_fused_forward(ops, B, H, N):
+    """fused tcgen05 attention forward (scores / probabilities stay in tensor memory): with and without the saved probabilities,
+    more heads than SMs (persistent loop), one- and two-tile sequences"""
+    d = 64
+    C = H * d
+    qkv = ops.round_tf32(rn(B * N, 3 * C))
+    t = qkv.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    attn = ((t[0] @ t[1].transpose(-2, -1)) * d ** -0.5).softmax(-1)
+    ref = (attn @ t[2]).transpose(1, 2).reshape(B * N, C)
+    ctx, P = ops.attention_fwd(qkv, B, H, N, d)
+    assert rel(ctx, ref) < TF32_TOL
+    assert rel(P[..., :N], attn) < TF32_TOL
+    assert (P[..., N:] == 0).all()
+    ctx2, none = ops.attention_fwd(qkv, B, H, N, d, save_P=False)
+    assert none is None and torch.equal(ctx2, ctx)

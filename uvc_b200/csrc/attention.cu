@@ -6,10 +6,266 @@
 // softmax, and the PV GEMM writing ctx directly in [B*N, H*d] layout.  P is kept ([B,H,N,ldp]) for the
 // backward, as the reference's autograd does.
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace uvc {
 
 int attn_ldp(int N) { return (N + 3) / 4 * 4; }
+
+// ====================================================================================================================
+// Fused forward: one persistent CTA per SM walks (image, head) pairs; scores and probabilities never leave the SM.
+//
+//   S_t = Q_t K^T        tcgen05.mma kind::tf32, A = Q tile (128 query rows) and B = K (208 key rows, zero-filled past N) from
+//                        TMA-staged swizzled shared memory, D = 128 lanes x 208 columns of TMEM; both query tiles (t = 0, 1) are
+//                        issued back to back into their own column ranges
+//   P_t = exp(S_t - max) eight softmax warps (four per query tile; warp w owns TMEM lanes 32 (w % 4) ..): each thread owns one query row,
+//                        reads it with tcgen05.ld, writes the un-normalised TF32-rounded probabilities back IN PLACE with tcgen05.st
+//   O_t = P_t V          tcgen05.mma with the A operand read straight from TMEM (the P just written), B = V (MN-major) from shared memory
+//   ctx = O_t / rowsum   epilogue by the same warps: tcgen05.ld, scale, TF32 rounding, 128-bit stores into [B*N, H*d]
+//
+// With save_P the normalised probabilities are also written to HBM for the (still GEMM-composed) backward; the teacher / inference
+// forward skips that and moves only qkv in and ctx out (the algorithmic minimum: 4 * B*N * 4C bytes).
+// TMEM columns: S0 [0,208)  S1 [208,416)  O [416,480) (one accumulator, tiles take turns).  Shared memory: Q 64 KB, K 52 KB, V 52 KB.
+// ====================================================================================================================
+constexpr int kANK = 208;                     // key rows staged / score columns (N <= 208)
+constexpr int kAThreads = 320;                // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax / epilogue
+constexpr int kAQBytes = 2 * 2 * 128 * 128;   // 2 query tiles x 2 k-blocks x 128 rows x 128 B
+constexpr int kAKBytes = 2 * kANK * 128;      // 2 k-blocks x 208 rows x 128 B
+constexpr int kAVBytes = 2 * kANK * 128;      // 2 groups of 32 head-dims x 208 tokens x 128 B
+constexpr int kASmem = kAQBytes + kAKBytes + kAVBytes + 1024;
+
+struct alignas(64) AttnFwdParams {
+  CUtensorMap tmQ, tmK, tmV;
+  float* P; float* ctx;
+  long long ldp;
+  int B, H, N, C, ntiles, save_P;
+  float scale_log2e;
+};
+
+__global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base, sK = sQ + kAQBytes, sV = sK + kAKBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  // Every barrier is waited on by parties that see EACH of its phases (a parity wait is only meaningful for the current or the
+  // immediately preceding phase), hence one o_full / o_empty per query tile although the tiles share one O accumulator.
+  const uint32_t qk_full = bar0, v_full = bar0 + 8, qk_empty = bar0 + 16, v_empty = bar0 + 24;
+  auto o_full = [&](int t) { return bar0 + 32 + 8u * t; };
+  auto o_empty = [&](int t) { return bar0 + 48 + 8u * t; };
+  auto s_full = [&](int t) { return bar0 + 64 + 8u * t; };
+  auto p_ready = [&](int t) { return bar0 + 80 + 8u * t; };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_empty, 1); mbar_init(v_empty, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(o_full(t), 1); mbar_init(o_empty(t), 4); mbar_init(s_full(t), 1); mbar_init(p_ready(t), 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int nheads = p.B * p.H;
+  const int ntiles = p.ntiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t it = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
+      const int b = hd / p.H, h = hd % p.H;
+      mbar_wait(qk_empty, (it & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(qk_full, (uint32_t)(ntiles * 2 * 128 * 128 + kAKBytes));
+        for (int t = 0; t < ntiles; ++t)
+          for (int kb = 0; kb < 2; ++kb) tma_load_4d(sQ + t * 32768 + kb * 16384, &p.tmQ, qk_full, kb * 32, t * 128, h, b);
+        for (int kb = 0; kb < 2; ++kb) tma_load_4d(sK + kb * (kANK * 128), &p.tmK, qk_full, kb * 32, 0, h, b);
+      }
+      __syncwarp();
+      mbar_wait(v_empty, (it & 1u) ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(v_full, kAVBytes);
+        for (int c = 0; c < 2; ++c) tma_load_4d(sV + c * (kANK * 128), &p.tmV, v_full, c * 32, 0, h, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kANK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);              // S = Q K^T
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // O = P V (B MN-major)
+    const uint32_t k_hi = umma_desc_hi(1024, 2), v_hi = umma_desc_hi(512, 1);
+    const uint32_t q_lo0 = umma_desc_lo(sQ, 16), k_lo0 = umma_desc_lo(sK, 16), v_lo0 = umma_desc_lo(sV, kANK * 128);
+    uint32_t it = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      mbar_wait(qk_full, ph);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) {
+        // S_t / P_t of the previous head must be fully consumed: group t arrives on o_empty[t] after its last TMEM read of that head
+        mbar_wait(o_empty(t), ph ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t kb = kk >> 2, k4 = kk & 3;
+            umma_tf32_lh(tmem_base + t * kANK, q_lo0 + ((t * 32768 + kb * 16384) >> 4) + k4 * 2, k_hi, k_lo0 + ((kb * (kANK * 128)) >> 4) + k4 * 2, k_hi, idesc1, kk ? 1u : 0u);
+          }
+          umma_commit(s_full(t));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(qk_empty);       // Q and K staging may be refilled for the next head
+      __syncwarp();
+      mbar_wait(v_full, ph);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(p_ready(t), ph);                  // P_t is in TMEM
+        // the single O accumulator: its previous user (the other tile of this head, or the last tile of the previous head, whose
+        // o_empty phase was already observed above) must have read it out
+        if (t > 0) mbar_wait(o_empty(t - 1), ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll 2
+          for (int ks = 0; ks < kANK / 8; ++ks)
+            umma_tf32_ts(tmem_base + 416, tmem_base + t * kANK + ks * 8, v_lo0 + ks * 64, v_hi, idesc2, ks ? 1u : 0u);
+          umma_commit(o_full(t));
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(v_empty);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax + epilogue =====================
+    const int ew = warp - 2;
+    const int t = ew >> 2;                           // query tile of this warp's group
+    const int q = warp & 3;                          // TMEM lane quadrant
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t s_addr = lane_addr + t * kANK;
+    const int row = t * 128 + q * 32 + lane;         // query row inside the head
+    const int N = p.N;
+    if (t < ntiles) {
+      uint32_t it = 0;
+      for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
+        const int b = hd / p.H, h = hd % p.H;
+        mbar_wait(s_full(t), it & 1u);
+        tc_fence_after();
+        // pass 1: row maximum over the valid key columns (columns >= N hold Q . 0 = 0 from the zero-filled key rows)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (c * 32 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        {
+          uint32_t r[16];
+          tmem_ld_32x16(s_addr + 192, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) if (192 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
+        }
+        // pass 2: e = exp((s - max) * scale), un-normalised, rounded to TF32, written back in place as the A operand of the PV MMA
+        const float mxs = mx * p.scale_log2e;
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
+            if (c * 32 + j >= N) e = 0.f;
+            e = round_tf32(e);
+            sum += e;
+            r[j] = __float_as_uint(e);
+          }
+          tmem_st_32x32(s_addr + c * 32, r);
+        }
+        {
+          uint32_t r[16];
+          tmem_ld_32x16(s_addr + 192, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
+            if (192 + j >= N) e = 0.f;
+            e = round_tf32(e);
+            sum += e;
+            r[j] = __float_as_uint(e);
+          }
+          tmem_st_32x16(s_addr + 192, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready(t));
+        const float inv = 1.0f / sum;
+        // optional pass 3: normalised probabilities to HBM for the backward (TMEM loads are warp-collective: only the stores are predicated)
+        if (p.save_P) {
+          float* prow = p.P + (((long long)b * p.H + h) * N + row) * p.ldp;
+          const bool rok = row < N;
+#pragma unroll 1
+          for (int c = 0; c < 6; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(s_addr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (rok && c * 32 + j < N)    // ldp % 4 == 0 and ldp >= N: a float4 starting below N stays inside the row's padding
+                *reinterpret_cast<float4*>(prow + c * 32 + j) = make_float4(round_tf32(__uint_as_float(r[j]) * inv), round_tf32(__uint_as_float(r[j + 1]) * inv),
+                                                                             round_tf32(__uint_as_float(r[j + 2]) * inv), round_tf32(__uint_as_float(r[j + 3]) * inv));
+            }
+          }
+          uint32_t r[16];
+          tmem_ld_32x16(s_addr + 192, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (rok && 192 + j < N)
+              *reinterpret_cast<float4*>(prow + 192 + j) = make_float4(round_tf32(__uint_as_float(r[j]) * inv), round_tf32(__uint_as_float(r[j + 1]) * inv),
+                                                                       round_tf32(__uint_as_float(r[j + 2]) * inv), round_tf32(__uint_as_float(r[j + 3]) * inv));
+          }
+        }
+        // epilogue: O_t / rowsum -> ctx
+        mbar_wait(o_full(t), it & 1u);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(lane_addr + 416, o0);
+        tmem_ld_32x32(lane_addr + 448, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty(t));
+        if (row < N) {
+          float* crow = p.ctx + ((long long)b * N + row) * p.C + h * 64;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + j) = make_float4(round_tf32(__uint_as_float(o0[j]) * inv), round_tf32(__uint_as_float(o0[j + 1]) * inv),
+                                                               round_tf32(__uint_as_float(o0[j + 2]) * inv), round_tf32(__uint_as_float(o0[j + 3]) * inv));
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(crow + 32 + j) = make_float4(round_tf32(__uint_as_float(o1[j]) * inv), round_tf32(__uint_as_float(o1[j + 1]) * inv),
+                                                                    round_tf32(__uint_as_float(o1[j + 2]) * inv), round_tf32(__uint_as_float(o1[j + 3]) * inv));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 
 static int check_attn(int B, int H, int N, int d) {
   UVC_REQUIRE(B > 0 && H > 0 && N > 0 && d > 0, UVC_ERR_BAD_SHAPE, "attention: bad dims B=%d H=%d N=%d d=%d", B, H, N, d);
@@ -18,9 +274,46 @@ static int check_attn(int B, int H, int N, int d) {
   return UVC_OK;
 }
 
-int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st) {
+static int attn_fused_mode() {
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("UVC_ATTN_FUSED"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
+// fused forward (d == 64, N <= 208): P may be NULL (inference / teacher: probabilities are never materialised)
+static int attention_fwd_fused(const float* qkv, float* P, float* ctx, int B, int H, int N, float scale, cudaStream_t st) {
+  const long long C = (long long)H * 64, ld3 = 3 * C;
+  AttnFwdParams kp;
+  const unsigned long long dims[4] = {64, (unsigned long long)N, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long strides[3] = {(unsigned long long)ld3 * 4, 64 * 4, (unsigned long long)N * ld3 * 4};
+  const unsigned int boxq[4] = {32, 128, 1, 1}, boxk[4] = {32, (unsigned)kANK, 1, 1};
+  int rc;
+  if ((rc = encode_tmap_4d(&kp.tmQ, qkv, dims, strides, boxq, false, "attn Q"))) return rc;
+  if ((rc = encode_tmap_4d(&kp.tmK, qkv + C, dims, strides, boxk, false, "attn K"))) return rc;
+  if ((rc = encode_tmap_4d(&kp.tmV, qkv + 2 * C, dims, strides, boxk, true, "attn V"))) return rc;
+  kp.P = P; kp.ctx = ctx; kp.ldp = attn_ldp(N);
+  kp.B = B; kp.H = H; kp.N = N; kp.C = (int)C; kp.ntiles = (N + 127) / 128; kp.save_P = P != nullptr;
+  kp.scale_log2e = scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmem);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn_fwd smem=%d): %s", kASmem, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = B * H < sms ? B * H : sms;
+  attn_fwd_kernel<<<grid, kAThreads, kASmem, st>>>(kp);
+  return check_launch("attn_fwd_kernel");
+}
+
+int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P) {
   int rc = check_attn(B, H, N, d);
   if (rc) return rc;
+  if (attn_fused_mode() && d == 64 && N <= kANK && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
+      (!P || (reinterpret_cast<uintptr_t>(P) & 15) == 0))
+    return attention_fwd_fused(qkv, need_P ? P : nullptr, ctx, B, H, N, scale, st);
+  UVC_REQUIRE(P != nullptr, UVC_ERR_BAD_ARG, "attention_fwd: the GEMM-composed path needs a P buffer");
   const long long C = (long long)H * d, ld3 = 3 * C, ldp = attn_ldp(N);
   const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
   // S[b,h] = scale * Q K^T
@@ -67,8 +360,8 @@ int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP
 
 extern "C" int32_t uvc_attn_ldp(int32_t N) { return uvc::attn_ldp(N); }
 extern "C" int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream) {
-  UVC_REQUIRE(qkv && P && ctx, UVC_ERR_BAD_ARG, "uvc_attention_fwd: NULL pointer");
-  return uvc::attention_fwd(qkv, P, ctx, B, H, N, d, scale, static_cast<cudaStream_t>(stream));
+  UVC_REQUIRE(qkv && ctx, UVC_ERR_BAD_ARG, "uvc_attention_fwd: NULL pointer");
+  return uvc::attention_fwd(qkv, P, ctx, B, H, N, d, scale, static_cast<cudaStream_t>(stream), P != nullptr);
 }
 extern "C" int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int32_t B, int32_t H, int32_t N,
                                  int32_t d, float scale, void* stream) {

@@ -558,6 +558,22 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
+// generic 4-D fp32 tiled tensor map (used by the fused attention kernels): 128 B swizzle, 16 B atoms (K-major operands) or 32 B atoms (MN-major)
+int encode_tmap_4d(CUtensorMap* tm, const float* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                   const unsigned int box[4], bool atom32, const char* name) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  UVC_REQUIRE(enc != nullptr, UVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UVC_REQUIRE(r == CUDA_SUCCESS, UVC_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
+  return UVC_OK;
+}
+
 // rows_mn: logical M or N extent; box_rows: tile rows for the K-major box
 static int make_tmap(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K, int nb1, int nb2, int box_rows, const char* name) {
   PFN_tmapEncodeTiled enc = get_encode_fn();

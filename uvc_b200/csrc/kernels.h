@@ -7,6 +7,8 @@
 namespace uvc {
 
 int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st);
+int encode_tmap_4d(CUtensorMap* tm, const float* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                   const unsigned int box[4], bool atom32, const char* name);
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
                   float* rstd, int M, int C, cudaStream_t st, int round_out = 0);
@@ -28,7 +30,7 @@ int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, co
 int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st);
 
 int attn_ldp(int N);
-int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st);
+int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P = true);
 int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int B, int H, int N, int d, float scale,
                   cudaStream_t st);
 

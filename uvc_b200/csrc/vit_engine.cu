@@ -213,7 +213,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
       LayerWs& L = w.layer[l];
       UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, L.ln1, C, L.mean1, L.rstd1, M, C, st, 1));
       UVC_TRY(linear_fwd(L.ln1, C, w.wr.qkv_w[l], p.qkv_b, L.qkv, 3 * C, M, 3 * C, C, st, UVC_EPI_ROUND_TF32));
-      UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st));
+      UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st, save));   // inference never materialises the probabilities
       UVC_TRY(linear_fwd(L.ctx, C, w.wr.proj_w[l], p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));     // x1 = x + proj(ctx)
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st, 1));
       UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1), hpre kept

@@ -185,10 +185,10 @@ def attn_ldp(N):
     return int(_lib.load().uvc_attn_ldp(int(N)))
 
 
-def attention_fwd(qkv, B, H, N, d, scale=None):
-    """qkv:[B*N, 3*H*d] -> (ctx:[B*N, H*d], P:[B,H,N,ldp])"""
+def attention_fwd(qkv, B, H, N, d, scale=None, save_P=True):
+    """qkv:[B*N, 3*H*d] -> (ctx:[B*N, H*d], P:[B,H,N,ldp] or None when save_P is False (inference: probabilities stay on chip))"""
     scale = d ** -0.5 if scale is None else scale
-    P = torch.empty(B, H, N, attn_ldp(N), device=qkv.device)
+    P = torch.zeros(B, H, N, attn_ldp(N), device=qkv.device) if save_P else None
     ctx = torch.empty(B * N, H * d, device=qkv.device)
     _call("uvc_attention_fwd", _p(qkv), _p(P), _p(ctx), B, H, N, d, float(scale))
     return ctx, P
