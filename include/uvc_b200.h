@@ -160,6 +160,13 @@ UVC_API int uvc_scale_add(float* y, const float* x, const float* s_dev, float s,
  */
 UVC_API int32_t uvc_attn_ldp(int32_t N);
 UVC_API int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+/* Training forward of the fused path (d == 64, N <= 208): instead of the probabilities it saves lse[B,H,N], the per-row log-sum-exp of the
+ * scaled scores in the log2 domain (P = exp2(S * scale * log2(e) - lse)), 4 bytes per row instead of an 800-byte row of P. */
+UVC_API int uvc_attention_fwd_lse(const float* qkv, float* lse, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+/* Fused backward with recomputation (autograd backward of models/model_distilled.py:175-185): dqkv [B*N, 3*H*d] from dctx, the forward's
+ * ctx and lse; D_ws is [B,H,N] scratch (rowsum(dctx .* ctx)).  Scores, probabilities and dS live only in tensor memory. */
+UVC_API int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv,
+                                    int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
 /* dqkv [B*N, 3*H*d] from dctx [B*N, H*d]; dP is scratch of the same size as P */
 UVC_API int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv,
                               int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);

@@ -25,3 +25,7 @@ if os.environ.get('UVC_ATTN_FUSED', '1') != '0':
     print(tag, "fwd no P   : %.1f us" % timeit(lambda: ops.attention_fwd(qkv, B, H, N, d, save_P=False)))
 ctx, P = ops.attention_fwd(qkv, B, H, N, d)
 print(tag, "bwd        : %.1f us" % timeit(lambda: ops.attention_bwd(qkv, P, dctx, B, H, N, d)))
+if os.environ.get('UVC_ATTN_FUSED', '1') != '0':
+    ctx2, lse = ops.attention_fwd_lse(qkv, B, H, N, d)
+    print(tag, "fwd lse    : %.1f us" % timeit(lambda: ops.attention_fwd_lse(qkv, B, H, N, d)))
+    print(tag, "bwd fused  : %.1f us" % timeit(lambda: ops.attention_bwd_fused(qkv, lse, ctx2, dctx, B, H, N, d)))

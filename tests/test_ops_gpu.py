@@ -263,3 +263,25 @@ def test_attention_fused_forward(ops, B, H, N):
     assert (P[..., N:] == 0).all()
     ctx2, none = ops.attention_fwd(qkv, B, H, N, d, save_P=False)
     assert none is None and torch.equal(ctx2, ctx)
+
+
+@pytest.mark.parametrize("B,H,N", [(2, 6, 197), (64, 6, 197), (3, 3, 50), (5, 2, 130), (2, 4, 208)])
+def test_attention_fused_backward(ops, B, H, N):
+    """fused forward (lse) + fused recompute backward against autograd of the plain fp32 formula"""
+    d = 64
+    C = H * d
+    qkv = ops.round_tf32(rn(B * N, 3 * C))
+    ctx, lse = ops.attention_fwd_lse(qkv, B, H, N, d)
+    q = qkv.clone().requires_grad_(True)
+    t = q.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    s_ = (t[0] @ t[1].transpose(-2, -1)) * d ** -0.5
+    ref = (s_.softmax(-1) @ t[2]).transpose(1, 2).reshape(B * N, C)
+    assert rel(ctx, ref.detach()) < TF32_TOL
+    assert rel(lse * 0.6931471805599453, torch.logsumexp(s_.detach(), -1)) < 1e-4
+    dctx = ops.round_tf32(rn(B * N, C, seed=7))
+    ref.backward(dctx)
+    dqkv = ops.attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d)
+    g = q.grad.view(B * N, 3, C)
+    got = dqkv.view(B * N, 3, C)
+    for i, nm in enumerate("qkv"):
+        assert rel(got[:, i], g[:, i]) < 2 * TF32_TOL, nm

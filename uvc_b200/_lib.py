@@ -88,7 +88,7 @@ EXPORTS = [
     "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_tf32",
     "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_layernorm_bwd_cs", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
     "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
-    "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
+    "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
@@ -144,6 +144,8 @@ def load():
         "uvc_scale_add": [vp, vp, vp, f32, i64, vp],
         "uvc_attention_fwd": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_attention_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_attention_fwd_lse": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_attention_bwd_fused": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_distill_loss": [vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp],
         "uvc_sqnorm_accum": [vp, i64, vp, vp],
         "uvc_clip_adamw": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],

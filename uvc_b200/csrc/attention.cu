@@ -36,7 +36,7 @@ constexpr int kASmem = kAQBytes + kAKBytes + kAVBytes + 1024;
 
 struct alignas(64) AttnFwdParams {
   CUtensorMap tmQ, tmK, tmV;
-  float* P; float* ctx;
+  float* P; float* ctx; float* lse;
   long long ldp;
   int B, H, N, C, ntiles, save_P;
   float scale_log2e;
@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready(t));
         const float inv = 1.0f / sum;
+        if (p.lse && row < N) p.lse[((long long)b * p.H + h) * N + row] = mxs + log2f(sum);   // log2-domain log-sum-exp: P = exp2(S scale log2e - lse)
         // optional pass 3: normalised probabilities to HBM for the backward (TMEM loads are warp-collective: only the stores are predicated)
         if (p.save_P) {
           float* prow = p.P + (((long long)b * p.H + h) * N + row) * p.ldp;
@@ -274,6 +275,308 @@ static int check_attn(int B, int H, int N, int d) {
   return UVC_OK;
 }
 
+
+// ====================================================================================================================
+// Fused backward with recomputation (no saved probabilities): two kernels per layer, both persistent over (image, head, 128-row tile).
+//
+//   phase 1 (query-major, produces dQ)          phase 2 (key-major, produces dK and dV)
+//     X = Q_t K^T          (scores)               X = K_t' Q^T          (scores, transposed)
+//     Y = dO_t V^T         (dP)                   Y = V_t' dO^T         (dP, transposed)
+//     Y <- dS = scale * P .* (dP - D)             X <- P^T,  Y <- dS^T
+//     dQ_t = dS K          (A operand = Y in TMEM)  dV_t' = P^T dO (A = X in TMEM),  dK_t' = dS^T Q (A = Y in TMEM)
+//
+// with P = exp2(S * scale * log2e - lse2) recomputed from the forward's per-row log-sum-exp (lse2, 4 B per row instead of the 800 B row of P)
+// and D = rowsum(dO .* O) from a small pre-kernel.  The transposed pass exists because the A operand of a TMEM-sourced MMA always has its
+// rows on the TMEM lanes: dK and dV need key-major probabilities, which are cheaper to recompute (one 128 x 208 x 64 MMA) than to transpose.
+// X and Y are 208 TMEM columns each; the output accumulators take 64 more (phase 2 parks dK in the first 64 columns of X once the dV MMA
+// has consumed P^T).  Eight elementwise warps split each 32-lane quadrant's 208 columns in two halves: the backward needs no row reduction.
+// Shared memory: two 32 KB A tiles + two (phase 1: three) 52 KB B operands; phase 2 reloads its B buffers with the MN-major (32 B swizzle atom)
+// view of dO and Q for the output MMAs while the elementwise pass runs (the tensor core accepts 32-bit MN-major operands only in that layout,
+// and K-major operands only in the 16 B atom layout, so one staged copy cannot serve both roles).
+// ====================================================================================================================
+constexpr int kBABytes = 2 * 128 * 128;       // one A tile: 2 k-blocks x 128 rows x 128 B
+constexpr int kBBBytes = 2 * kANK * 128;      // one B operand: 2 x 208 rows x 128 B
+
+struct alignas(64) AttnBwdParams {
+  CUtensorMap tmA0, tmA1;      // A tiles (128-row boxes, K-major):           phase 1: Q, dO    phase 2: K, V
+  CUtensorMap tmB0, tmB1;      // score B operands (208-row boxes, K-major):  phase 1: K, V     phase 2: Q, dO
+  CUtensorMap tmC0, tmC1;      // output B operands (MN-major, 32 B atoms):   phase 1: K, -     phase 2: Q, dO
+  const float* lse; const float* Dv;    // [B, H, N]
+  float* out0; float* out1;    // phase 1: dq, -   phase 2: dv, dk   (pointers to column 0 of the head-0 slice inside dqkv, row stride ldo)
+  long long ldo;
+  int B, H, N, ntiles;
+  float scale, scale_log2e;
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_lse[256];
+  __shared__ __align__(16) float s_D[256];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA0 = smem_base, sA1 = sA0 + kBABytes, sB0 = sA1 + kBABytes, sB1 = sB0 + kBBBytes, sB2 = sB1 + kBBBytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t a_full = bar0, a_empty = bar0 + 8, bs_full = bar0 + 16, bs_empty = bar0 + 24, bo_full = bar0 + 32, bo_empty = bar0 + 40,
+                 sc_full = bar0 + 48, el_done = bar0 + 56, acc_full = bar0 + 64, acc_empty = bar0 + 72, mid = bar0 + 80;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0); tma_prefetch_desc(&p.tmA1); tma_prefetch_desc(&p.tmB0); tma_prefetch_desc(&p.tmB1); tma_prefetch_desc(&p.tmC0);
+    if (PHASE == 2) tma_prefetch_desc(&p.tmC1);
+    mbar_init(a_full, 1); mbar_init(a_empty, 1); mbar_init(bs_full, 1); mbar_init(bs_empty, 1); mbar_init(bo_full, 1); mbar_init(bo_empty, 1);
+    mbar_init(sc_full, 1); mbar_init(el_done, 8); mbar_init(acc_full, 1); mbar_init(acc_empty, 8); mbar_init(mid, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int nheads = p.B * p.H, ntiles = p.ntiles;
+  constexpr uint32_t kX = 0, kY = kANK, kAcc = 2 * kANK;     // TMEM columns
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    uint32_t ia = 0, ibs = 0, ibo = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x) {
+      const int b = hd / p.H, h = hd % p.H;
+      for (int t = 0; t < ntiles; ++t, ++ia) {
+        mbar_wait(a_empty, (ia & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(a_full, 2 * kBABytes);
+          for (int kb = 0; kb < 2; ++kb) {
+            tma_load_4d(sA0 + kb * 16384, &p.tmA0, a_full, kb * 32, t * 128, h, b);
+            tma_load_4d(sA1 + kb * 16384, &p.tmA1, a_full, kb * 32, t * 128, h, b);
+          }
+        }
+        __syncwarp();
+        if (PHASE == 2 || t == 0) {
+          mbar_wait(bs_empty, (ibs & 1u) ^ 1u);                    // score MMAs that read the previous contents are done
+          if (PHASE == 2) mbar_wait(bo_empty, (ibo & 1u) ^ 1u);    // same memory was last used by the output MMAs of the previous tile
+          if (elect_one()) {
+            mbar_expect_tx(bs_full, 2 * kBBBytes);
+            for (int kb = 0; kb < 2; ++kb) {
+              tma_load_4d(sB0 + kb * (kANK * 128), &p.tmB0, bs_full, kb * 32, 0, h, b);
+              tma_load_4d(sB1 + kb * (kANK * 128), &p.tmB1, bs_full, kb * 32, 0, h, b);
+            }
+          }
+          __syncwarp();
+          ++ibs;
+        }
+        if (PHASE == 1) {
+          if (t == 0) {
+            mbar_wait(bo_empty, (ibo & 1u) ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(bo_full, kBBBytes);
+              for (int c = 0; c < 2; ++c) tma_load_4d(sB2 + c * (kANK * 128), &p.tmC0, bo_full, c * 32, 0, h, b);
+            }
+            __syncwarp();
+            ++ibo;
+          }
+        } else {
+          mbar_wait(bs_empty, (ibs - 1u) & 1u);                    // this tile's score MMAs have consumed the K-major copies: restage MN-major
+          if (elect_one()) {
+            mbar_expect_tx(bo_full, 2 * kBBBytes);
+            for (int c = 0; c < 2; ++c) {
+              tma_load_4d(sB0 + c * (kANK * 128), &p.tmC0, bo_full, c * 32, 0, h, b);
+              tma_load_4d(sB1 + c * (kANK * 128), &p.tmC1, bo_full, c * 32, 0, h, b);
+            }
+          }
+          __syncwarp();
+          ++ibo;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kANK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);              // 128 x 208, K-major A and B
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // 128 x 64, B MN-major
+    const uint32_t k_hi = umma_desc_hi(1024, 2), m_hi = umma_desc_hi(512, 1);
+    const uint32_t a0_lo = umma_desc_lo(sA0, 16), a1_lo = umma_desc_lo(sA1, 16), b0_lo = umma_desc_lo(sB0, 16), b1_lo = umma_desc_lo(sB1, 16);
+    const uint32_t m0_lo = umma_desc_lo(sB0, kANK * 128), m1_lo = umma_desc_lo(sB1, kANK * 128), m2_lo = umma_desc_lo(sB2, kANK * 128);
+    uint32_t ia = 0, ibs = 0, ibo = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x) {
+      for (int t = 0; t < ntiles; ++t, ++ia) {
+        const uint32_t ph = ia & 1u;
+        mbar_wait(a_full, ph);
+        if (PHASE == 2 || t == 0) { mbar_wait(bs_full, ibs & 1u); ++ibs; }
+        mbar_wait(acc_empty, ph ^ 1u);               // previous tile's epilogue has drained X / Y / accumulators
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t kb = kk >> 2, k4 = kk & 3;
+            umma_tf32_lh(tmem_base + kX, a0_lo + ((kb * 16384) >> 4) + k4 * 2, k_hi, b0_lo + ((kb * (kANK * 128)) >> 4) + k4 * 2, k_hi, idesc1, kk ? 1u : 0u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t kb = kk >> 2, k4 = kk & 3;
+            umma_tf32_lh(tmem_base + kY, a1_lo + ((kb * 16384) >> 4) + k4 * 2, k_hi, b1_lo + ((kb * (kANK * 128)) >> 4) + k4 * 2, k_hi, idesc1, kk ? 1u : 0u);
+          }
+          umma_commit(sc_full);
+          umma_commit(a_empty);
+          if (PHASE == 2 || t == ntiles - 1) umma_commit(bs_empty);
+        }
+        __syncwarp();
+        mbar_wait(el_done, ph);                      // dS (and P^T) are in TMEM
+        if (PHASE == 2 || t == 0) { mbar_wait(bo_full, ibo & 1u); ++ibo; }
+        tc_fence_after();
+        if (PHASE == 1) {
+          if (elect_one()) {
+#pragma unroll 2
+            for (int ks = 0; ks < kANK / 8; ++ks) umma_tf32_ts(tmem_base + kAcc, tmem_base + kY + ks * 8, m2_lo + ks * 64, m_hi, idesc2, ks ? 1u : 0u);   // dQ = dS K
+            umma_commit(acc_full);
+            if (t == ntiles - 1) umma_commit(bo_empty);
+          }
+          __syncwarp();
+        } else {
+          if (elect_one()) {
+#pragma unroll 2
+            for (int ks = 0; ks < kANK / 8; ++ks) umma_tf32_ts(tmem_base + kAcc, tmem_base + kX + ks * 8, m1_lo + ks * 64, m_hi, idesc2, ks ? 1u : 0u);   // dV = P^T dO
+            umma_commit(mid);
+          }
+          __syncwarp();
+          mbar_wait(mid, ph);                        // P^T consumed: its first 64 columns become the dK accumulator
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll 2
+            for (int ks = 0; ks < kANK / 8; ++ks) umma_tf32_ts(tmem_base + kX, tmem_base + kY + ks * 8, m0_lo + ks * 64, m_hi, idesc2, ks ? 1u : 0u);     // dK = dS^T Q
+            umma_commit(acc_full);
+            umma_commit(bo_empty);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== elementwise pass + epilogue (8 warps) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                          // TMEM lane quadrant
+    const int hh = ew >> 2;                          // column half: [104 hh, 104 hh + 104)
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int N = p.N;
+    const int tid2 = threadIdx.x - 64;
+    uint32_t ia = 0;
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x) {
+      const int b = hd / p.H, h = hd % p.H;
+      const long long srow = ((long long)b * p.H + h) * N;
+      if (PHASE == 2) {                              // per-query statistics of this head, indexed by score column
+        named_bar_sync(1, 256);
+        s_lse[tid2] = tid2 < N ? __ldg(p.lse + srow + tid2) : INFINITY;
+        s_D[tid2] = tid2 < N ? __ldg(p.Dv + srow + tid2) : 0.f;
+        named_bar_sync(1, 256);
+      }
+      for (int t = 0; t < ntiles; ++t, ++ia) {
+        const int row = t * 128 + q * 32 + lane;     // phase 1: query row ; phase 2: key row
+        float lse_r = INFINITY, D_r = 0.f;
+        if (PHASE == 1 && row < N) { lse_r = __ldg(p.lse + srow + row); D_r = __ldg(p.Dv + srow + row); }
+        mbar_wait(sc_full, ia & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = hh * 104 + c * 32;
+          if (c < 3) {
+            uint32_t rx[32], ry[32];
+            tmem_ld_32x32(lane_addr + kX + col0, rx);
+            tmem_ld_32x32(lane_addr + kY + col0, ry);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float pr, ds;
+              if (PHASE == 1) {
+                pr = (col0 + j < N) ? ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r)) : 0.f;
+                ds = pr * (__uint_as_float(ry[j]) - D_r) * p.scale;
+              } else {
+                pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
+                ds = pr * (__uint_as_float(ry[j]) - s_D[col0 + j]) * p.scale;
+                rx[j] = __float_as_uint(round_tf32(pr));
+              }
+              ry[j] = __float_as_uint(round_tf32(ds));
+            }
+            if (PHASE == 2) tmem_st_32x32(lane_addr + kX + col0, rx);
+            tmem_st_32x32(lane_addr + kY + col0, ry);
+          } else {
+            uint32_t rx[8], ry[8];
+            tmem_ld_32x8(lane_addr + kX + col0, rx);
+            tmem_ld_32x8(lane_addr + kY + col0, ry);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float pr, ds;
+              if (PHASE == 1) {
+                pr = (col0 + j < N) ? ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r)) : 0.f;
+                ds = pr * (__uint_as_float(ry[j]) - D_r) * p.scale;
+              } else {
+                pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
+                ds = pr * (__uint_as_float(ry[j]) - s_D[col0 + j]) * p.scale;
+                rx[j] = __float_as_uint(round_tf32(pr));
+              }
+              ry[j] = __float_as_uint(round_tf32(ds));
+            }
+            if (PHASE == 2) tmem_st_32x8(lane_addr + kX + col0, rx);
+            tmem_st_32x8(lane_addr + kY + col0, ry);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(el_done);
+        // epilogue: this warp's 32 rows x its 32-column half of the 64-wide outputs
+        mbar_wait(acc_full, ia & 1u);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(lane_addr + kAcc + hh * 32, o0);
+        if (PHASE == 2) tmem_ld_32x32(lane_addr + kX + hh * 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        if (row < N) {
+          const long long off = ((long long)b * N + row) * p.ldo + h * 64 + hh * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(p.out0 + off + j) = make_float4(round_tf32(__uint_as_float(o0[j])), round_tf32(__uint_as_float(o0[j + 1])),
+                                                                       round_tf32(__uint_as_float(o0[j + 2])), round_tf32(__uint_as_float(o0[j + 3])));
+          if (PHASE == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.out1 + off + j) = make_float4(round_tf32(__uint_as_float(o1[j])), round_tf32(__uint_as_float(o1[j + 1])),
+                                                                         round_tf32(__uint_as_float(o1[j + 2])), round_tf32(__uint_as_float(o1[j + 3])));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[b,h,row] = sum_j dO[row, h*64 + j] * O[row, h*64 + j]   (one warp per token row; 16 lanes x float4 cover one head)
+__global__ void __launch_bounds__(256) attn_rowdot_kernel(const float* __restrict__ dO, const float* __restrict__ O, float* __restrict__ Dv, int B, int H, int N) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * N) return;
+  const int b = (int)(row / N), n = (int)(row % N);
+  const int C4 = H * 16;
+  const float4* a = reinterpret_cast<const float4*>(dO) + row * C4;
+  const float4* o = reinterpret_cast<const float4*>(O) + row * C4;
+  for (int c0 = 0; c0 < C4; c0 += 32) {
+    const int c = c0 + lane;
+    float v = 0.f;
+    if (c < C4) { const float4 x = a[c], y = o[c]; v = (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w); }
+#pragma unroll
+    for (int s2 = 8; s2 > 0; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);
+    if ((lane & 15) == 0 && c < C4) Dv[((long long)b * H + (c >> 4)) * N + n] = v;
+  }
+}
+
 static int attn_fused_mode() {
   static int mode = -1;
   if (mode < 0) { const char* e = getenv("UVC_ATTN_FUSED"); mode = e ? atoi(e) : 1; }
@@ -281,7 +584,7 @@ static int attn_fused_mode() {
 }
 
 // fused forward (d == 64, N <= 208): P may be NULL (inference / teacher: probabilities are never materialised)
-static int attention_fwd_fused(const float* qkv, float* P, float* ctx, int B, int H, int N, float scale, cudaStream_t st) {
+static int attention_fwd_fused(const float* qkv, float* P, float* ctx, float* lse, int B, int H, int N, float scale, cudaStream_t st) {
   const long long C = (long long)H * 64, ld3 = 3 * C;
   AttnFwdParams kp;
   const unsigned long long dims[4] = {64, (unsigned long long)N, (unsigned long long)H, (unsigned long long)B};
@@ -291,7 +594,7 @@ static int attention_fwd_fused(const float* qkv, float* P, float* ctx, int B, in
   if ((rc = encode_tmap_4d(&kp.tmQ, qkv, dims, strides, boxq, false, "attn Q"))) return rc;
   if ((rc = encode_tmap_4d(&kp.tmK, qkv + C, dims, strides, boxk, false, "attn K"))) return rc;
   if ((rc = encode_tmap_4d(&kp.tmV, qkv + 2 * C, dims, strides, boxk, true, "attn V"))) return rc;
-  kp.P = P; kp.ctx = ctx; kp.ldp = attn_ldp(N);
+  kp.P = P; kp.ctx = ctx; kp.lse = lse; kp.ldp = attn_ldp(N);
   kp.B = B; kp.H = H; kp.N = N; kp.C = (int)C; kp.ntiles = (N + 127) / 128; kp.save_P = P != nullptr;
   kp.scale_log2e = scale * 1.4426950408889634f;
   static bool attr_set = false;
@@ -307,12 +610,15 @@ static int attention_fwd_fused(const float* qkv, float* P, float* ctx, int B, in
   return check_launch("attn_fwd_kernel");
 }
 
-int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P) {
+bool attn_fused_ok(int N, int d) { return attn_fused_mode() != 0 && d == 64 && N <= kANK; }
+
+int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P, float* lse) {
   int rc = check_attn(B, H, N, d);
   if (rc) return rc;
-  if (attn_fused_mode() && d == 64 && N <= kANK && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
+  if (attn_fused_ok(N, d) && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0 &&
       (!P || (reinterpret_cast<uintptr_t>(P) & 15) == 0))
-    return attention_fwd_fused(qkv, need_P ? P : nullptr, ctx, B, H, N, scale, st);
+    return attention_fwd_fused(qkv, need_P ? P : nullptr, ctx, lse, B, H, N, scale, st);
+  UVC_REQUIRE(lse == nullptr, UVC_ERR_BAD_SHAPE, "attention_fwd: the log-sum-exp output needs the fused kernel (d == 64, N <= %d)", kANK);
   UVC_REQUIRE(P != nullptr, UVC_ERR_BAD_ARG, "attention_fwd: the GEMM-composed path needs a P buffer");
   const long long C = (long long)H * d, ld3 = 3 * C, ldp = attn_ldp(N);
   const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
@@ -326,6 +632,60 @@ int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, i
   c.nb1 = H; c.nb2 = B; c.d_bs1 = d; c.d_bs2 = (long long)N * C;
   c.flags = UVC_EPI_ROUND_TF32;
   return gemm_tf32(c, st);
+}
+
+
+// 4-D view (head-dim, token, head, image) of a [B*N, ld] activation matrix whose columns are grouped in heads of 64
+static int attn_tmap(CUtensorMap* tm, const float* base, long long ld, int B, int H, int N, unsigned box_rows, bool atom32, const char* name) {
+  const unsigned long long dims[4] = {64, (unsigned long long)N, (unsigned long long)H, (unsigned long long)B};
+  const unsigned long long strides[3] = {(unsigned long long)ld * 4, 64 * 4, (unsigned long long)N * ld * 4};
+  const unsigned int box[4] = {32, box_rows, 1, 1};
+  return encode_tmap_4d(tm, base, dims, strides, box, atom32, name);
+}
+
+// fused backward with recomputation: needs the forward's lse [B,H,N], ctx and a [B,H,N] scratch for D = rowsum(dctx .* ctx)
+int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* Dv, float* dqkv, int B, int H, int N, float scale,
+                        cudaStream_t st) {
+  UVC_REQUIRE(N <= kANK, UVC_ERR_BAD_SHAPE, "attention_bwd_fused: N=%d > %d", N, kANK);
+  const long long C = (long long)H * 64, ld3 = 3 * C;
+  const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
+  attn_rowdot_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(dctx, ctx, Dv, B, H, N);
+  int rc = check_launch("attn_rowdot_kernel");
+  if (rc) return rc;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = B * H < sms ? B * H : sms;
+  constexpr int smem1 = 2 * kBABytes + 3 * kBBBytes + 1024, smem2 = 2 * kBABytes + 2 * kBBBytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn_bwd): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  AttnBwdParams kp;
+  kp.lse = lse; kp.Dv = Dv; kp.ldo = ld3; kp.B = B; kp.H = H; kp.N = N; kp.ntiles = (N + 127) / 128;
+  kp.scale = scale; kp.scale_log2e = scale * 1.4426950408889634f;
+  // phase 1: dQ
+  if ((rc = attn_tmap(&kp.tmA0, q, ld3, B, H, N, 128, false, "attn bwd Q tile"))) return rc;
+  if ((rc = attn_tmap(&kp.tmA1, dctx, C, B, H, N, 128, false, "attn bwd dO tile"))) return rc;
+  if ((rc = attn_tmap(&kp.tmB0, k, ld3, B, H, N, kANK, false, "attn bwd K"))) return rc;
+  if ((rc = attn_tmap(&kp.tmB1, v, ld3, B, H, N, kANK, false, "attn bwd V"))) return rc;
+  if ((rc = attn_tmap(&kp.tmC0, k, ld3, B, H, N, kANK, true, "attn bwd K (MN)"))) return rc;
+  kp.tmC1 = kp.tmC0;
+  kp.out0 = dqkv; kp.out1 = nullptr;
+  attn_bwd_kernel<1><<<grid, kAThreads, smem1, st>>>(kp);
+  if ((rc = check_launch("attn_bwd_kernel<1>"))) return rc;
+  // phase 2: dK, dV
+  if ((rc = attn_tmap(&kp.tmA0, k, ld3, B, H, N, 128, false, "attn bwd K tile"))) return rc;
+  if ((rc = attn_tmap(&kp.tmA1, v, ld3, B, H, N, 128, false, "attn bwd V tile"))) return rc;
+  if ((rc = attn_tmap(&kp.tmB0, q, ld3, B, H, N, kANK, false, "attn bwd Q"))) return rc;
+  if ((rc = attn_tmap(&kp.tmB1, dctx, C, B, H, N, kANK, false, "attn bwd dO"))) return rc;
+  if ((rc = attn_tmap(&kp.tmC0, q, ld3, B, H, N, kANK, true, "attn bwd Q (MN)"))) return rc;
+  if ((rc = attn_tmap(&kp.tmC1, dctx, C, B, H, N, kANK, true, "attn bwd dO (MN)"))) return rc;
+  kp.out0 = dqkv + 2 * C; kp.out1 = dqkv + C;
+  attn_bwd_kernel<2><<<grid, kAThreads, smem2, st>>>(kp);
+  return check_launch("attn_bwd_kernel<2>");
 }
 
 int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int B, int H, int N, int d, float scale,
@@ -362,6 +722,16 @@ extern "C" int32_t uvc_attn_ldp(int32_t N) { return uvc::attn_ldp(N); }
 extern "C" int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream) {
   UVC_REQUIRE(qkv && ctx, UVC_ERR_BAD_ARG, "uvc_attention_fwd: NULL pointer");
   return uvc::attention_fwd(qkv, P, ctx, B, H, N, d, scale, static_cast<cudaStream_t>(stream), P != nullptr);
+}
+extern "C" int uvc_attention_fwd_lse(const float* qkv, float* lse, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream) {
+  UVC_REQUIRE(qkv && lse && ctx, UVC_ERR_BAD_ARG, "uvc_attention_fwd_lse: NULL pointer");
+  return uvc::attention_fwd(qkv, nullptr, ctx, B, H, N, d, scale, static_cast<cudaStream_t>(stream), false, lse);
+}
+extern "C" int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv, int32_t B,
+                                       int32_t H, int32_t N, int32_t d, float scale, void* stream) {
+  UVC_REQUIRE(qkv && lse && ctx && dctx && D_ws && dqkv, UVC_ERR_BAD_ARG, "uvc_attention_bwd_fused: NULL pointer");
+  UVC_REQUIRE(uvc::attn_fused_ok(N, d), UVC_ERR_BAD_SHAPE, "uvc_attention_bwd_fused: needs d == 64 and N <= 208 (got d=%d, N=%d)", d, N);
+  return uvc::attention_bwd_fused(qkv, lse, ctx, dctx, D_ws, dqkv, B, H, N, scale, static_cast<cudaStream_t>(stream));
 }
 extern "C" int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int32_t B, int32_t H, int32_t N,
                                  int32_t d, float scale, void* stream) {

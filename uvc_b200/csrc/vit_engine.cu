@@ -28,7 +28,7 @@ struct Bump {
 
 struct LayerWs {
   float *mean1, *rstd1, *mean2, *rstd2;
-  float *ln1, *qkv, *P, *ctx, *x1, *ln2, *hpre, *h, *t, *xout;
+  float *ln1, *qkv, *P, *lse, *ctx, *x1, *ln2, *hpre, *h, *t, *xout;   // fused attention saves lse [B,H,ntok] instead of P
 };
 
 struct WeightsR {   // TF32-rounded copies of every GEMM weight (refreshed at the start of each forward)
@@ -42,7 +42,7 @@ struct Ws {
   float *cols, *pe, *tok, *mean_f, *rstd_f, *cls_ln, *accum;
   LayerWs layer[UVC_MAX_DEPTH];
   // scratch
-  float *g_a, *g_b, *g_c, *dh, *dqkv, *dP, *dcls_ln, *dpe;
+  float *g_a, *g_b, *g_c, *dh, *dqkv, *dP, *Dv, *dcls_ln, *dpe;
   size_t bytes;
 };
 
@@ -72,7 +72,9 @@ int check_dims(const uvc_vit_dims& v, Dims* o) {
 void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
   Bump b(base, cap);
   const size_t M = (size_t)D.M, C = D.C, Fh = D.Fh;
-  const size_t psz = (size_t)D.B * D.H * D.ntok * attn_ldp(D.ntok);
+  const bool fused_attn = attn_fused_ok(D.ntok, D.d);       // fused tcgen05 attention: no probabilities in HBM, 4 B per row of statistics instead
+  const size_t psz = fused_attn ? 0 : (size_t)D.B * D.H * D.ntok * attn_ldp(D.ntok);
+  const size_t lsz = fused_attn ? (size_t)D.B * D.H * D.ntok : 0;
   w->wr.patch_w = b.f(C * (size_t)D.Kp); w->wr.head_w = b.f((size_t)D.NC * C);
   for (int l = 0; l < D.L; ++l) {
     w->wr.qkv_w[l] = b.f(3 * C * C); w->wr.proj_w[l] = b.f(C * C); w->wr.fc1_w[l] = b.f(Fh * C); w->wr.fc2_w[l] = b.f(C * Fh);
@@ -87,23 +89,23 @@ void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
     for (int l = 0; l < D.L; ++l) {
       LayerWs& L = w->layer[l];
       L.mean1 = b.f(M); L.rstd1 = b.f(M); L.mean2 = b.f(M); L.rstd2 = b.f(M);
-      L.ln1 = b.f(M * C); L.qkv = b.f(M * 3 * C); L.P = b.f(psz); L.ctx = b.f(M * C);
+      L.ln1 = b.f(M * C); L.qkv = b.f(M * 3 * C); L.P = psz ? b.f(psz) : nullptr; L.lse = lsz ? b.f(lsz) : nullptr; L.ctx = b.f(M * C);
       L.x1 = b.f(M * C); L.ln2 = b.f(M * C); L.hpre = b.f(M * Fh); L.h = b.f(M * Fh);
       L.t = b.f(M * C); L.xout = b.f(M * C);
     }
     w->g_a = b.f(M * C); w->g_b = b.f(M * C); w->g_c = b.f(M * C);
-    w->dh = b.f(M * Fh); w->dqkv = b.f(M * 3 * C); w->dP = b.f(psz);
+    w->dh = b.f(M * Fh); w->dqkv = b.f(M * 3 * C); w->dP = psz ? b.f(psz) : nullptr; w->Dv = lsz ? b.f(lsz) : nullptr;
     w->dcls_ln = b.f((size_t)D.B * C); w->dpe = b.f((size_t)D.B * D.np * C);
   } else {
     // inference: every layer reuses one set of buffers; the residual stream ping-pongs between t and xout
     LayerWs L0;
     L0.mean1 = L0.rstd1 = L0.mean2 = L0.rstd2 = nullptr;
-    L0.ln1 = b.f(M * C); L0.qkv = b.f(M * 3 * C); L0.P = b.f(psz); L0.ctx = b.f(M * C);
+    L0.ln1 = b.f(M * C); L0.qkv = b.f(M * 3 * C); L0.P = psz ? b.f(psz) : nullptr; L0.lse = nullptr; L0.ctx = b.f(M * C);
     L0.x1 = b.f(M * C); L0.ln2 = L0.ln1; L0.hpre = nullptr; L0.h = b.f(M * Fh);
     L0.t = b.f(M * C); L0.xout = b.f(M * C);
     float* ping = L0.xout; float* pong = b.f(M * C);
     for (int l = 0; l < D.L; ++l) { w->layer[l] = L0; w->layer[l].xout = (l & 1) ? pong : ping; }
-    w->g_a = w->g_b = w->g_c = w->dh = w->dqkv = w->dP = w->dcls_ln = w->dpe = nullptr;
+    w->g_a = w->g_b = w->g_c = w->dh = w->dqkv = w->dP = w->Dv = w->dcls_ln = w->dpe = nullptr;
   }
   w->bytes = b.off;
 }
@@ -213,7 +215,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
       LayerWs& L = w.layer[l];
       UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, L.ln1, C, L.mean1, L.rstd1, M, C, st, 1));
       UVC_TRY(linear_fwd(L.ln1, C, w.wr.qkv_w[l], p.qkv_b, L.qkv, 3 * C, M, 3 * C, C, st, UVC_EPI_ROUND_TF32));
-      UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st, save));   // inference never materialises the probabilities
+      UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st, save && L.P != nullptr, save ? L.lse : nullptr));   // fused path: probabilities never reach HBM
       UVC_TRY(linear_fwd(L.ctx, C, w.wr.proj_w[l], p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));     // x1 = x + proj(ctx)
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st, 1));
       UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1), hpre kept
@@ -306,7 +308,8 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
       UVC_TRY(linear_wgrad(dx1, C, L.ctx, C, gp.proj_w, nullptr, M, C, C, st));
       float* dctx = spare1;                                        // dt is dead after the LN2 backward
       UVC_TRY(linear_dgrad(dx1, C, w.wr.proj_w[l], dctx, C, M, C, C, st, UVC_EPI_ROUND_TF32));
-      UVC_TRY(attention_bwd(L.qkv, L.P, dctx, w.dP, w.dqkv, D.B, D.H, D.ntok, D.d, scale, st));
+      if (L.lse) UVC_TRY(attention_bwd_fused(L.qkv, L.lse, L.ctx, dctx, w.Dv, w.dqkv, D.B, D.H, D.ntok, scale, st));   // recompute S, P in tensor memory
+      else UVC_TRY(attention_bwd(L.qkv, L.P, dctx, w.dP, w.dqkv, D.B, D.H, D.ntok, D.d, scale, st));
       UVC_TRY(linear_wgrad(w.dqkv, 3 * C, L.ln1, C, gp.qkv_w, gp.qkv_b, M, 3 * C, C, st));
       UVC_TRY(linear_dgrad(w.dqkv, 3 * C, w.wr.qkv_w[l], spare1, C, M, 3 * C, C, st));                                  // dln1
       // dx = dx1 + LN1'(dln1) + d0 g        (written over spare1)

@@ -194,6 +194,23 @@ def attention_fwd(qkv, B, H, N, d, scale=None, save_P=True):
     return ctx, P
 
 
+def attention_fwd_lse(qkv, B, H, N, d, scale=None):
+    """training forward of the fused path: (ctx, lse[B,H,N]) — no probabilities are materialised"""
+    scale = d ** -0.5 if scale is None else scale
+    lse = torch.empty(B, H, N, device=qkv.device)
+    ctx = torch.empty(B * N, H * d, device=qkv.device)
+    _call("uvc_attention_fwd_lse", _p(qkv), _p(lse), _p(ctx), B, H, N, d, float(scale))
+    return ctx, lse
+
+
+def attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d, scale=None):
+    scale = d ** -0.5 if scale is None else scale
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B, H, N, device=qkv.device)
+    _call("uvc_attention_bwd_fused", _p(qkv), _p(lse), _p(ctx), _p(dctx), _p(ws), _p(dqkv), B, H, N, d, float(scale))
+    return dqkv
+
+
 def attention_bwd(qkv, P, dctx, B, H, N, d, scale=None):
     scale = d ** -0.5 if scale is None else scale
     dP = torch.empty_like(P)
