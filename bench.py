@@ -180,11 +180,15 @@ def run_gpu(a):
         step(x_dev.clone(), y_dev)
     for i in range(a.warmup):
         dev_step(i)
+    if getattr(step, "_timing", None) is not None:
+        step._timing = []          # UVC_STEP_TIMING: report the timed steps only
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     n0 = lib.uvc_launch_count()
     ms = timed(dev_step, a.steps)
+    if os.environ.get("UVC_STEP_TIMING") and rank == 0:
+        print(step.timing_report(), file=sys.stderr); step._timing = None
     launches = int(lib.uvc_launch_count() - n0)
     clk = clocks.stop() if rank == 0 else None
 

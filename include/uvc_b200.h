@@ -121,7 +121,7 @@ UVC_API int uvc_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, c
 UVC_API int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                               const float* gamma, const float* r1, const float* r2, const float* s2_dev,
                               float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t C, void* stream);
-/* Same, and additionally cs_r1[col] += sum_rows r1[row,col], cs_out[col] += sum_rows dx[row,col] (either may be NULL): the bias gradients of
+/* Same, and additionally cs_r1[col] += sum_rows (r1 + s2*r2)[row,col], cs_out[col] += sum_rows dx[row,col] (either may be NULL): the bias gradients of
  * the Linear layers on either side of the norm are column sums of tensors this kernel streams anyway (fc2.bias <- r1 = d(block output),
  * attn.proj.bias <- dx = d(x1) for norm2 of models/model_distilled.py:204,243). */
 UVC_API int uvc_layernorm_bwd_cs(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,

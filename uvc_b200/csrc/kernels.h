@@ -50,7 +50,7 @@ inline uvc_gemm_args gemm_args(int M, int N, int K, uvc_operand A, uvc_operand B
 // split-K factor for a weight-gradient GEMM (few output tiles, very long K): fill ~2 waves of 148 SMs
 inline int wgrad_splits(int M, int N, int K) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
-  int s = (2 * 148 + tiles - 1) / tiles;
+  int s = (2 * 148) / tiles;            // floor: tiles * s CTAs must fit ONE wave of 2 CTAs per SM (a 297th CTA costs a whole second wave)
   const int nkb = (K + 31) / 32;
   if (s > nkb / 4) s = nkb / 4;
   if (s < 1) s = 1;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // dx[row] = r1[row] + s2 * r2[row] + rstd * (g - mean(g) - xhat * mean(g * xhat)),   g = dy * gamma
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (register partials per lane -> smem -> atomics)
 // Optional fused bias gradients of the neighbouring Linears (they are column sums of tensors this kernel touches anyway):
-//   cs_r1[col] += sum_rows r1[row, col]      cs_out[col] += sum_rows dx[row, col]
+//   cs_r1[col] += sum_rows (r1 + s2 * r2)[row, col]      cs_out[col] += sum_rows dx[row, col]
 template <int NV, bool CS>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -112,11 +112,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       res[i] = make_float4(0, 0, 0, 0);
       if (c < nv) {
         const float4 d = dyr[c], xv = xr[c], gm = __ldg(g4 + c);
-        if (r1r) {
-          res[i] = r1r[c];
-          if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
-        }
+        if (r1r) res[i] = r1r[c];
         if (r2r) { const float4 a = r2r[c]; res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w; }
+        if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
         xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
         gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
         sg += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
@@ -434,7 +432,7 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
                   cudaStream_t st, float* cs_r1, float* cs_out) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
   UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
-  UVC_REQUIRE(!cs_r1 || r1, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without r1");
+  UVC_REQUIRE(!cs_r1 || r1 || r2, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without a residual input");
   if (M <= 0) return UVC_OK;
   int blocks = 148 * 6;
   int rpb = (M + blocks - 1) / blocks;

@@ -123,17 +123,20 @@ int linear_fwd(const float* X, long long ldx, const float* W, const float* bias,
 }
 // dX[M,K] = dY[M,N] W[N,K]   (W read MN-major)
 int linear_dgrad(const float* dY, long long lddy, const float* W, float* dX, long long lddx, int M, int N, int K, cudaStream_t st,
-                 int extra_flags = 0, float* aux = nullptr, long long ldaux = 0, float* colsum_out = nullptr) {
+                 int extra_flags = 0, float* aux = nullptr, long long ldaux = 0, float* colsum_out = nullptr, const float* scale_dev = nullptr) {
   uvc_gemm_args a = gemm_args(M, K, N, op_k(dY, lddy), op_mn(W, K), dX, lddx);
   a.flags = extra_flags;
+  a.alpha_dev = scale_dev;              // dY is scaled by a device scalar (the block gate) without materialising the product
   if (aux) { a.aux = aux; a.ldaux = ldaux; }
   if (colsum_out) { a.colsum = colsum_out; a.flags |= UVC_EPI_COLSUM; }   // bias gradient of the layer below, summed in the epilogue
   return gemm_tf32(a, st);
 }
 // dW[N,K] += dY[M,N]^T X[M,K]   (split-K, atomic accumulate) ; db[N] += colsum(dY)
-int linear_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, float* db, int M, int N, int K, cudaStream_t st) {
+int linear_wgrad(const float* dY, long long lddy, const float* X, long long ldx, float* dW, float* db, int M, int N, int K, cudaStream_t st,
+                 const float* scale_dev = nullptr) {
   uvc_gemm_args a = gemm_args(N, K, M, op_mn(dY, lddy), op_mn(X, ldx), dW, K);
   a.flags = UVC_EPI_ATOMIC;
+  a.alpha_dev = scale_dev;
   a.splits = wgrad_splits(N, K, M);
   UVC_TRY(gemm_tf32(a, st));
   if (db) UVC_TRY(colsum(dY, lddy, M, N, nullptr, db, st));
@@ -284,29 +287,25 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
       const LayerWs& L = w.layer[l];
       const float* x = xin[l];
       const float* d = a.blend ? a.blend + 2 * l : nullptr;
-      // gate blend: x_out = d1 t + d0 x  ->  dt = d1 g, dx += d0 g, dd0 = <g,x>, dd1 = <g,t>
+      // gate blend: x_out = d1 t + d0 x  ->  dt = d1 g, dx += d0 g, dd0 = <g,x>, dd1 = <g,t>.  dt is never materialised: the two fc2 GEMMs take d1
+      // as a device-scalar alpha and the LN2 backward adds d1 * g as its scaled residual input.
       const float* dt = g;
-      if (d) {
-        UVC_TRY(blend_dots(g, L.t, x, a.d_blend + 2 * l, (long long)M * C, st));
-        e = cudaMemsetAsync(spare1, 0, xbytes, st);
-        UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: memset: %s", cudaGetErrorString(e));
-        UVC_TRY(scale_add(spare1, g, d + 1, 1.0f, (long long)M * C, st));
-        dt = spare1;
-      }
+      const float* d1 = d ? d + 1 : nullptr;
+      if (d) UVC_TRY(blend_dots(g, L.t, x, a.d_blend + 2 * l, (long long)M * C, st));
       // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2)))
       // Bias gradients are column sums of tensors other kernels stream anyway, so they ride along instead of costing a pass each:
       //   fc1_b <- epilogue of the fc2 dgrad GEMM (sums dhpre), fc2_b / proj_b <- the LN2 backward (sums its residual input dt / its output dx1).
-      UVC_TRY(linear_wgrad(dt, C, L.h, Fh, gp.fc2_w, nullptr, M, C, Fh, st));
-      UVC_TRY(linear_dgrad(dt, C, w.wr.fc2_w[l], w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD | UVC_EPI_ROUND_TF32, L.hpre, Fh, gp.fc1_b));     // dhpre
+      UVC_TRY(linear_wgrad(dt, C, L.h, Fh, gp.fc2_w, nullptr, M, C, Fh, st, d1));
+      UVC_TRY(linear_dgrad(dt, C, w.wr.fc2_w[l], w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD | UVC_EPI_ROUND_TF32, L.hpre, Fh, gp.fc1_b, d1));     // dhpre
       UVC_TRY(linear_wgrad(w.dh, Fh, L.ln2, C, gp.fc1_w, nullptr, M, Fh, C, st));
       UVC_TRY(linear_dgrad(w.dh, Fh, w.wr.fc1_w[l], spare2, C, M, Fh, C, st));                                          // dln2
       // dx1 = dt + LN2'(dln2)
-      UVC_TRY(layernorm_bwd(spare2, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, dt, nullptr, nullptr, spare2, C, gp.norm2_w, gp.norm2_b, M, C, st,
-                            gp.fc2_b, gp.proj_b));
+      UVC_TRY(layernorm_bwd(spare2, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, d ? nullptr : dt, d ? g : nullptr, d1, spare2, C, gp.norm2_w, gp.norm2_b,
+                            M, C, st, gp.fc2_b, gp.proj_b));
       float* dx1 = spare2;
       // ---- attention:  x1 = x + proj(ctx)
       UVC_TRY(linear_wgrad(dx1, C, L.ctx, C, gp.proj_w, nullptr, M, C, C, st));
-      float* dctx = spare1;                                        // dt is dead after the LN2 backward
+      float* dctx = spare1;
       UVC_TRY(linear_dgrad(dx1, C, w.wr.proj_w[l], dctx, C, M, C, C, st, UVC_EPI_ROUND_TF32));
       if (L.lse) UVC_TRY(attention_bwd_fused(L.qkv, L.lse, L.ctx, dctx, w.Dv, w.dqkv, D.B, D.H, D.ntok, scale, st));   // recompute S, P in tensor memory
       else UVC_TRY(attention_bwd(L.qkv, L.P, dctx, w.dP, w.dqkv, D.B, D.H, D.ntok, D.d, scale, st));

@@ -186,19 +186,45 @@ class Stage1Step:
         self.gating_grad_list = []
         self.uvc_fn = uvc_optimizer if args.enable_pruning else uvc_optimizer_gating
         self.last = {}
+        self._timing = [] if os.environ.get("UVC_STEP_TIMING") else None
+
+    def _mark(self, name):
+        """UVC_STEP_TIMING=1: CPU wall clock + CUDA event at every phase boundary (bring-up aid; off by default)"""
+        if self._timing is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True); ev.record()
+        self._timing.append((name, time.perf_counter(), ev))
+
+    def timing_report(self):
+        if not self._timing:
+            return ""
+        torch.cuda.synchronize()
+        agg, prev = {}, None
+        for name, t, ev in self._timing:
+            if prev is not None and name != "start":
+                a = agg.setdefault(name, [0.0, 0.0, 0])
+                a[0] += (t - prev[1]) * 1e3; a[1] += prev[2].elapsed_time(ev); a[2] += 1
+            prev = (name, t, ev)
+        return "\n".join(f"  {k:12s} cpu {v[0]/v[2]:7.3f} ms   gpu-timeline {v[1]/v[2]:7.3f} ms" for k, v in agg.items())
 
     def __call__(self, x, y, epoch=0, total_steps=1):
         args = self.args
+        self._mark("start")
         if len(x) % 2 != 0:
             x, y = x[:-1], y[:-1]
         tau = get_tau(10, 0.1, self.global_step, total_steps) if args.enable_patch_gating == 2 else -1
         if self.mixup_fn is not None:
             x, y = self.mixup_fn(x, y)
+        self._mark("mixup")
         outputs, flops_list = self.ddp_model(x, tau, args.patch_ratio)
+        self._mark("student_fwd")
         loss = self.criterion(x, outputs, y)
+        self._mark("teacher+loss")
         loss.backward()
+        self._mark("backward")
         self.optimizer.step()                 # global-norm clip (max_grad_norm) + AdamW, fused
         self.scheduler.step()
+        self._mark("optimizer")
         self.global_step += 1
         out = {"loss": loss}
         if args.uvc_train:
@@ -210,7 +236,9 @@ class Stage1Step:
                 self.optimizer, minimax_model, s_optimizer, r_optimizer, gating_optimizer, dual_optimizer, args, {"global_step": self.global_step},
                 [], flops_list, args.z_grad_clip, self.global_step, args.gating_interval, self.gating_grad_list)
             out.update(cur_resource=cur_resource, s=s_data, r=r_data, gating=gating_data)
+        self._mark("admm")
         self.optimizer.zero_grad()
+        self._mark("zero_grad")
         self.last = out
         return out
 
