@@ -75,8 +75,9 @@ typedef struct {
 
 enum {
   UVC_EPI_BIAS = 1,        /* v += bias[col] */
-  UVC_EPI_GELU = 2,        /* aux[row,col] = v (pre-activation, if aux != NULL); v = gelu_erf(v) */
-  UVC_EPI_GELU_BWD = 4,    /* v *= gelu'(aux[row,col]) */
+  UVC_EPI_GELU = 2,        /* aux[row,col] = gelu_erf'(v) (if aux != NULL: the derivative at the pre-activation, all the backward needs);
+                              v = gelu_erf(v) */
+  UVC_EPI_GELU_BWD = 4,    /* v *= aux[row,col]   (aux as written by UVC_EPI_GELU: the GELU backward is a multiply) */
   UVC_EPI_RESIDUAL = 8,    /* v += beta * R[row,col] */
   UVC_EPI_ATOMIC = 16,     /* D += v with red.global.add (required when splits > 1) */
   UVC_EPI_ROUND_TF32 = 32, /* round v to nearest TF32 before the store: for outputs that only feed other GEMMs (the

@@ -71,6 +71,13 @@ __device__ __forceinline__ float gelu_f(float x) {
   gelu_parts(x, Phi, e);
   return x * Phi;
 }
+// gelu(x) and gelu'(x) together (the forward epilogue stores the derivative, so the backward epilogue is a plain multiply)
+__device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  float Phi, e;
+  gelu_parts(x, Phi, e);
+  g = x * Phi;
+  dg = fmaf(x * 0.3989422804014327f, e, Phi);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float Phi, e;
   gelu_parts(x, Phi, e);

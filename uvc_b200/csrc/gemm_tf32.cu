@@ -200,28 +200,29 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
           for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
         }
         if (flags & UVC_EPI_GELU) {
-          if (Xrow) {
+          float dg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gelu_both(v[j], v[j], dg[j]);
+          if (Xrow) {                                // aux receives gelu'(pre-activation): all the backward needs
             if (full && vec_ok) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(Xrow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(Xrow + col0 + j) = make_float4(dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) Xrow[col0 + j] = v[j];
+              for (int j = 0; j < 32; ++j) if (col0 + j < p.N) Xrow[col0 + j] = dg[j];
             }
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
         }
         if (flags & UVC_EPI_GELU_BWD) {
           if (full && vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 u = *reinterpret_cast<const float4*>(Xrow + col0 + j);
-              v[j] *= gelu_grad_f(u.x); v[j + 1] *= gelu_grad_f(u.y); v[j + 2] *= gelu_grad_f(u.z); v[j + 3] *= gelu_grad_f(u.w);
+              v[j] *= u.x; v[j + 1] *= u.y; v[j + 2] *= u.z; v[j + 3] *= u.w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] *= gelu_grad_f(Xrow[col0 + j]);
+            for (int j = 0; j < 32; ++j) if (col0 + j < p.N) v[j] *= Xrow[col0 + j];
           }
         }
         if ((flags & UVC_EPI_RESIDUAL) && first_split) {
@@ -503,11 +504,12 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             if (!(colok && i * 4 < rows_left) || (flags & (1 << 30))) continue;   // (bit 30: bring-up, no global traffic)
             v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y); v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
             if (MODE == kEpiGelu) {
-              if (p.aux) *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = v;
-              v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w);
+              float4 dg;                                 // aux receives gelu'(pre-activation): the same exponential gives both, and the backward
+              gelu_both(v.x, v.x, dg.x); gelu_both(v.y, v.y, dg.y); gelu_both(v.z, v.z, dg.z); gelu_both(v.w, v.w, dg.w);   // epilogue becomes a multiply
+              if (p.aux) *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = dg;
             }
             if (MODE == kEpiGeluBwd) {
-              v.x *= gelu_grad_f(rr[i].x); v.y *= gelu_grad_f(rr[i].y); v.z *= gelu_grad_f(rr[i].z); v.w *= gelu_grad_f(rr[i].w);
+              v.x *= rr[i].x; v.y *= rr[i].y; v.z *= rr[i].z; v.w *= rr[i].w;
             } else if (do_res) {
               v.x = fmaf(beta, rr[i].x, v.x); v.y = fmaf(beta, rr[i].y, v.y); v.z = fmaf(beta, rr[i].z, v.z); v.w = fmaf(beta, rr[i].w, v.w);
             }

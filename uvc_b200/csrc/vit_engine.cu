@@ -221,7 +221,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
       UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st, save && L.P != nullptr, save ? L.lse : nullptr));   // fused path: probabilities never reach HBM
       UVC_TRY(linear_fwd(L.ctx, C, w.wr.proj_w[l], p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));     // x1 = x + proj(ctx)
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st, 1));
-      UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1), hpre kept
+      UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1); hpre holds gelu'(fc1) for the backward
       if (a.blend) {
         UVC_TRY(linear_fwd(L.h, Fh, w.wr.fc2_w[l], p.fc2_b, L.t, C, M, C, Fh, st, 0, nullptr, L.x1, C));    // t = x1 + fc2(h)
         UVC_TRY(blend_fwd(L.t, x, a.blend + 2 * l, L.xout, (long long)M * C, st));                            // x <- d1 t + d0 x
