@@ -53,44 +53,88 @@ __global__ void __launch_bounds__(256) colnorm_kernel(const __grid_constant__ WP
   }
 }
 
-// one block per layer: head sums, ranks inside each head (c1), across heads (c2), across neurons (c3)
-__global__ void __launch_bounds__(1024) rank_kernel(int H, int d, int Fh, const float* __restrict__ c1, float* __restrict__ c2,
-                                                    const float* __restrict__ c3, int* __restrict__ rank1, int* __restrict__ rank2,
-                                                    int* __restrict__ rank3) {
+// ranks ("k smallest" == rank < k, ties -> lower index first, as torch.topk(largest=False) on CPU).  grid (L, 1 + ceil(Fh/256)):
+//   blockIdx.y == 0 : head sums (fixed order: deterministic), ranks inside each head (c1) and across heads (c2)
+//   blockIdx.y >= 1 : 256 neurons of the layer each, ranked against all Fh (the O(Fh^2) part, spread over ~7 blocks per layer instead of one)
+__global__ void __launch_bounds__(256) rank_kernel(int H, int d, int Fh, const float* __restrict__ c1, float* __restrict__ c2,
+                                                   const float* __restrict__ c3, int* __restrict__ rank1, int* __restrict__ rank2,
+                                                   int* __restrict__ rank3) {
   __shared__ float sv[kMaxFh];
   __shared__ float sh[kMaxH];
   const int l = blockIdx.x, C = H * d, tid = threadIdx.x;
-  // c1 -> smem, rank inside head
-  for (int i = tid; i < C; i += blockDim.x) sv[i] = c1[(long long)l * C + i];
-  __syncthreads();
-  for (int i = tid; i < C; i += blockDim.x) {
-    const int h = i / d, j = i - h * d;
-    const float v = sv[i];
-    int rk = 0;
-    for (int m = 0; m < d; ++m) { const float u = sv[h * d + m]; rk += (u < v) || (u == v && m < j); }
-    rank1[(long long)l * C + i] = rk;
+  if (blockIdx.y == 0) {
+    for (int i = tid; i < C; i += blockDim.x) sv[i] = c1[(long long)l * C + i];
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) {
+      const int h = i / d, j = i - h * d;
+      const float v = sv[i];
+      int rk = 0;
+      for (int m = 0; m < d; ++m) { const float u = sv[h * d + m]; rk += (u < v) || (u == v && m < j); }
+      rank1[(long long)l * C + i] = rk;
+    }
+    if (tid < H) {        // head sums in a fixed order (deterministic)
+      float s = 0.f;
+      for (int m = 0; m < d; ++m) s += sv[tid * d + m];
+      sh[tid] = s;
+      c2[l * H + tid] = s;
+    }
+    __syncthreads();
+    if (tid < H) {
+      const float v = sh[tid];
+      int rk = 0;
+      for (int m = 0; m < H; ++m) rk += (sh[m] < v) || (sh[m] == v && m < tid);
+      rank2[l * H + tid] = rk;
+    }
+    return;
   }
-  if (tid < H) {        // head sums in a fixed order (deterministic)
-    float s = 0.f;
-    for (int m = 0; m < d; ++m) s += sv[tid * d + m];
-    sh[tid] = s;
-    c2[l * H + tid] = s;
-  }
-  __syncthreads();
-  if (tid < H) {
-    const float v = sh[tid];
-    int rk = 0;
-    for (int m = 0; m < H; ++m) rk += (sh[m] < v) || (sh[m] == v && m < tid);
-    rank2[l * H + tid] = rk;
-  }
-  __syncthreads();
   for (int i = tid; i < Fh; i += blockDim.x) sv[i] = c3[(long long)l * Fh + i];
   __syncthreads();
-  for (int i = tid; i < Fh; i += blockDim.x) {
+  const int i = (blockIdx.y - 1) * 256 + tid;
+  if (i < Fh) {
     const float v = sv[i];
     int rk = 0;
+#pragma unroll 4
     for (int m = 0; m < Fh; ++m) { const float u = sv[m]; rk += (u < v) || (u == v && m < i); }
     rank3[(long long)l * Fh + i] = rk;
+  }
+}
+
+// prox shrink (uvc_utils.py:315-345): W[:, col] *= 1/(1+2 lr p) for the bottom-ceil(r) columns of each head, then *= 1/(1+2 lr y) for the
+// columns of the bottom-ceil(s0) heads (W1) / the bottom-ceil(s1) neurons (W3).  grid (ceil(cols/128), L, 2), block (32, 8): a thread owns
+// 4 adjacent columns (one 128-bit access per row) and every 8th row; threads whose 4 columns are all unselected exit without touching memory.
+__global__ void __launch_bounds__(256) prox_kernel(const __grid_constant__ WPtrs P, int H, int d, int Fh, const int* __restrict__ rank1,
+                                                   const int* __restrict__ rank2, const int* __restrict__ rank3, const float* __restrict__ s,
+                                                   const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ p, double lr) {
+  const int which = blockIdx.z, l = blockIdx.y, C = H * d;
+  const int cols = which ? Fh : C;
+  const int col0 = blockIdx.x * 128 + threadIdx.x * 4;
+  if (col0 >= cols) return;
+  float fa[4], fb[4];
+  bool any = false;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int col = col0 + e;
+    fa[e] = fb[e] = 1.0f;
+    if (col >= cols) continue;
+    if (which == 0) {
+      const int h = col / d;
+      const int R = (int)ceilf(r[l * H + h]), S0 = (int)ceilf(s[l * 2 + 0]);
+      if (rank1[(long long)l * C + col] < R) { fa[e] = 1.0f / (float)(1.0 + 2.0 * lr * (double)p[l * H + h]); any = true; }
+      if (rank2[l * H + h] < S0) { fb[e] = 1.0f / (float)(1.0 + 2.0 * lr * (double)y[l * 2 + 0]); any = true; }
+    } else {
+      const int S1 = (int)ceilf(s[l * 2 + 1]);
+      if (rank3[(long long)l * Fh + col] < S1) { fa[e] = 1.0f / (float)(1.0 + 2.0 * lr * (double)y[l * 2 + 1]); any = true; }
+    }
+  }
+  if (!any) return;
+  float* W = (which ? P.w3[l] : P.w1[l]) + col0;
+  // the reference multiplies selected columns by the first factor, then by the second: keep the two roundings (x * 1.0f is exact)
+#pragma unroll 4
+  for (int row = threadIdx.y; row < C; row += 8) {
+    float4* q = reinterpret_cast<float4*>(W + (long long)row * cols);
+    float4 v = *q;
+    v.x = (v.x * fa[0]) * fb[0]; v.y = (v.y * fa[1]) * fb[1]; v.z = (v.z * fa[2]) * fb[2]; v.w = (v.w * fa[3]) * fb[3];
+    *q = v;
   }
 }
 
@@ -228,11 +272,11 @@ __device__ __forceinline__ float block_absmax(float v, float* red) {
   return m;
 }
 
-// single block of 256 threads
-__global__ void __launch_bounds__(256) admm_primal_kernel(const AdmmK k) {
+// single block of 1024 threads (the scans over L*Fh ranks are latency-bound: more threads = fewer serial rounds)
+__global__ void __launch_bounds__(1024) admm_primal_kernel(const AdmmK k) {
   __shared__ float S[kMaxL * 2], R[kMaxL * kMaxH], gs[kMaxL * 2], gr[kMaxL * kMaxH], kth2[kMaxL], kth3[kMaxL], kth1[kMaxL * kMaxH];
   __shared__ LayerTerms T[kMaxL];
-  __shared__ float red[16];
+  __shared__ float red[40];
   const int tid = threadIdx.x, L = k.L, H = k.H, d = k.d, Fh = k.Fh, C = H * d;
   for (int i = tid; i < L * 2; i += blockDim.x) S[i] = ceilf(k.s[i]);
   for (int i = tid; i < L * H; i += blockDim.x) R[i] = ceilf(k.r[i]);
@@ -338,10 +382,10 @@ __global__ void __launch_bounds__(256) admm_primal_kernel(const AdmmK k) {
 }
 
 // dual ascent with the NEW s, r (uvc_optimizer.py:126-135, uvc_utils.py:231-269,403-406)
-__global__ void __launch_bounds__(256) admm_dual_kernel(const AdmmK k) {
+__global__ void __launch_bounds__(1024) admm_dual_kernel(const AdmmK k) {
   __shared__ float S[kMaxL * 2], R[kMaxL * kMaxH], acc2[kMaxL], acc3[kMaxL], acc1[kMaxL * kMaxH];
   __shared__ LayerTerms T[kMaxL];
-  __shared__ float red[16];
+  __shared__ float red[40];
   const int tid = threadIdx.x, L = k.L, H = k.H, d = k.d, Fh = k.Fh;
   const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
   for (int i = tid; i < L * 2; i += blockDim.x) S[i] = ceilf(k.s[i]);
@@ -379,7 +423,7 @@ __global__ void __launch_bounds__(256) admm_dual_kernel(const AdmmK k) {
 __global__ void __launch_bounds__(256) admm_resource_kernel(const AdmmK k) {
   __shared__ float S[kMaxL * 2], R[kMaxL * kMaxH];
   __shared__ LayerTerms T[kMaxL];
-  __shared__ float red[16];
+  __shared__ float red[40];
   for (int i = threadIdx.x; i < k.L * 2; i += blockDim.x) S[i] = ceilf(k.s[i]);
   for (int i = threadIdx.x; i < k.L * k.H; i += blockDim.x) R[i] = ceilf(k.r[i]);
   __syncthreads();
@@ -438,7 +482,7 @@ int admm_scores(const uvc_admm_args& a, cudaStream_t st) {
   const int mx = a.Fh > C ? a.Fh : C;
   colnorm_kernel<<<dim3((mx + 31) / 32, a.L, 2), dim3(32, 8), 0, st>>>(make_ptrs(a, false), C, a.Fh, a.c1, a.c3);
   if ((rc = check_launch("admm colnorm"))) return rc;
-  rank_kernel<<<a.L, 1024, 0, st>>>(a.H, a.d, a.Fh, a.c1, a.c2, a.c3, a.rank1, a.rank2, a.rank3);
+  rank_kernel<<<dim3(a.L, 1 + (a.Fh + 255) / 256), 256, 0, st>>>(a.H, a.d, a.Fh, a.c1, a.c2, a.c3, a.rank1, a.rank2, a.rank3);
   return check_launch("admm rank");
 }
 
@@ -448,8 +492,13 @@ int admm_prox(const uvc_admm_args& a, cudaStream_t st) {
   UVC_REQUIRE(a.s && a.r && a.y && a.p, UVC_ERR_BAD_ARG, "admm_prox: NULL s / r / y / p");
   const int C = a.H * a.d;
   const int mx = a.Fh > C ? a.Fh : C;
-  prox_mask_kernel<<<dim3((mx + 127) / 128, a.L, 2), 128, 0, st>>>(make_ptrs(a, false), 0, a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y,
-                                                                  a.p, a.lr);
+  bool vec_ok = (C % 4 == 0) && (a.Fh % 4 == 0);
+  for (int l = 0; l < a.L && vec_ok; ++l) vec_ok = ((reinterpret_cast<uintptr_t>(a.w1[l]) | reinterpret_cast<uintptr_t>(a.w3[l])) & 15) == 0;
+  if (vec_ok)
+    prox_kernel<<<dim3((mx + 127) / 128, a.L, 2), dim3(32, 8), 0, st>>>(make_ptrs(a, false), a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y, a.p, a.lr);
+  else
+    prox_mask_kernel<<<dim3((mx + 127) / 128, a.L, 2), 128, 0, st>>>(make_ptrs(a, false), 0, a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y,
+                                                                    a.p, a.lr);
   return check_launch("admm prox");
 }
 
@@ -471,7 +520,7 @@ int admm_primal(const uvc_admm_args& a, cudaStream_t st) {
   if ((rc = check_scalar(a))) return rc;
   UVC_REQUIRE(a.warmup || (a.y && a.p && a.z), UVC_ERR_BAD_ARG, "admm_primal: NULL y / p / z");
   UVC_REQUIRE(a.L * 2 <= 256, UVC_ERR_BAD_SHAPE, "admm_primal: too many layers");
-  admm_primal_kernel<<<1, 256, 0, st>>>(make_k(a));
+  admm_primal_kernel<<<1, 1024, 0, st>>>(make_k(a));
   return check_launch("admm primal");
 }
 
@@ -480,7 +529,7 @@ int admm_dual(const uvc_admm_args& a, cudaStream_t st) {
   if (rc) return rc;
   if ((rc = check_scalar(a))) return rc;
   UVC_REQUIRE(a.y && a.p && a.z, UVC_ERR_BAD_ARG, "admm_dual: NULL y / p / z");
-  admm_dual_kernel<<<1, 256, 0, st>>>(make_k(a));
+  admm_dual_kernel<<<1, 1024, 0, st>>>(make_k(a));
   return check_launch("admm dual");
 }
 

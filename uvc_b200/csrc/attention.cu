@@ -460,19 +460,33 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
     const int N = p.N;
     const int tid2 = threadIdx.x - 64;
     uint32_t ia = 0;
+    // The per-row statistics are fetched one step AHEAD (phase 1: next tile's row values into registers; phase 2: the next head's 208 column
+    // values, one per thread): issued right before use, their DRAM latency sat on the critical path of every tile (10-15 % of the kernel).
+    float nx_lse = INFINITY, nx_D = 0.f;
+    auto fetch = [&](int hd2, int t2) {
+      nx_lse = INFINITY; nx_D = 0.f;
+      if (hd2 >= nheads) return;
+      const long long sr = (long long)hd2 * N;     // (b*H + h) * N with hd2 = b*H + h
+      const int idx = (PHASE == 1) ? t2 * 128 + q * 32 + lane : tid2;
+      if (idx < N) { nx_lse = __ldg(p.lse + sr + idx); nx_D = __ldg(p.Dv + sr + idx); }
+    };
+    fetch(blockIdx.x, 0);
     for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x) {
       const int b = hd / p.H, h = hd % p.H;
-      const long long srow = ((long long)b * p.H + h) * N;
       if (PHASE == 2) {                              // per-query statistics of this head, indexed by score column
         named_bar_sync(1, 256);
-        s_lse[tid2] = tid2 < N ? __ldg(p.lse + srow + tid2) : INFINITY;
-        s_D[tid2] = tid2 < N ? __ldg(p.Dv + srow + tid2) : 0.f;
+        s_lse[tid2] = nx_lse;
+        s_D[tid2] = nx_D;
         named_bar_sync(1, 256);
+        fetch(hd + gridDim.x, 0);
       }
       for (int t = 0; t < ntiles; ++t, ++ia) {
         const int row = t * 128 + q * 32 + lane;     // phase 1: query row ; phase 2: key row
         float lse_r = INFINITY, D_r = 0.f;
-        if (PHASE == 1 && row < N) { lse_r = __ldg(p.lse + srow + row); D_r = __ldg(p.Dv + srow + row); }
+        if (PHASE == 1) {
+          lse_r = nx_lse; D_r = nx_D;
+          if (t + 1 < ntiles) fetch(hd, t + 1); else fetch(hd + gridDim.x, 0);
+        }
         mbar_wait(sc_full, ia & 1u);
         tc_fence_after();
 #pragma unroll 1
