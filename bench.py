@@ -231,7 +231,9 @@ def run_gpu(a):
     torch.cuda.synchronize()
     import ctypes
     t_ms, t_fl, n_l = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-    lib.uvc_gemm_profile_read(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(n_l))
+    lib.uvc_gemm_profile_read_kind(2, ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(n_l))       # the dominant kernel: persistent CTA-pair GEMM
+    a_ms, a_fl, a_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    lib.uvc_gemm_profile_read_kind(0, ctypes.byref(a_ms), ctypes.byref(a_fl), ctypes.byref(a_n))       # every GEMM launch (both kernels)
     lib.uvc_gemm_profile(0)
     barrier()
 
@@ -240,6 +242,12 @@ def run_gpu(a):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm2_traffic.json")) as f:     # dram bytes per launch of the same kernel, from an ncu capture of this bench
+            traffic = json.load(f)
+    except Exception:
+        pass
     imgs = B * world * a.steps
     value = imgs / (ms / 1e3)
     step_flops = 4 * DENSE_FWD_FLOPS[MODEL] * B          # student fwd + bwd (2x) + dense teacher fwd, reference MAC accounting
@@ -257,11 +265,18 @@ def run_gpu(a):
                 "h2d_bytes_per_step": int(x_host[0].numel() * 4 + y_host[0].numel() * 8), "d2h_bytes_per_step": int(d2h[0])},
         "gpu_launches": launches,
         "step_tflops_per_gpu": round(step_flops / (ms / a.steps / 1e3) / 1e12, 1),
-        "roofline": {"bound": "tensor", "kernel": "uvc::gemm_tf32_kernel (tcgen05.mma kind::tf32)", "achieved": round(gemm_tflops, 1),
-                     "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_tflops / tf32_peak, 3), "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "uvc::gemm2_tf32_kernel (persistent CTA pairs, tcgen05.mma cta_group::2 kind::tf32)",
+                     "achieved": round(gemm_tflops, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_tflops / tf32_peak, 3),
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_source": traffic["source"] if traffic else None,
+                     "algorithmic_flops_per_launch": round(t_fl.value / max(1, n_l.value)),
+                     "avg_launch_us": round(t_ms.value * 1e3 / max(1, n_l.value), 2),
                      "peak_source": f"TF32 dense = 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}); bf16 sustained {peaks['bf16_sustained']}",
-                     "launches_per_step": int(n_l.value // 2), "gemm_ms_per_step": round(t_ms.value / 2, 3),
-                     "how": "CUDA-event pair around every GEMM launch of 2 instrumented steps run right after the timed region",
+                     "launches_per_step": int(n_l.value // 2), "kernel_ms_per_step": round(t_ms.value / 2, 3),
+                     "all_gemm_launches_per_step": int(a_n.value // 2), "all_gemm_ms_per_step": round(a_ms.value / 2, 3),
+                     "all_gemm_tflops": round((a_fl.value / max(a_ms.value, 1e-9)) / 1e9, 1),
+                     "how": "CUDA-event pair on the launching stream around every GEMM launch of 2 instrumented steps run right after the timed region; "
+                            "achieved = sum of 2*M*N*K over the CTA-pair kernel's launches / sum of their durations",
                      "step_frac_of_tf32_peak": round(step_flops / (ms / a.steps / 1e3) / 1e12 / tf32_peak, 3)},
     }
     out["cpu_baseline"] = run_cpu_sample(steps=2, warmup=1) if world == 1 and not a.no_cpu_baseline else None

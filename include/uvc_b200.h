@@ -51,6 +51,8 @@ UVC_API long long uvc_launch_count(void);      /* kernels this library has launc
  * returns the summed kernel time, the summed algorithmic FLOPs (2*M*N*K*batch) and the number of launches. */
 UVC_API int uvc_gemm_profile(int enable);
 UVC_API int uvc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
+/* same, restricted to one kernel: kind 1 = gemm_tf32_kernel (128 x 128 tiles), 2 = gemm2_tf32_kernel (persistent CTA pairs), 0 = both */
+UVC_API int uvc_gemm_profile_read_kind(int kind, double* total_ms, double* total_flops, long long* launches);
 
 /* ------------------------------------------------------------------------------------------
  * Batched TF32 tensor-core GEMM (tcgen05.mma + TMEM accumulator + TMA operand staging)

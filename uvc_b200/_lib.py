@@ -85,7 +85,7 @@ UVC_MAX_DEPTH = 32
 
 # every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_tf32",
+    "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_profile_read_kind", "uvc_gemm_tf32",
     "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_layernorm_bwd_cs", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
     "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
     "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
@@ -162,6 +162,8 @@ def load():
     lib.uvc_gemm_profile.argtypes = [C.c_int]; lib.uvc_gemm_profile.restype = C.c_int
     lib.uvc_gemm_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     lib.uvc_gemm_profile_read.restype = C.c_int
+    lib.uvc_gemm_profile_read_kind.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    lib.uvc_gemm_profile_read_kind.restype = C.c_int
     lib.uvc_attn_ldp.argtypes = [i32]; lib.uvc_attn_ldp.restype = i32
     lib.uvc_vit_workspace_bytes.argtypes = [C.POINTER(VitDims), i32]; lib.uvc_vit_workspace_bytes.restype = C.c_uint64
     _lib = lib

@@ -15,7 +15,7 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // counts the launch; cudaGetLastError -> UVC_ERR_CUDA
 long long launch_count();
 bool prof_enabled();
-void prof_begin(cudaStream_t st, double flops);
+void prof_begin(cudaStream_t st, double flops, int kind = 1);   // kind: 1 = 128x128 kernel, 2 = CTA-pair kernel
 void prof_end(cudaStream_t st);
 
 #define UVC_REQUIRE(cond, code, ...)                                   \

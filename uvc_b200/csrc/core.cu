@@ -31,12 +31,12 @@ int check_launch(const char* what) {
 
 // ---- optional per-launch timing of the GEMM kernel with CUDA events on the launching stream (bench.py's roofline leg)
 static bool g_prof_on = false;
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; double flops; int kind; };
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 bool prof_enabled() { return g_prof_on; }
-void prof_begin(cudaStream_t st, double flops) {
-  ProfRec r; r.flops = flops;
+void prof_begin(cudaStream_t st, double flops, int kind) {
+  ProfRec r; r.flops = flops; r.kind = kind;
   cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
   cudaEventRecord(r.e0, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -54,6 +54,22 @@ extern "C" int uvc_gemm_profile(int enable) {
   for (auto& r : uvc::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   uvc::g_prof.clear();
   uvc::g_prof_on = enable != 0;
+  return UVC_OK;
+}
+extern "C" int uvc_gemm_profile_read_kind(int kind, double* total_ms, double* total_flops, long long* launches) {
+  std::lock_guard<std::mutex> lk(uvc::g_prof_mu);
+  double ms = 0.0, fl = 0.0;
+  long long n = 0;
+  for (auto& r : uvc::g_prof) {
+    if (kind && r.kind != kind) continue;
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) { uvc::set_error("uvc_gemm_profile_read_kind: event sync failed"); return UVC_ERR_CUDA; }
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms += t; fl += r.flops; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = n;
   return UVC_OK;
 }
 extern "C" int uvc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {

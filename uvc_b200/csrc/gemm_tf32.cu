@@ -771,7 +771,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
     kp.units = (int)units;
     const int np = units < pairs ? (int)units : pairs;
     const bool prof2 = prof_enabled();
-    if (prof2) prof_begin(st, 2.0 * a.M * a.N * (double)a.K);
+    if (prof2) prof_begin(st, 2.0 * a.M * a.N * (double)a.K, 2);
     if (bn2 == 256) rc = launch2<256, 6>(kp, np, st);
     else if (bn2 == 192) rc = launch2<192, 6>(kp, np, st);
     else rc = launch2<128, 8>(kp, np, st);
