@@ -48,7 +48,10 @@ def uvc_args_namespace(H, **over):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler is started before the warm-up (nvidia-smi takes a
+    second or more to produce its first line on an 8-GPU box) and every line is stamped on arrival, so the summary can be restricted to the
+    timed window; if that window was too short to catch a sample, the samples of the following end-to-end leg (same step, under load) are used
+    and the summary says so."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -57,7 +60,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -65,20 +68,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, windows):
+        """windows: [(t0, t1, label), ...] in preference order"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        num = lambda v: v.replace(".", "").isdigit()
+        for t0, t1, label in windows:
+            rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05 and len(r) >= 7]
+            if rows:
+                break
+        else:
+            rows, label = [r for _, r in self.rows if len(r) >= 7], "whole run"
+        sm = [float(r[0]) for r in rows if num(r[0])]
+        mx = [float(r[1]) for r in rows if num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in rows if num(r[2])]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": label}
 
 
 def measured_peaks():
@@ -178,19 +189,20 @@ def run_gpu(a):
     # ---- device-resident arm (inputs already in HBM; the step's own 77 MB clone + mixup happen inside)
     def dev_step(i):
         step(x_dev.clone(), y_dev)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for i in range(a.warmup):
         dev_step(i)
     if getattr(step, "_timing", None) is not None:
         step._timing = []          # UVC_STEP_TIMING: report the timed steps only
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     n0 = lib.uvc_launch_count()
+    w0 = time.time()
     ms = timed(dev_step, a.steps)
+    w1 = time.time()
     if os.environ.get("UVC_STEP_TIMING") and rank == 0:
         print(step.timing_report(), file=sys.stderr); step._timing = None
     launches = int(lib.uvc_launch_count() - n0)
-    clk = clocks.stop() if rank == 0 else None
 
     # ---- end-to-end arm: pinned host -> device every step (double-buffered on a copy stream), results read back every step
     copy_stream = torch.cuda.Stream(device)
@@ -222,7 +234,10 @@ def run_gpu(a):
         return loss
     for i in range(min(3, a.warmup)):
         e2e_step(i)
+    w2 = time.time()
     ms_e2e = timed(e2e_step, a.steps)
+    w3 = time.time()
+    clk = clocks.stop([(w0, w1, "timed region"), (w2, w3, "end-to-end leg (timed region too short for a sample)")]) if rank == 0 else None
 
     # ---- roofline leg: every GEMM launch of 2 instrumented steps timed with a CUDA-event pair on the launching stream
     lib.uvc_gemm_profile(1)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 3
+#define UVC_ABI_VERSION 4
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -167,9 +167,10 @@ UVC_API int uvc_attention_fwd(const float* qkv, float* P, float* ctx, int32_t B,
  * scaled scores in the log2 domain (P = exp2(S * scale * log2(e) - lse)), 4 bytes per row instead of an 800-byte row of P. */
 UVC_API int uvc_attention_fwd_lse(const float* qkv, float* lse, float* ctx, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
 /* Fused backward with recomputation (autograd backward of models/model_distilled.py:175-185): dqkv [B*N, 3*H*d] from dctx, the forward's
- * ctx and lse; D_ws is [B,H,N] scratch (rowsum(dctx .* ctx)).  Scores, probabilities and dS live only in tensor memory. */
+ * ctx and lse; D_ws is [B,H,N] scratch (rowsum(dctx .* ctx)).  Scores, probabilities and dS live only in tensor memory.
+ * dqkv_bias (optional, [3*H*d]) accumulates the column sums of dqkv, i.e. the gradient of attn.qkv.bias, in the same pass. */
 UVC_API int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv,
-                                    int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+                                    float* dqkv_bias, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
 /* dqkv [B*N, 3*H*d] from dctx [B*N, H*d]; dP is scratch of the same size as P */
 UVC_API int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv,
                               int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);

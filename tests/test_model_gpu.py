@@ -127,3 +127,32 @@ def test_backward_accumulates_like_autograd():
     (o, _), _ = m(x); o.square().mean().backward()
     assert rel(m.blocks[0].mlp.fc1.weight.grad, g1) < 1e-3
     assert m.blocks[0].mlp.fc1.weight.grad.data_ptr() >= m.flat_grad.data_ptr()
+
+
+@pytest.mark.parametrize("model_type,depth,B", [("deit_base_patch16_224", 2, 2), ("deit_small_patch16_224", 2, 3)])
+def test_train_step_matches_oracle_at_other_widths(model_type, depth, B):
+    """BASELINE.json configs 3/4 widths (C = 384 / 768, H = 6 / 12): logits, loss and every gradient of one gated training step against the
+    oracle on this box's CPU (the golden train step is DeiT-Tiny)."""
+    from uvc_b200 import ops
+    from uvc_b200.models.model_distilled import _VitFunction, _engine_param_list
+    sd, dims = fx.make_state_dict(model_type, depth, seed=17)
+    x, _ = fx.make_batch(B, seed=9)
+    tgt = fx.soft_targets(B, seed=9)
+    t_logits = torch.randn(B, 1000, generator=torch.Generator().manual_seed(3))
+    blend0 = torch.tensor([[0.3, 0.7], [0.55, 0.45]])
+    m = build(model_type, depth, sd).train()
+    blend = blend0.cuda().contiguous().requires_grad_(True)
+    params = [p for _, p in _engine_param_list(m)]
+    logits = _VitFunction.apply(m, x.cuda(), blend, None, None, None, *params)
+    out, dl = ops.distill_loss(logits.detach(), t_logits.cuda(), tgt.cuda(), 0.1, 1.0)
+    logits.backward(dl)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    br = blend0.clone().requires_grad_(True)
+    lo = vo.forward(sdr, x, depth, dims["num_heads"], blend=br)
+    loss, _, _ = vo.distillation_loss(lo, t_logits, tgt, 0.1, 1.0)
+    loss.backward()
+    assert rel(logits.detach(), lo.detach()) < LOGIT_TOL
+    assert abs(out[0].item() - float(loss)) < 2e-3 * abs(float(loss))
+    bad = [(k, rel(p.grad, sdr[k].grad)) for k, p in m.named_parameters() if p.grad is not None and not rel(p.grad, sdr[k].grad) < GRAD_TOL]
+    assert not bad, bad
+    assert rel(blend.grad, br.grad) < GRAD_TOL

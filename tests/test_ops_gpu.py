@@ -279,7 +279,9 @@ def test_attention_fused_backward(ops, B, H, N):
     assert rel(lse * 0.6931471805599453, torch.logsumexp(s_.detach(), -1)) < 1e-4
     dctx = ops.round_tf32(rn(B * N, C, seed=7))
     ref.backward(dctx)
-    dqkv = ops.attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d)
+    db = torch.ones(3 * C, device="cuda")
+    dqkv = ops.attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d, dbias=db)
+    assert rel(db - 1, q.grad.sum(0)) < 2 * TF32_TOL          # fused qkv bias gradient (column sums of dqkv)
     g = q.grad.view(B * N, 3, C)
     got = dqkv.view(B * N, 3, C)
     for i, nm in enumerate("qkv"):

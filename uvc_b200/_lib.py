@@ -145,7 +145,7 @@ def load():
         "uvc_attention_fwd": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_attention_bwd": [vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_attention_fwd_lse": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
-        "uvc_attention_bwd_fused": [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_attention_bwd_fused": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_distill_loss": [vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp],
         "uvc_sqnorm_accum": [vp, i64, vp, vp],
         "uvc_clip_adamw": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],

@@ -294,6 +294,20 @@ static int check_attn(int B, int H, int N, int d) {
 // view of dO and Q for the output MMAs while the elementwise pass runs (the tensor core accepts 32-bit MN-major operands only in that layout,
 // and K-major operands only in the 16 B atom layout, so one staged copy cannot serve both roles).
 // ====================================================================================================================
+// v[j] of lane l = element (row l, column j) of a 32 x 32 block; on return v[0] of lane c is the sum of column c over the 32 rows
+__device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = upper ? v[k] : v[k + s];
+      const float keep = upper ? v[k + s] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
 constexpr int kBABytes = 2 * 128 * 128;       // one A tile: 2 k-blocks x 128 rows x 128 B
 constexpr int kBBBytes = 2 * kANK * 128;      // one B operand: 2 x 208 rows x 128 B
 
@@ -303,6 +317,7 @@ struct alignas(64) AttnBwdParams {
   CUtensorMap tmC0, tmC1;      // output B operands (MN-major, 32 B atoms):   phase 1: K, -     phase 2: Q, dO
   const float* lse; const float* Dv;    // [B, H, N]
   float* out0; float* out1;    // phase 1: dq, -   phase 2: dv, dk   (pointers to column 0 of the head-0 slice inside dqkv, row stride ldo)
+  float* db0; float* db1;      // optional bias gradients of the same slices (column sums over all rows, accumulated with atomics), or NULL
   long long ldo;
   int B, H, N, ntiles;
   float scale, scale_log2e;
@@ -548,6 +563,20 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
+        if (p.db0) {
+          // qkv bias gradient = column sums of dq / dk / dv: a 32 x 32 transpose-reduce over the warp (31 shuffles) leaves column `lane` in each lane
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = row < N ? __uint_as_float(o0[j]) : 0.f;
+          warp_colsum32(v, lane);
+          atomicAdd(p.db0 + h * 64 + hh * 32 + lane, v[0]);
+          if (PHASE == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = row < N ? __uint_as_float(o1[j]) : 0.f;
+            warp_colsum32(v, lane);
+            atomicAdd(p.db1 + h * 64 + hh * 32 + lane, v[0]);
+          }
+        }
         if (row < N) {
           const long long off = ((long long)b * N + row) * p.ldo + h * 64 + hh * 32;
 #pragma unroll
@@ -659,7 +688,7 @@ static int attn_tmap(CUtensorMap* tm, const float* base, long long ld, int B, in
 
 // fused backward with recomputation: needs the forward's lse [B,H,N], ctx and a [B,H,N] scratch for D = rowsum(dctx .* ctx)
 int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* Dv, float* dqkv, int B, int H, int N, float scale,
-                        cudaStream_t st) {
+                        cudaStream_t st, float* dqkv_bias) {
   UVC_REQUIRE(N <= kANK, UVC_ERR_BAD_SHAPE, "attention_bwd_fused: N=%d > %d", N, kANK);
   const long long C = (long long)H * 64, ld3 = 3 * C;
   const float* q = qkv; const float* k = qkv + C; const float* v = qkv + 2 * C;
@@ -688,6 +717,7 @@ int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, co
   if ((rc = attn_tmap(&kp.tmC0, k, ld3, B, H, N, kANK, true, "attn bwd K (MN)"))) return rc;
   kp.tmC1 = kp.tmC0;
   kp.out0 = dqkv; kp.out1 = nullptr;
+  kp.db0 = dqkv_bias; kp.db1 = nullptr;
   attn_bwd_kernel<1><<<grid, kAThreads, smem1, st>>>(kp);
   if ((rc = check_launch("attn_bwd_kernel<1>"))) return rc;
   // phase 2: dK, dV
@@ -698,6 +728,7 @@ int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, co
   if ((rc = attn_tmap(&kp.tmC0, q, ld3, B, H, N, kANK, true, "attn bwd Q (MN)"))) return rc;
   if ((rc = attn_tmap(&kp.tmC1, dctx, C, B, H, N, kANK, true, "attn bwd dO (MN)"))) return rc;
   kp.out0 = dqkv + 2 * C; kp.out1 = dqkv + C;
+  kp.db0 = dqkv_bias ? dqkv_bias + 2 * C : nullptr; kp.db1 = dqkv_bias ? dqkv_bias + C : nullptr;
   attn_bwd_kernel<2><<<grid, kAThreads, smem2, st>>>(kp);
   return check_launch("attn_bwd_kernel<2>");
 }
@@ -741,11 +772,11 @@ extern "C" int uvc_attention_fwd_lse(const float* qkv, float* lse, float* ctx, i
   UVC_REQUIRE(qkv && lse && ctx, UVC_ERR_BAD_ARG, "uvc_attention_fwd_lse: NULL pointer");
   return uvc::attention_fwd(qkv, nullptr, ctx, B, H, N, d, scale, static_cast<cudaStream_t>(stream), false, lse);
 }
-extern "C" int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv, int32_t B,
-                                       int32_t H, int32_t N, int32_t d, float scale, void* stream) {
+extern "C" int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv,
+                                       float* dqkv_bias, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream) {
   UVC_REQUIRE(qkv && lse && ctx && dctx && D_ws && dqkv, UVC_ERR_BAD_ARG, "uvc_attention_bwd_fused: NULL pointer");
   UVC_REQUIRE(uvc::attn_fused_ok(N, d), UVC_ERR_BAD_SHAPE, "uvc_attention_bwd_fused: needs d == 64 and N <= 208 (got d=%d, N=%d)", d, N);
-  return uvc::attention_bwd_fused(qkv, lse, ctx, dctx, D_ws, dqkv, B, H, N, scale, static_cast<cudaStream_t>(stream));
+  return uvc::attention_bwd_fused(qkv, lse, ctx, dctx, D_ws, dqkv, B, H, N, scale, static_cast<cudaStream_t>(stream), dqkv_bias);
 }
 extern "C" int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int32_t B, int32_t H, int32_t N,
                                  int32_t d, float scale, void* stream) {

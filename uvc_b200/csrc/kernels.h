@@ -33,7 +33,7 @@ int attn_ldp(int N);
 int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P = true, float* lse = nullptr);
 bool attn_fused_ok(int N, int d);     // the fused tcgen05 attention kernels cover d == 64, N <= 208
 int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* Dv, float* dqkv, int B, int H, int N, float scale,
-                        cudaStream_t st);
+                        cudaStream_t st, float* dqkv_bias = nullptr);   // dqkv_bias [3*H*64]: += column sums of dqkv (the qkv bias gradient)
 int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int B, int H, int N, int d, float scale,
                   cudaStream_t st);
 

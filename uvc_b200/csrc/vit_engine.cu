@@ -307,9 +307,10 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
       UVC_TRY(linear_wgrad(dx1, C, L.ctx, C, gp.proj_w, nullptr, M, C, C, st));
       float* dctx = spare1;
       UVC_TRY(linear_dgrad(dx1, C, w.wr.proj_w[l], dctx, C, M, C, C, st, UVC_EPI_ROUND_TF32));
-      if (L.lse) UVC_TRY(attention_bwd_fused(L.qkv, L.lse, L.ctx, dctx, w.Dv, w.dqkv, D.B, D.H, D.ntok, scale, st));   // recompute S, P in tensor memory
+      // fused path: S, P recomputed in tensor memory; its epilogues also sum the columns of dqkv (the qkv bias gradient)
+      if (L.lse) UVC_TRY(attention_bwd_fused(L.qkv, L.lse, L.ctx, dctx, w.Dv, w.dqkv, D.B, D.H, D.ntok, scale, st, gp.qkv_b));
       else UVC_TRY(attention_bwd(L.qkv, L.P, dctx, w.dP, w.dqkv, D.B, D.H, D.ntok, D.d, scale, st));
-      UVC_TRY(linear_wgrad(w.dqkv, 3 * C, L.ln1, C, gp.qkv_w, gp.qkv_b, M, 3 * C, C, st));
+      UVC_TRY(linear_wgrad(w.dqkv, 3 * C, L.ln1, C, gp.qkv_w, L.lse ? nullptr : gp.qkv_b, M, 3 * C, C, st));
       UVC_TRY(linear_dgrad(w.dqkv, 3 * C, w.wr.qkv_w[l], spare1, C, M, 3 * C, C, st));                                  // dln1
       // dx = dx1 + LN1'(dln1) + d0 g        (written over spare1)
       UVC_TRY(layernorm_bwd(spare1, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st));

@@ -203,11 +203,12 @@ def attention_fwd_lse(qkv, B, H, N, d, scale=None):
     return ctx, lse
 
 
-def attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d, scale=None):
+def attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d, scale=None, dbias=None):
+    """dqkv (and, accumulated into `dbias` [3*H*d] if given, the qkv bias gradient = column sums of dqkv)"""
     scale = d ** -0.5 if scale is None else scale
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(B, H, N, device=qkv.device)
-    _call("uvc_attention_bwd_fused", _p(qkv), _p(lse), _p(ctx), _p(dctx), _p(ws), _p(dqkv), B, H, N, d, float(scale))
+    _call("uvc_attention_bwd_fused", _p(qkv), _p(lse), _p(ctx), _p(dctx), _p(ws), _p(dqkv), _p(dbias), B, H, N, d, float(scale))
     return dqkv
 
 
