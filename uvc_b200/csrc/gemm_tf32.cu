@@ -287,16 +287,21 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
 //               the fused epilogue (bias / GELU (+aux) / GELU' / residual / TF32 rounding / store or red.add) is a fully
 //               coalesced 128-bit access: 8 lanes cover 128 contiguous bytes of one output row.
 // ====================================================================================================================
-constexpr int kThreads2 = 320;
-constexpr int kEpiWarps2 = 8;
+// epilogue warps: 8 (two per TMEM lane quadrant, each half of the BN columns); the GELU / GELU' epilogues at BN = 192 take 12 (three per
+// quadrant, 64 columns each): they are issue-bound on the transcendental math with only two warps per SM sub-partition
+__host__ __device__ constexpr int epi_warps2(int BN, int MODE) { return (BN == 192 && MODE != 0) ? 12 : 8; }
+__host__ __device__ constexpr int threads2(int BN, int MODE) { return 64 + 32 * epi_warps2(BN, MODE); }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MODE = 0>
 struct Gemm2Cfg {
+  static constexpr int EW = epi_warps2(BN, MODE);
+  static constexpr int WPQ = EW / 4;                  // warps per lane quadrant
+  static constexpr int COLS_PER_WARP = BN / WPQ;      // 64, 96 or 128
   static constexpr int HALF_N = BN / 2;
   static constexpr int A_BYTES = 128 * BK * 4;
   static constexpr int B_BYTES = HALF_N * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STG_BYTES = kEpiWarps2 * 4096;
+  static constexpr int STG_BYTES = EW * 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
@@ -304,9 +309,9 @@ struct Gemm2Cfg {
 enum { kEpiPlain = 0, kEpiGelu = 1, kEpiGeluBwd = 2 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads2(BN, MODE), 1)
 gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
-  using Cfg = Gemm2Cfg<BN, STAGES>;
+  using Cfg = Gemm2Cfg<BN, STAGES, MODE>;
   constexpr int HALF_N = Cfg::HALF_N;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -328,7 +333,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * kEpiWarps2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * Cfg::EW); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -437,7 +442,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     // inlined the loop body was 2.5 K instructions (40 KB) and the eight epilogue warps were instruction-fetch bound.
     const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                          // which half of the BN columns
+    const int part = ew >> 2;                          // which slice of the BN columns (Cfg::COLS_PER_WARP each)
     const uint32_t stg = stg_base + ew * 4096;
     const int flags = p.flags;
     float alpha = p.alpha, beta = p.beta;
@@ -462,8 +467,8 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
       if (row_base < p.M) {
         const int rows_left = p.M - row_base - rl;     // row i*4 + rl is valid iff i*4 < rows_left
 #pragma unroll 1
-        for (int c = 0; c < HALF_N / 32; ++c) {
-          const int col_t = half * HALF_N + c * 32;
+        for (int c = 0; c < Cfg::COLS_PER_WARP / 32; ++c) {
+          const int col_t = part * Cfg::COLS_PER_WARP + c * 32;
           const int col0 = nt * BN + col_t;
           if (col0 >= p.N) break;                      // warp-uniform
           if (flags & (1 << 29)) break;                // bring-up: no epilogue body
@@ -633,14 +638,14 @@ static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
 static int launch2k(const GemmKParams& kp, int pairs, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN, STAGES>;
+  using Cfg = Gemm2Cfg<BN, STAGES, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE><<<dim3(2 * pairs), kThreads2, Cfg::SMEM_BYTES, st>>>(kp);
+  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE><<<dim3(2 * pairs), threads2(BN, MODE), Cfg::SMEM_BYTES, st>>>(kp);
   return check_launch("gemm2_tf32_kernel");
 }
 template <int BN, int STAGES, bool A_MN, bool B_MN>
