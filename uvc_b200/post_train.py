@@ -151,7 +151,19 @@ def main(argv=None):
         if hasattr(m, "weight"):
             m.register_buffer("mask", torch.ones_like(m.weight))
     if args.checkpoint_dir:
-        jt.load_checkpoint(model, args.checkpoint_dir, strict=True)
+        # Strict, as the reference (post_train.py:676-683) -- except for `patch_gating`: Stage 1 with `--enable_patch_gating 1` (the shipped
+        # run_uvc_train.sh) attaches that Parameter to the model after construction (uvc_utils.py:287-288), so it lands in the checkpoint,
+        # while the Stage-2 model is built without it (post_train.py:150-155) and the reference's own strict load would reject the file.
+        # Stage 2 never applies the patch gate, so the key is dropped with a notice instead of failing.
+        ck = torch.load(args.checkpoint_dir, map_location='cpu')
+        for key in ("model", "state_dict_ema", "state_dict"):
+            if isinstance(ck, dict) and key in ck:
+                ck = ck[key]
+                break
+        if "patch_gating" in ck and model.patch_gating is None:
+            print("[post_train] dropping `patch_gating` from the Stage-1 checkpoint: the Stage-2 model has no patch gate (reference post_train.py:150-155)")
+            ck = {k: v for k, v in ck.items() if k != "patch_gating"}
+        model.load_state_dict(ck, strict=True)
     model.to(args.device)
     model.flatten_parameters()
     mixup_fn = Mixup(mixup_alpha=args.mixup, cutmix_alpha=args.cutmix, prob=args.mixup_prob, switch_prob=args.mixup_switch_prob,
