@@ -438,9 +438,10 @@ class DistilledVisionTransformer(VisionTransformer):
             if self.enable_warmup:
                 return torch.full((L, 2), 0.5, device=dev), None
             if self.use_gumbel == 1:
-                # one 2-element draw per block, in block order: the reference's RNG consumption
-                rows = [F.gumbel_softmax(self.block_skip_gating[i], tau=0.5, hard=self.gumbel_hard, eps=1e-10, dim=-1) for i in range(L)]
-                return torch.stack(rows).contiguous(), None
+                # The reference draws one 2-element Gumbel sample per block inside its block loop (:480-483); here all L rows are drawn in ONE
+                # call (same distribution per row, same arithmetic; the Philox offsets differ from L separate calls, and the reference's CPU/CUDA
+                # stream cannot be reproduced bit-for-bit across devices anyway).  12 x 6 tiny launches per forward become 6.
+                return F.gumbel_softmax(self.block_skip_gating, tau=0.5, hard=self.gumbel_hard, eps=1e-10, dim=-1).contiguous(), None
             g1 = self.block_skip_gating[:, 1] ** 2
             d1 = g1 / (g1 + self.eps)
             return torch.stack([1 - d1, d1], dim=1).contiguous(), None
