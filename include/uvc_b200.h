@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 4
+#define UVC_ABI_VERSION 5
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -84,8 +84,10 @@ enum {
   UVC_EPI_ATOMIC = 16,     /* D += v with red.global.add (required when splits > 1) */
   UVC_EPI_ROUND_TF32 = 32, /* round v to nearest TF32 before the store: for outputs that only feed other GEMMs (the
                               tensor core truncates its inputs, rounding here keeps the error unbiased) */
-  UVC_EPI_COLSUM = 64      /* colsum[col] += sum_rows v[row,col] (before TF32 rounding): the bias gradient of the Linear whose
+  UVC_EPI_COLSUM = 64,     /* colsum[col] += sum_rows v[row,col] (before TF32 rounding): the bias gradient of the Linear whose
                               output gradient this GEMM produces, fused so the tensor is not re-read (fp32 atomics) */
+  UVC_GEMM_F16 = 128       /* A and B hold fp16 values (K-major, ld in fp16 elements, ld % 8 == 0): tcgen05.mma kind::f16 with fp32
+                              accumulation -- the 10 mantissa bits of TF32 at half the operand bytes.  Unbatched, M >= 1, K-major only. */
 };
 
 typedef struct {
@@ -104,6 +106,8 @@ typedef struct {
   int32_t flags;           /* UVC_EPI_* */
   int32_t _pad;
   float* colsum;           /* [N], accumulated into when UVC_EPI_COLSUM is set */
+  void* D16; int64_t ldd16; /* optional fp16 copy of the output [M, ldd16] (round to nearest), for consumers that read it as an fp16 GEMM
+                              operand; D may then be NULL.  Needs the unbatched CTA-pair kernel (N % 4 == 0, 16 B-aligned rows). */
 } uvc_gemm_args;
 
 UVC_API int uvc_gemm_tf32(const uvc_gemm_args* args, void* stream);

@@ -286,3 +286,18 @@ def test_attention_fused_backward(ops, B, H, N):
     got = dqkv.view(B * N, 3, C)
     for i, nm in enumerate("qkv"):
         assert rel(got[:, i], g[:, i]) < 2 * TF32_TOL, nm
+
+
+@pytest.mark.parametrize("M,N,K", [(25216, 1152, 384), (1000, 388, 104), (25216, 384, 1536), (300, 64, 64)])
+def test_gemm_fp16_operands(ops, M, N, K):
+    """fp16 operand storage (kind::f16, fp32 accumulate): fp32 and fp16 outputs, fused bias + GELU, against fp32 math on the same fp16 values"""
+    A, B = rn(M, K).half(), (rn(N, K) * 0.1).half()
+    bias = rn(N)
+    D = torch.empty(M, N, device="cuda"); D16 = torch.empty(M, N, device="cuda", dtype=torch.float16)
+    ops.gemm(A, B, D, M, N, K, bias=bias, D16=D16)
+    ref = A.float() @ B.float().t() + bias
+    assert rel(D, ref) < 1e-5 * max(1, K // 64) + 2e-6           # exact products, fp32 accumulation: only summation-order error
+    assert rel(D16.float(), ref) < 1e-3
+    aux = torch.empty(M, N, device="cuda")
+    ops.gemm(A, B, None, M, N, K, bias=bias, aux=aux, flags=ops.EPI_GELU, D16=D16)
+    assert rel(D16.float(), F.gelu(ref)) < 1.5e-3

@@ -297,4 +297,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+
+// fp16 operands (kind::f16, K = 16 per instruction, fp32 accumulate): same 10-bit mantissa as TF32 at half the operand bytes and twice the rate
+__device__ __forceinline__ void umma_f16_2sm_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n}\n"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// four floats -> four fp16 (round to nearest), packed for one 8-byte store
+__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
+  uint2 r;
+  asm("{\n.reg .b16 l, h;\ncvt.rn.f16.f32 l, %1;\ncvt.rn.f16.f32 h, %2;\nmov.b32 %0, {l, h};\n}\n" : "=r"(r.x) : "f"(a), "f"(b));
+  asm("{\n.reg .b16 l, h;\ncvt.rn.f16.f32 l, %1;\ncvt.rn.f16.f32 h, %2;\nmov.b32 %0, {l, h};\n}\n" : "=r"(r.y) : "f"(c), "f"(d));
+  return r;
+}
+
 }  // namespace uvc

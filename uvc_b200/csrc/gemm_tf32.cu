@@ -14,6 +14,7 @@
 //
 // Replaces: models/model_distilled.py:116,122,149,175,179,184,187,522 and their autograd backward.
 #include "kernels.h"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace uvc {
@@ -30,10 +31,12 @@ struct alignas(64) GemmKParams {
   float* aux; long long ldaux, aux_bs1, aux_bs2;
   const float* alpha_dev; const float* beta_dev;
   float* colsum;
+  void* D16; long long ldd16;           // optional fp16 copy of the output (v2 kernel), row stride in fp16 elements
   float alpha, beta;
   int M, N, K, nb1, nb2, splits, flags;
   int a_mn, b_mn;
   int a_use1, a_use2, b_use1, b_use2;   // operand varies with batch index i1 / i2 (else coordinate 0)
+  int f16;                              // v2: A and B are fp16 in memory (K-major), MMA kind::f16
   int a_grp, b_grp;                     // v2: MN-major operand described by a grouped tensor map (one TMA op per stage)
   int m_tiles, n_tiles, units;          // v2 (persistent CTA-pair kernel): 256-row x BN-column tiles, units = tiles * splits
 };
@@ -344,7 +347,8 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
   const uint32_t tmem_base = tmem_slot;
 
   const int tiles = p.m_tiles * p.n_tiles;
-  const int nkb_total = (p.K + BK - 1) / BK;
+  const int bke = p.f16 ? 2 * BK : BK;                 // elements per 128-byte k-block row: 32 fp32 or 64 fp16
+  const int nkb_total = (p.K + bke - 1) / bke;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -364,7 +368,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(full_bar(s), 2 * Cfg::STAGE_BYTES);
             const uint32_t fb = full0_leader + 8u * s;
-            const int k0 = kb * BK;
+            const int k0 = kb * bke;
             const uint32_t sA = smem_base + s * Cfg::STAGE_BYTES;
             const uint32_t sB = sA + Cfg::A_BYTES;
             if constexpr (!A_MN) {
@@ -400,8 +404,11 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     // one add (stage: STAGE_BYTES/16, k-slice: 2 (K-major, 32 B) or 64 (MN-major, 8 rows of 128 B)).
     if (rank == 0) {
       // the whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers); one elected lane issues
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      // instruction descriptor: accumulator F32 (bits 4-5 = 1), operand formats at bits 7-9 / 10-12 (F16 = 0, TF32 = 2), majors, N >> 3, M >> 4
+      const uint32_t fmt = p.f16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const bool f16 = p.f16 != 0;
       constexpr uint32_t a_hi = A_MN ? ((512u >> 4) | (1u << 14) | (1u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
       constexpr uint32_t b_hi = B_MN ? ((512u >> 4) | (1u << 14) | (1u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
       constexpr uint32_t a_k = A_MN ? 64u : 2u, b_k = B_MN ? 64u : 2u;
@@ -424,7 +431,10 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
             const uint32_t b_lo = b_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 8; ++k4) umma_tf32_2sm_lh(d_tmem, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+            for (int k4 = 0; k4 < BK / 8; ++k4) {       // four K-slices of 32 bytes per stage row: K = 8 (tf32) or 16 (fp16) each
+              if (f16) umma_f16_2sm_lh(d_tmem, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+              else umma_tf32_2sm_lh(d_tmem, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+            }
             umma_commit_2sm(empty_bar(s), 3);          // frees this smem stage in BOTH CTAs
           }
           __syncwarp();
@@ -520,9 +530,12 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             }
             if (p.colsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
             if (do_round) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            float* dp = dptr + (long long)i * 4 * p.ldd;
-            if (do_atomic) red_add_v4(dp, v.x, v.y, v.z, v.w);
-            else *reinterpret_cast<float4*>(dp) = v;
+            if (p.D16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.D16) + (roff + i * 4) * p.ldd16 + gcol) = pack_half4(v.x, v.y, v.z, v.w);
+            if (p.D) {
+              float* dp = dptr + (long long)i * 4 * p.ldd;
+              if (do_atomic) red_add_v4(dp, v.x, v.y, v.z, v.w);
+              else *reinterpret_cast<float4*>(dp) = v;
+            }
           }
           if (p.colsum) {                              // lanes with the same cc hold the same 4 columns: fold the 4 row phases, one red per 4 columns
             cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
@@ -604,6 +617,24 @@ static int make_tmap(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UVC_REQUIRE(r == CUDA_SUCCESS, UVC_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (dims %llu x %llu x %llu x %llu, ld %lld)",
               name, (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3], (long long)op.ld);
+  return UVC_OK;
+}
+
+// K-major fp16 operand [rows][K]: boxes of 64 elements (128 B) x box_rows, 128 B swizzle -- byte-for-byte the staging layout of the fp32 path
+static int make_tmap_f16(CUtensorMap* tm, const uvc_operand& op, int rows, int K, int box_rows, const char* name) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  UVC_REQUIRE(enc != nullptr, UVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  UVC_REQUIRE(op.ptr != nullptr && !op.mn_major, UVC_ERR_BAD_ARG, "gemm (fp16 operands): %s must be a non-NULL K-major operand", name);
+  UVC_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0 && op.ld >= K && (op.ld & 7) == 0, UVC_ERR_BAD_SHAPE,
+              "gemm (fp16 operands): %s needs a 16 B-aligned base and ld=%lld >= K, a multiple of 8", name, (long long)op.ld);
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, 1, 1};
+  const cuuint64_t row_bytes = (cuuint64_t)op.ld * 2;
+  cuuint64_t strides[3] = {row_bytes, row_bytes * rows, row_bytes * rows};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<float*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UVC_REQUIRE(r == CUDA_SUCCESS, UVC_ERR_CUDA, "cuTensorMapEncodeTiled(%s, fp16) failed with CUresult %d", name, (int)r);
   return UVC_OK;
 }
 
@@ -694,7 +725,10 @@ static bool v2_legal(const uvc_gemm_args& a) {
   if (a.nb1 != 1 || a.nb2 != 1 || a.K < 1) return false;
   if ((a.flags & UVC_EPI_GELU) && (a.flags & UVC_EPI_GELU_BWD)) return false;
   if ((a.flags & UVC_EPI_GELU_BWD) && (a.flags & UVC_EPI_RESIDUAL)) return false;
-  if ((a.N & 3) || (a.ldd & 3) || !al16(a.D)) return false;
+  if (a.N & 3) return false;
+  if (a.D && ((a.ldd & 3) || !al16(a.D))) return false;
+  if (a.D16 && ((a.ldd16 & 3) || (reinterpret_cast<uintptr_t>(a.D16) & 7))) return false;
+  if (!a.D && !a.D16) return false;
   if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
   if ((a.flags & UVC_EPI_COLSUM) && !al16(a.colsum)) return false;
   if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
@@ -719,7 +753,7 @@ static int v2_pick_bn(int M, int N, int splits, int pairs) {
 int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   UVC_REQUIRE(a.M > 0 && a.N > 0 && a.K >= 0, UVC_ERR_BAD_SHAPE, "gemm: bad M,N,K = %d,%d,%d", a.M, a.N, a.K);
   UVC_REQUIRE(a.nb1 >= 1 && a.nb2 >= 1 && a.splits >= 1, UVC_ERR_BAD_ARG, "gemm: nb1, nb2, splits must be >= 1");
-  UVC_REQUIRE(a.D != nullptr, UVC_ERR_BAD_ARG, "gemm: D is NULL");
+  UVC_REQUIRE(a.D != nullptr || a.D16 != nullptr, UVC_ERR_BAD_ARG, "gemm: D and D16 are both NULL");
   UVC_REQUIRE(a.splits == 1 || (a.flags & UVC_EPI_ATOMIC), UVC_ERR_BAD_ARG, "gemm: splits > 1 requires UVC_EPI_ATOMIC");
   UVC_REQUIRE(!(a.flags & UVC_EPI_ATOMIC) || !(a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)), UVC_ERR_BAD_ARG, "gemm: GELU epilogues cannot be combined with split-K accumulation");
   UVC_REQUIRE(!(a.flags & UVC_EPI_ATOMIC) || !(a.flags & UVC_EPI_ROUND_TF32), UVC_ERR_BAD_ARG, "gemm: UVC_EPI_ROUND_TF32 cannot be combined with atomic accumulation");
@@ -737,8 +771,10 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const int mode = gemm_v2_mode();
   const int pairs = sm_pairs();
   int bn2 = 0;
-  const bool need_v2 = (a.flags & UVC_EPI_COLSUM) && !colsum_simple;   // only the CTA-pair epilogue sums columns after a non-linear epilogue
-  UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: UVC_EPI_COLSUM with GELU / residual epilogues needs unbatched, 16 B-aligned operands");
+  const bool f16 = (a.flags & UVC_GEMM_F16) != 0;
+  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || f16 || a.D16 || !a.D;   // features only the CTA-pair kernel has
+  UVC_REQUIRE(!f16 || (!a.A.mn_major && !a.B.mn_major && a.splits == 1), UVC_ERR_BAD_ARG, "gemm: fp16 operands must be K-major, without split-K");
+  UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: fp16 operands / D16 / UVC_EPI_COLSUM with GELU or residual epilogues need unbatched, 16 B-aligned operands and N % 4 == 0");
   if ((mode > 0 || need_v2) && v2_legal(a) && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
     // split-K (caller allows it by passing splits > 1 with UVC_EPI_ATOMIC): the persistent kernel wants ~2 units per SM pair
     if (splits > 1 && !getenv("UVC_GEMM_V2_KEEP_SPLITS")) {
@@ -753,10 +789,17 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   }
   kp.a_grp = kp.b_grp = 0;
   int rc = UVC_OK;
-  if (bn2 && a.A.mn_major && make_tmap_grouped(&kp.tmA, a.A, a.M, a.K, 4) == 0) kp.a_grp = 1;
-  else if ((rc = make_tmap(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A"))) return rc;
-  if (bn2 && a.B.mn_major && make_tmap_grouped(&kp.tmB, a.B, a.N, a.K, bn2 / 64) == 0) kp.b_grp = 1;
-  else if ((rc = make_tmap(&kp.tmB, a.B, a.N, a.K, a.nb1, a.nb2, bn2 ? bn2 / 2 : BN, "B"))) return rc;
+  kp.f16 = f16 ? 1 : 0;
+  kp.D16 = a.D16; kp.ldd16 = a.ldd16;
+  if (f16) {
+    if ((rc = make_tmap_f16(&kp.tmA, a.A, a.M, a.K, BM, "A"))) return rc;
+    if ((rc = make_tmap_f16(&kp.tmB, a.B, a.N, a.K, bn2 / 2, "B"))) return rc;
+  } else {
+    if (bn2 && a.A.mn_major && make_tmap_grouped(&kp.tmA, a.A, a.M, a.K, 4) == 0) kp.a_grp = 1;
+    else if ((rc = make_tmap(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A"))) return rc;
+    if (bn2 && a.B.mn_major && make_tmap_grouped(&kp.tmB, a.B, a.N, a.K, bn2 / 64) == 0) kp.b_grp = 1;
+    else if ((rc = make_tmap(&kp.tmB, a.B, a.N, a.K, a.nb1, a.nb2, bn2 ? bn2 / 2 : BN, "B"))) return rc;
+  }
   kp.D = a.D; kp.ldd = a.ldd; kp.d_bs1 = a.d_bs1; kp.d_bs2 = a.d_bs2;
   kp.bias = a.bias;
   kp.R = (a.flags & UVC_EPI_RESIDUAL) ? a.R : nullptr; kp.ldr = a.ldr; kp.r_bs1 = a.r_bs1; kp.r_bs2 = a.r_bs2;
@@ -776,7 +819,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
     kp.units = (int)units;
     const int np = units < pairs ? (int)units : pairs;
     const bool prof2 = prof_enabled();
-    if (prof2) prof_begin(st, 2.0 * a.M * a.N * (double)a.K, 2);
+    if (prof2) prof_begin(st, 2.0 * a.M * a.N * (double)a.K, f16 ? 3 : 2);
     if (bn2 == 256) rc = launch2<256, 6>(kp, np, st);
     else if (bn2 == 192) rc = launch2<192, 6>(kp, np, st);
     else rc = launch2<128, 8>(kp, np, st);

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GemmArgs, Operand  # noqa: F401
+from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GEMM_F16, GemmArgs, Operand  # noqa: F401
 
 
 def _stream():
@@ -31,7 +31,7 @@ def operand(t, ld=None, bs1=0, bs2=0, mn_major=False):
 
 
 def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=None, ldr=None, r_bs=(0, 0),
-         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None):
+         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None, D16=None):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T) with A:[M,K], B:[N,K] (see include/uvc_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
@@ -40,8 +40,12 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
     a.splits = int(splits)
     a.A = A if isinstance(A, Operand) else operand(A)
     a.B = B if isinstance(B, Operand) else operand(B)
-    a.D = D.data_ptr()
-    a.ldd = int(ldd if ldd is not None else D.stride(-2))
+    if D is not None:
+        a.D = D.data_ptr()
+        a.ldd = int(ldd if ldd is not None else D.stride(-2))
+    if D16 is not None:
+        assert D16.dtype == torch.float16
+        a.D16 = D16.data_ptr(); a.ldd16 = int(D16.stride(-2))
     a.d_bs1, a.d_bs2 = int(d_bs[0]), int(d_bs[1])
     if bias is not None:
         a.bias = bias.data_ptr(); flags |= EPI_BIAS
@@ -53,6 +57,8 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
     a.alpha, a.beta = float(alpha), float(beta)
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     a.beta_dev = beta_dev.data_ptr() if beta_dev is not None else None
+    if (isinstance(A, torch.Tensor) and A.dtype == torch.float16):
+        flags |= GEMM_F16
     if colsum is not None:
         a.colsum = colsum.data_ptr(); flags |= EPI_COLSUM
     a.flags = int(flags)
