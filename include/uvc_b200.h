@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 5
+#define UVC_ABI_VERSION 6
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -208,7 +208,7 @@ UVC_API int uvc_clip_adamw(float* p, float* g, float* m, float* v, const float* 
  */
 typedef struct {
   float *norm1_w, *norm1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
-} uvc_block_tensors;
+} uvc_block_tensors;             /* qkv_b may be NULL (qkv_bias=False, T2TViT/models/transformer_block.py:50) */
 
 typedef struct {
   float *patch_w, *patch_b;      /* [C, in_chans*patch*patch], [C] */
@@ -237,6 +237,9 @@ typedef struct {
   float* logits;                 /* [B, num_classes] */
   float* pe_out;                 /* optional [B*np, C]: raw patch embeddings (before gates), may be NULL */
   void* workspace; uint64_t workspace_bytes;
+  const float* pe_in;            /* optional [B*np, C]: token embeddings computed by the caller; replaces x -> im2col -> patch GEMM.
+                                    This is how the T2T-ViT backbone (T2TViT/models/t2t_vit.py:168-208: cls + sinusoid pos-embed, 14 Blocks,
+                                    norm, head) runs behind the same entry point, fed by tokens_to_token (:46-105).  x, w.patch_* may be NULL. */
 } uvc_vit_forward_args;
 
 typedef struct {
@@ -254,6 +257,7 @@ typedef struct {
   float* d_patch_scale;          /* [np] accumulated, or NULL */
   float* d_token_mask;           /* [B, np] written, or NULL */
   void* workspace; uint64_t workspace_bytes;   /* the workspace the forward ran with */
+  float* d_pe;                   /* forward ran with pe_in: gradient w.r.t. pe_in, [B*np, C] WRITTEN (g.patch_* untouched); else NULL */
 } uvc_vit_backward_args;
 
 UVC_API uint64_t uvc_vit_workspace_bytes(const uvc_vit_dims* dims, int32_t save_for_backward);

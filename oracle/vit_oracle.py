@@ -60,15 +60,67 @@ def block_macs(B, N, C, H, Fh):
     return [B * 3 * C * N * C, N * B * H * N * d, N * B * H * N * d, B * N * C * C, Fh * B * N * C, C * B * N * Fh]
 
 
-def forward(sd, x, depth, num_heads, eps=1e-6, blend=None, skip=None, patch_scale=None, token_mask=None, enable_jumping=False, patch=16):
+def token_performer(sd, pre, x):
+    """T2TViT/models/token_performer.py:31-69 in eval mode (dropouts are identities): LayerNorm -> kqv Linear ->
+    positive random features exp(w^T x - |x|^2/2)/sqrt(m) for k and q -> linear attention normalised by D -> proj
+    with v as the skip connection -> LayerNorm + 2-layer GELU MLP residual."""
+    emb = sd[pre + "proj.weight"].shape[0]
+    w = sd[pre + "w"]
+    m = w.shape[0]
+    x = F.layer_norm(x, (x.shape[-1],), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"], 1e-5)
+    k, q, v = torch.split(F.linear(x, sd[pre + "kqv.weight"], sd[pre + "kqv.bias"]), emb, dim=-1)
+
+    def prm_exp(t):   # :31-43
+        td = (t * t).sum(dim=-1, keepdim=True).repeat(1, 1, m) / 2
+        return torch.exp(torch.einsum('bti,mi->btm', t, w) - td) / math.sqrt(m)
+
+    kp, qp = prm_exp(k), prm_exp(q)
+    D = torch.einsum('bti,bi->bt', qp, kp.sum(dim=1)).unsqueeze(dim=2)
+    kptv = torch.einsum('bin,bim->bnm', v, kp)
+    y = torch.einsum('bti,bni->btn', qp, kptv) / (D.repeat(1, 1, emb) + 1e-8)
+    y = v + F.linear(y, sd[pre + "proj.weight"], sd[pre + "proj.bias"])
+    h = F.layer_norm(y, (emb,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], 1e-5)
+    h = F.linear(F.gelu(F.linear(h, sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"])), sd[pre + "mlp.2.weight"], sd[pre + "mlp.2.bias"])
+    return y + h
+
+
+def token_performer_macs(B, T, dim, emb, m):
+    """MAC bookkeeping of Token_performer (token_performer.py:54-68), B included as the reference does."""
+    attn = B * (T * dim * 3 * emb + 2 * (T * emb + emb * T * emb) + T * m + T * emb * m + T * m * emb + T * emb * emb)
+    return attn + B * (T * emb * emb + emb * emb * emb)
+
+
+def t2t_tokens(sd, x):
+    """T2T_module.forward, tokens_type='performer' (T2TViT/models/t2t_vit.py:83-105): Unfold 7x7/4 -> performer ->
+    Unfold 3x3/2 -> performer -> Unfold 3x3/2 -> project.  Returns ([B, 196, C] tokens, macs) for 224x224 inputs."""
+    pre = "tokens_to_token."
+    B = x.shape[0]
+    macs = 0
+    t = F.unfold(x, kernel_size=7, stride=4, padding=2).transpose(1, 2)
+    for name in ("attention1.", "attention2."):
+        emb, m = sd[pre + name + "proj.weight"].shape[0], sd[pre + name + "w"].shape[0]
+        macs += token_performer_macs(B, t.shape[1], t.shape[2], emb, m)
+        t = token_performer(sd, pre + name, t)
+        side = int(math.isqrt(t.shape[1]))
+        t = t.transpose(1, 2).reshape(B, t.shape[2], side, side)
+        t = F.unfold(t, kernel_size=3, stride=2, padding=1).transpose(1, 2)
+    return F.linear(t, sd[pre + "project.weight"], sd[pre + "project.bias"]), macs
+
+
+def forward(sd, x, depth, num_heads, eps=1e-6, blend=None, skip=None, patch_scale=None, token_mask=None, enable_jumping=False, patch=16,
+            tokens=None):
     """DistilledVisionTransformer.forward_features + forward, enable_dist == 0 (models/model_distilled.py:429-531).
+
+    With `tokens` ([B, np, C], e.g. from t2t_tokens) the same body is T2T_ViT.forward_features + forward
+    (T2TViT/models/t2t_vit.py:168-208; Block = transformer_block.py:42-112, the same arithmetic as block() with
+    eps 1e-5 and no qkv bias); `blend` rows are then the softmax / Gumbel `distrib` of :183-187.
 
     blend: [L,2] tensor of (d0, d1) = the `distrib` of :480-493 (already sampled), or None
     skip:  list[bool] of hard-skipped blocks (:496-500), or None
     patch_scale: [196] multiplier (:434-444); token_mask: [B,196] multiplier (:446-456)
     returns logits [B, num_classes]
     """
-    x = patch_embed(sd, x, patch)
+    x = patch_embed(sd, x, patch) if tokens is None else tokens
     if patch_scale is not None:
         x = x * patch_scale.view(1, -1, 1)
     if token_mask is not None:

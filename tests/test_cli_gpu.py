@@ -43,3 +43,24 @@ def test_stage1_then_stage2_cli(tmp_path, capsys):
     if best:        # written when the (random-data) accuracy improves on 0
         sd2 = torch.load(best[-1], map_location="cpu")
         assert float(sd2["blocks.0.mlp.fc2.weight"][:, :100].abs().max()) == 0.0 and float(sd2["blocks.0.mlp.fc1.weight"][:100].abs().max()) == 0.0
+
+
+def test_stage1_cli_t2t_vit_14(tmp_path, capsys):
+    """`--model_type t2t_vit_14` (joint_train.py:143-148; not runnable at the reference's HEAD, SURVEY.md §8 row a-T): warm-up + one UVC/ADMM
+    epoch on the 14-block backbone (L=14, H=6, Fh=1152 through the same ADMM kernels), checkpoint with the reference's T2T key set."""
+    from uvc_b200 import joint_train as jt
+    out = str(tmp_path)
+    jt.main(["--dataset", "synthetic", "--model_type", "t2t_vit_14", "--pretrained", "0", "--output_dir", out, "--train_batch_size", "4",
+             "--eval_batch_size", "4", "--synthetic_steps", "3", "--seed", "730", "--print_every", "1", "--distillation-type", "soft",
+             "--distillation-alpha", "0.1", "--local_rank", "-1", "--name", "t2t", "--uvc_train", "--num_epochs", "2", "--warmup_epochs", "1",
+             "--budget", "0.6", "--enable_patch_gating", "2", "--enable_block_gating", "1", "--zlr_schedule_list", "1,5", "--log_interval", "1",
+             "--gating_interval", "2", "--skip_post_training", "1"])
+    txt = capsys.readouterr().out
+    # 2 * (tokens_to_token 256 647 680 MACs + 14 blocks x 320 293 632 MACs) at batch 1, the reference's own accounting
+    assert "** Initial FLOP size: 9481.52M" in txt
+    assert "Warm Up" in txt and "UVC Train" in txt and "nan" not in txt.lower()
+    cks = sorted(glob.glob(os.path.join(out, "t2t", "t2t_vit_14_*.pth.tar")))
+    assert cks, "Stage 1 wrote no checkpoint"
+    sd = torch.load(cks[-1], map_location="cpu")
+    assert "tokens_to_token.attention1.w" in sd and "blocks.13.mlp.fc2.mask" in sd and "blocks.0.attn.qkv.bias" not in sd
+    assert sd["block_skip_gating"].shape == (14, 2)

@@ -1,0 +1,163 @@
+"""T2T-ViT with UVC block gates, backbone on the sm_100a engine (reference UVC/T2TViT/models/t2t_vit.py:46-250).
+
+`T2T_ViT` keeps the reference's constructor arguments, attribute names and state-dict keys (`tokens_to_token.*`, `cls_token`,
+the fixed sinusoid `pos_embed`, `blocks.N.*` without a qkv bias, `norm`, `head`, `block_skip_gating`), so a reference T2T checkpoint
+loads unchanged.  The 14 `Block`s (transformer_block.py:42-112 — the DeiT block arithmetic with LayerNorm eps 1e-5, no qkv bias,
+mlp_ratio 3), the token assembly, the final norm and the head run through `uvc_vit_forward` / `uvc_vit_backward`: the front end's
+[B, 196, C] tokens enter as `pe_in`, and their gradient comes back as `d_pe` and continues through torch autograd into
+`tokens_to_token`.
+
+Deviations from the reference, which cannot execute T2T + UVC at HEAD (SURVEY.md §5 / §8 row a-T):
+  * `forward` accepts the `(x, tau, number)` call joint_train.py:410,1012 makes (the reference's takes `x` only and raises);
+  * the block-gate branch works (`F` is not imported in the reference file; `self.gumbel_hard` is never set there — here it is);
+  * `enable_patch_gating` 1 / 2 apply the DeiT gate logic (models/model_distilled.py:434-456) to the tokens_to_token output.  The flags are
+    set on the model AFTER construction (uvc_optimizer.py:125-129), so the token scorer `gumbel` = Linear(C, 1) always exists: the state dict
+    is the reference's plus `gumbel.weight` / `gumbel.bias` (reference checkpoints load with strict=False, as joint_train.py:148 does).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..._lib import VitDims
+from ...models.model_distilled import DistilledVisionTransformer, _VitFunction, _engine_param_list, gumbel_softmax
+from .token_performer import Token_performer
+
+
+def get_sinusoid_encoding(n_position, d_hid):
+    """Fixed sinusoid table [1, n_position, d_hid] (transformer_block.py:115-125): float64 angles pos / 10000^(2*(j//2)/d),
+    sin on even columns, cos on odd ones, stored as float32."""
+    pos = torch.arange(n_position, dtype=torch.float64).unsqueeze(1)
+    j = torch.arange(d_hid, dtype=torch.float64).unsqueeze(0)
+    ang = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2 * torch.div(j, 2, rounding_mode="floor") / d_hid)
+    even = (torch.arange(d_hid) % 2 == 0).unsqueeze(0)
+    return torch.where(even, torch.sin(ang), torch.cos(ang)).float().unsqueeze(0)
+
+
+class T2T_module(nn.Module):
+    """Tokens-to-token front end, tokens_type='performer' (t2t_vit.py:46-105): three soft splits (Unfold 7x7/4, 3x3/2, 3x3/2)
+    with a Token_performer after the first two, then a Linear to the embedding width.  Torch device ops (see token_performer.py)."""
+
+    def __init__(self, img_size=224, tokens_type='performer', in_chans=3, embed_dim=768, token_dim=64):
+        super().__init__()
+        if tokens_type != 'performer':
+            raise NotImplementedError(f"tokens_type={tokens_type!r}: UVC builds t2t_vit_14, which uses 'performer' (t2t_vit.py:248)")
+        self.soft_split0 = nn.Unfold(kernel_size=(7, 7), stride=(4, 4), padding=(2, 2))
+        self.soft_split1 = nn.Unfold(kernel_size=(3, 3), stride=(2, 2), padding=(1, 1))
+        self.soft_split2 = nn.Unfold(kernel_size=(3, 3), stride=(2, 2), padding=(1, 1))
+        self.attention1 = Token_performer(dim=in_chans * 7 * 7, in_dim=token_dim, kernel_ratio=0.5)
+        self.attention2 = Token_performer(dim=token_dim * 3 * 3, in_dim=token_dim, kernel_ratio=0.5)
+        self.project = nn.Linear(token_dim * 3 * 3, embed_dim)
+        self.num_patches = (img_size // 16) * (img_size // 16)
+
+    def forward(self, x):
+        B = x.shape[0]
+        x = self.soft_split0(x).transpose(1, 2)
+        macs = 0
+        for attn, split in ((self.attention1, self.soft_split1), (self.attention2, self.soft_split2)):
+            x, m = attn(x)
+            macs += m
+            side = math.isqrt(x.shape[1])
+            x = split(x.transpose(1, 2).reshape(B, x.shape[2], side, side)).transpose(1, 2)
+        return self.project(x), macs          # the reference does not count project's MACs either (:105)
+
+
+class T2T_ViT(DistilledVisionTransformer):
+    def __init__(self, img_size=224, tokens_type='performer', in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4., qkv_bias=False, qk_scale=None, drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=nn.LayerNorm,
+                 token_dim=64, enable_block_gating=False, enable_jumping=False, enable_patch_gating=0, gumbel_hard=True, use_gumbel=False):
+        if qk_scale is not None:
+            raise NotImplementedError("qk_scale: only the default head_dim ** -0.5 is on the sm_100a path (t2t_vit_14() leaves it unset)")
+        super().__init__(enable_dist=0, enable_jumping=enable_jumping, enable_block_gating=enable_block_gating, enable_patch_gating=enable_patch_gating,
+                         gumbel_hard=gumbel_hard, use_gumbel=use_gumbel, img_size=img_size, patch_size=16, in_chans=in_chans,
+                         num_classes=num_classes, embed_dim=embed_dim, depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                         drop_rate=drop_rate, attn_drop_rate=attn_drop_rate, drop_path_rate=drop_path_rate, norm_layer=norm_layer)
+        # the DeiT patch conv is replaced by the tokens-to-token module; keep only its geometry (196 tokens on a 14x14 grid)
+        self._img, self._in_chans = int(img_size), int(in_chans)
+        del self.patch_embed
+        self.tokens_to_token = T2T_module(img_size=img_size, tokens_type=tokens_type, in_chans=in_chans, embed_dim=embed_dim, token_dim=token_dim)
+        self.num_patches = self.tokens_to_token.num_patches
+        self.pos_embed = nn.Parameter(get_sinusoid_encoding(self.num_patches + 1, embed_dim), requires_grad=False)
+        self.tokens_to_token.apply(self._init_weights)
+
+    def _init_weights(self, m):      # t2t_vit.py:162-169
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {'cls_token'}
+
+    def get_classifier(self):
+        return self.head
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _dims(self, B):
+        d = VitDims()
+        d.B, d.img, d.patch, d.in_chans = int(B), self._img, 16, self._in_chans     # geometry only: 196 + 1 tokens
+        d.C, d.H, d.Fh, d.L = self.embed_dim, self.blocks[0].attn.num_heads, self.blocks[0].mlp.fc1.out_features, len(self.blocks)
+        d.num_classes = self.num_classes
+        d.ln_eps = float(self.norm.eps)
+        return d
+
+    def _macs_backbone(self, B, executed):
+        C_, N = self.embed_dim, self.num_patches + 1
+        H = self.blocks[0].attn.num_heads
+        d = C_ // H
+        Fh = self.blocks[0].mlp.fc1.out_features
+        per_block = [B * 3 * C_ * N * C_, N * B * H * N * d, N * B * H * N * d, B * N * C_ * C_, Fh * B * N * C_, C_ * B * N * Fh]   # transformer_block.py:30,36,62,67,70,74
+        return [list(per_block) if e else [] for e in executed]
+
+    def _block_gates(self):
+        """t2t_vit.py:181-194: with block gating the blend is a (Gumbel-)softmax over each gate row; otherwise hard skipping."""
+        if self.enable_block_gating:
+            if self.use_gumbel:
+                return F.gumbel_softmax(self.block_skip_gating, tau=0.5, hard=self.gumbel_hard, eps=1e-10, dim=-1).contiguous(), None
+            return F.softmax(self.block_skip_gating, dim=-1).contiguous(), None
+        gate = self.block_skip_gating.detach().tolist()
+        return None, [not (g[1] > g[0]) for g in gate]
+
+    def forward_logits(self, x, tau=-1, ratio=0.9):
+        B = x.shape[0]
+        if not x.is_cuda:
+            from ..._lib import UvcError
+            raise UvcError("uvc_b200 runs on CUDA tensors only (no CPU fallback): move the model and the batch to a B200")
+        pe, macs_embed = self.tokens_to_token(x.float())
+        np_ = self.num_patches
+        patch_scale = token_mask = None
+        if self.enable_patch_gating == 1:
+            pg = torch.sigmoid(self.patch_gating).reshape(np_)
+            if self.patch_hard:
+                pg = (pg.detach() >= 0.5).float()
+                pg[0] = 1
+            patch_scale = pg.contiguous()
+        if tau > 0 and self.enable_patch_gating == 2:
+            scored = pe if patch_scale is None else pe * patch_scale.view(1, -1, 1)
+            scores = F.linear(scored, self.gumbel.weight, self.gumbel.bias).reshape(B, -1)
+            token_mask = gumbel_softmax(F.log_softmax(scores, dim=-1), k=int(ratio * np_), tau=tau, hard=True).clone()
+            token_mask[:, 0] = 1.
+            token_mask = token_mask.contiguous()
+        blend, skip = self._block_gates()
+        params = [p for _, p in _engine_param_list(self)]
+        logits = _VitFunction.apply(self, pe.contiguous(), blend, patch_scale, token_mask, skip, *params)
+        executed = [True] * len(self.blocks) if skip is None else [not s for s in skip]
+        return logits, (macs_embed, self._macs_backbone(B, executed))
+
+    def forward(self, x, tau=-1, number=0.9):
+        x, macs_list = self.forward_logits(x, tau, number)
+        if self.training:
+            return (x, x), macs_list
+        return x, macs_list
+
+
+def t2t_vit_14(pretrained=False, **kwargs):
+    """t2t_vit.py:244-250."""
+    if pretrained:
+        raise NotImplementedError("pretrained=True needs the upstream checkpoint download; load a local checkpoint with load_state_dict")
+    return T2T_ViT(tokens_type='performer', embed_dim=384, depth=14, num_heads=6, mlp_ratio=3., **kwargs)

@@ -53,14 +53,14 @@ class VitDims(C.Structure):
 class VitForwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("x", _F), ("blend", _F), ("skip_host", C.c_void_p),
                 ("patch_scale", _F), ("token_mask", _F), ("save_for_backward", C.c_int32), ("enable_jumping", C.c_int32),
-                ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+                ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("pe_in", _F)]
 
 
 class VitBackwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("g", VitTensors), ("dlogits", _F), ("blend", _F),
                 ("skip_host", C.c_void_p), ("patch_scale", _F), ("token_mask", _F), ("enable_jumping", C.c_int32),
                 ("_pad", C.c_int32), ("d_blend", _F), ("d_patch_scale", _F), ("d_token_mask", _F),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("d_pe", _F)]
 
 
 class AdmmArgs(C.Structure):

@@ -148,7 +148,7 @@ int round_weights(const uvc_vit_tensors& p, const Dims& D, const WeightsR& wr, c
   const float* src[2 + 4 * UVC_MAX_DEPTH]; float* dst[2 + 4 * UVC_MAX_DEPTH]; long long n[2 + 4 * UVC_MAX_DEPTH];
   int k = 0;
   const long long C = D.C, Fh = D.Fh;
-  src[k] = p.patch_w; dst[k] = wr.patch_w; n[k++] = C * D.Kp;
+  if (p.patch_w) { src[k] = p.patch_w; dst[k] = wr.patch_w; n[k++] = C * D.Kp; }   // absent when the caller supplies the token embeddings
   src[k] = p.head_w; dst[k] = wr.head_w; n[k++] = (long long)D.NC * C;
   for (int l = 0; l < D.L; ++l) {
     const uvc_block_tensors& b = p.blocks[l];
@@ -160,8 +160,8 @@ int round_weights(const uvc_vit_tensors& p, const Dims& D, const WeightsR& wr, c
   return round_tf32_segs(src, dst, n, k, st);
 }
 
-int check_tensors(const uvc_vit_tensors& w, int L, const char* what) {
-  UVC_REQUIRE(w.patch_w && w.patch_b && w.cls_token && w.pos_embed && w.norm_w && w.norm_b && w.head_w && w.head_b && w.blocks, UVC_ERR_BAD_ARG,
+int check_tensors(const uvc_vit_tensors& w, int L, const char* what, bool need_patch) {
+  UVC_REQUIRE((!need_patch || (w.patch_w && w.patch_b)) && w.cls_token && w.pos_embed && w.norm_w && w.norm_b && w.head_w && w.head_b && w.blocks, UVC_ERR_BAD_ARG,
               "vit: %s has a NULL tensor", what);
   for (int l = 0; l < L; ++l) {
     const uvc_block_tensors& b = w.blocks[l];
@@ -184,8 +184,8 @@ unsigned long long vit_workspace_bytes(const uvc_vit_dims& dims, int save) {
 int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
-  UVC_TRY(check_tensors(a.w, D.L, "w"));
-  UVC_REQUIRE(a.x && a.logits && a.workspace, UVC_ERR_BAD_ARG, "vit_forward: NULL x / logits / workspace");
+  UVC_TRY(check_tensors(a.w, D.L, "w", a.pe_in == nullptr));
+  UVC_REQUIRE((a.x || a.pe_in) && a.logits && a.workspace, UVC_ERR_BAD_ARG, "vit_forward: NULL x / logits / workspace");
   const bool save = a.save_for_backward != 0;
   Ws w;
   carve(D, save, a.workspace, a.workspace_bytes, &w);
@@ -197,11 +197,18 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
 
   // patch embed: 16x16/16 conv == GEMM over im2col rows
   UVC_TRY(round_weights(a.w, D, w.wr, st));
-  UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
-  float* pe = a.pe_out ? a.pe_out : w.pe;
-  UVC_TRY(linear_fwd(w.cols, D.Kp, w.wr.patch_w, a.w.patch_b, pe, C, D.B * D.np, C, D.Kp, st));
+  const float* pe = a.pe_in;
+  if (!pe) {
+    UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
+    float* pe_w = a.pe_out ? a.pe_out : w.pe;
+    UVC_TRY(linear_fwd(w.cols, D.Kp, w.wr.patch_w, a.w.patch_b, pe_w, C, D.B * D.np, C, D.Kp, st));
+    pe = pe_w;
+  } else if (a.pe_out && a.pe_out != pe) {
+    cudaError_t e = cudaMemcpyAsync(a.pe_out, pe, (size_t)D.B * D.np * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_forward: memcpy pe_out: %s", cudaGetErrorString(e));
+  }
   UVC_TRY(assemble_tokens(pe, a.w.cls_token, a.w.pos_embed, a.patch_scale, a.token_mask, w.tok, D.B, D.np, C, st));
-  if (a.pe_out && save) {
+  if (pe != w.pe && save) {   // the gate gradients of the token assembly read the raw embeddings
     cudaError_t e = cudaMemcpyAsync(w.pe, pe, (size_t)D.B * D.np * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_forward: memcpy pe: %s", cudaGetErrorString(e));
   }
@@ -242,8 +249,8 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
 int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
-  UVC_TRY(check_tensors(a.w, D.L, "w"));
-  UVC_TRY(check_tensors(a.g, D.L, "g"));
+  UVC_TRY(check_tensors(a.w, D.L, "w", a.d_pe == nullptr));
+  UVC_TRY(check_tensors(a.g, D.L, "g", a.d_pe == nullptr));
   UVC_REQUIRE(a.dlogits && a.workspace, UVC_ERR_BAD_ARG, "vit_backward: NULL dlogits / workspace");
   UVC_REQUIRE(!a.blend || a.d_blend, UVC_ERR_BAD_ARG, "vit_backward: blend given without d_blend");
   Ws w;
@@ -322,9 +329,10 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
 
   // token assembly + patch embed
   const int rows = D.B * D.np;
-  UVC_TRY(assemble_tokens_bwd(g, w.pe, a.patch_scale, a.token_mask, w.dpe, a.patch_scale ? a.d_patch_scale : nullptr,
+  float* dpe = a.d_pe ? a.d_pe : w.dpe;
+  UVC_TRY(assemble_tokens_bwd(g, w.pe, a.patch_scale, a.token_mask, dpe, a.patch_scale ? a.d_patch_scale : nullptr,
                               a.token_mask ? a.d_token_mask : nullptr, a.g.pos_embed, a.g.cls_token, D.B, D.np, C, st));
-  UVC_TRY(linear_wgrad(w.dpe, C, w.cols, D.Kp, a.g.patch_w, a.g.patch_b, rows, C, D.Kp, st));
+  if (!a.d_pe) UVC_TRY(linear_wgrad(w.dpe, C, w.cols, D.Kp, a.g.patch_w, a.g.patch_b, rows, C, D.Kp, st));
   return UVC_OK;
 }
 

@@ -86,8 +86,12 @@ def count_parameters(model):
 
 
 def make_model(args, config, gumbel_hard):
+    if "t2t" in args.model_type:
+        # joint_train.py:143-148: t2t_vit_14() with its defaults; the backbone Blocks run on the engine, tokens_to_token feeds `pe_in`
+        from .T2TViT.models import t2t_vit_14
+        return t2t_vit_14(gumbel_hard=gumbel_hard, num_classes=args.num_classes)
     if "deit" not in args.model_type:
-        raise NotImplementedError(f"--model_type {args.model_type}: the sm_100a hot path covers the DeiT family ({', '.join(DEIT_FAMILY)})")
+        raise NotImplementedError(f"--model_type {args.model_type}: the sm_100a hot path covers the DeiT family ({', '.join(DEIT_FAMILY)}) and t2t_vit_14")
     return DistilledVisionTransformer(enable_dist=args.enable_deit, patch_size=config.patch_size, embed_dim=config.embed_dim, depth=config.depth,
                                       num_heads=config.num_heads, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6),
                                       drop_rate=0, gumbel_hard=gumbel_hard, num_classes=args.num_classes)

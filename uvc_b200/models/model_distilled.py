@@ -187,7 +187,8 @@ class _EngineState:
 
 def _engine_param_list(model):
     """(name, Parameter) in the fixed order the autograd Function receives them."""
-    out = [("patch_w", model.patch_embed.proj.weight), ("patch_b", model.patch_embed.proj.bias), ("cls_token", model.cls_token),
+    pe = getattr(model, "patch_embed", None)      # absent for T2T-ViT: the tokens arrive from tokens_to_token (engine `pe_in`)
+    out = [("patch_w", pe.proj.weight if pe is not None else None), ("patch_b", pe.proj.bias if pe is not None else None), ("cls_token", model.cls_token),
            ("pos_embed", model.pos_embed), ("norm_w", model.norm.weight), ("norm_b", model.norm.bias),
            ("head_w", model.head.weight), ("head_b", model.head.bias)]
     for i, blk in enumerate(model.blocks):
@@ -222,6 +223,7 @@ class _VitFunction(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         logits = model._engine_forward(x, blend, patch_scale, token_mask, skip, save=need_grad)
         ctx.model, ctx.skip, ctx.B = model, skip, x.shape[0]
+        ctx.pe_mode = x.dim() == 3      # x is [B, np, C] token embeddings computed by the caller (T2T front end), not images
         ctx.save_for_backward(blend, patch_scale, token_mask)
         ctx.param_requires = [p is not None and p.requires_grad for p in params]
         return logits
@@ -229,9 +231,10 @@ class _VitFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         blend, patch_scale, token_mask = ctx.saved_tensors
-        grads, d_blend, d_ps, d_tm = ctx.model._engine_backward(ctx.B, dlogits.contiguous(), blend, patch_scale, token_mask, ctx.skip)
+        grads, d_blend, d_ps, d_tm, d_pe = ctx.model._engine_backward(ctx.B, dlogits.contiguous(), blend, patch_scale, token_mask, ctx.skip,
+                                                                      ctx.pe_mode)
         out = [g if (g is not None and req) else None for g, req in zip(grads, ctx.param_requires)]
-        return (None, None, d_blend, d_ps, d_tm, None, *out)
+        return (None, d_pe, d_blend, d_ps, d_tm, None, *out)
 
 
 class DistilledVisionTransformer(VisionTransformer):
@@ -323,7 +326,10 @@ class DistilledVisionTransformer(VisionTransformer):
         a = VitForwardArgs()
         a.dims = self._dims(B)
         a.w = es.w
-        a.x = x.data_ptr()
+        if x.dim() == 3:
+            a.pe_in = x.data_ptr()
+        else:
+            a.x = x.data_ptr()
         a.blend = None if blend is None else blend.data_ptr()
         skip_arr = None
         if skip is not None:
@@ -340,20 +346,23 @@ class DistilledVisionTransformer(VisionTransformer):
         _lib.check(lib.uvc_vit_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_forward")
         return logits
 
-    def _engine_backward(self, B, dlogits, blend, patch_scale, token_mask, skip):
+    def _engine_backward(self, B, dlogits, blend, patch_scale, token_mask, skip, pe_mode=False):
         lib = _lib.load()
         es = self._tables()
         dev = dlogits.device
         plist = _engine_param_list(self)
-        first = plist[0][1]
-        accumulate = first.grad is not None and first.grad.data_ptr() == es.grad_views[0].data_ptr()
+        first = next(p for _, p in plist if p is not None)
+        accumulate = first.grad is not None and first.grad.data_ptr() == next(v for v in es.grad_views if v is not None).data_ptr()
         if not accumulate:
             es.grad_arena.zero_()
         a = VitBackwardArgs()
         a.dims = self._dims(B)
         a.w, a.g = es.w, es.g
         a.dlogits = dlogits.data_ptr()
-        d_blend = d_ps = d_tm = None
+        d_blend = d_ps = d_tm = d_pe = None
+        if pe_mode:
+            d_pe = torch.empty(B, a.dims.img // a.dims.patch * (a.dims.img // a.dims.patch), a.dims.C, device=dev, dtype=torch.float32)
+            a.d_pe = d_pe.data_ptr()
         if blend is not None:
             a.blend = blend.data_ptr()
             d_blend = torch.zeros_like(blend)
@@ -378,7 +387,7 @@ class DistilledVisionTransformer(VisionTransformer):
         # adopting (not copying) is what makes every .grad a window of the flat arena
         grads = [None] * len(plist) if accumulate else \
             [None if p is None else es.grad_arena[o:o + p.numel()].view(p.shape) for (_, p), o in zip(plist, es.grad_offs)]
-        return grads, d_blend, d_ps, d_tm
+        return grads, d_blend, d_ps, d_tm, d_pe
 
     def flatten_parameters(self):
         """Move every engine parameter into ONE flat fp32 arena laid out exactly like the gradient arena (same order, same
@@ -405,7 +414,7 @@ class DistilledVisionTransformer(VisionTransformer):
     @property
     def flat_param(self):
         fp = getattr(self, "_flat_param", None)
-        if fp is None or _engine_param_list(self)[0][1].data_ptr() != fp.data_ptr():
+        if fp is None or _engine_param_list(self)[0][1] is None or _engine_param_list(self)[0][1].data_ptr() != fp.data_ptr():
             return None              # never flattened, or re-materialised by .to() / load with assign
         return fp
 

@@ -157,8 +157,8 @@ class UVC_CP_MiniMax(nn.Module):
         self.z = Parameter(torch.tensor(float(z_init), device=dev))
         self.resource_fn = resource_fn
         self.enable_patch_gating = args.enable_patch_gating
-        gs = model.patch_embed.grid_size
-        self.patch_gating = Parameter(3 * torch.ones(1, gs[0] * gs[1], 1, device=dev)) if self.enable_patch_gating == 1 else None
+        n_patches = model.patch_embed.num_patches if hasattr(model, "patch_embed") else model.num_patches     # T2T-ViT: tokens_to_token, no patch conv
+        self.patch_gating = Parameter(3 * torch.ones(1, n_patches, 1, device=dev)) if self.enable_patch_gating == 1 else None
         self.update_patch()
         self.enable_part_gating = args.enable_part_gating
         self.enable_block_gating = args.enable_block_gating
