@@ -154,10 +154,25 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         const int b = hd / p.H, h = hd % p.H;
         mbar_wait(s_full(t), it & 1u);
         tc_fence_after();
-        // pass 1: row maximum over the valid key columns (columns >= N hold Q . 0 = 0 from the zero-filled key rows)
+        // pass 1: row maximum over the valid key columns (columns >= N hold Q . 0 = 0 from the zero-filled key rows).  Chunks that lie
+        // entirely below N (all six for N >= 192) run without the per-column validity test: this loop and the next are issue-bound.
+        const int full_chunks = min(6, N >> 5);
         float mx = -INFINITY;
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
+        for (int c = 0; c < full_chunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c * 32, r);
+          tmem_ld_wait();
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int j = 4; j < 32; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[j])); m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[j + 2])); m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        }
+#pragma unroll 1
+        for (int c = full_chunks; c < 6; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(s_addr + c * 32, r);
           tmem_ld_wait();
@@ -171,11 +186,31 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) if (192 + j < N) mx = fmaxf(mx, __uint_as_float(r[j]));
         }
-        // pass 2: e = exp((s - max) * scale), un-normalised, rounded to TF32, written back in place as the A operand of the PV MMA
+        // pass 2: e = exp((s - max) * scale), un-normalised, written back in place as the A operand of the PV MMA.  The tensor core
+        // truncates the low 13 mantissa bits of a TF32 operand, so adding half a TF32 ulp to the bit pattern (e is in [0, 1]: no overflow)
+        // makes that truncation a round-to-nearest: one integer add per element instead of the three-instruction cvt.rna sequence.
+        // The row sum uses the unrounded e: it differs from the sum of the rounded values by a zero-mean 2^-12 / sqrt(N) relative error.
         const float mxs = mx * p.scale_log2e;
-        float sum = 0.f;
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
+        for (int c = 0; c < full_chunks; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(s_addr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2e, -mxs));
+            const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), p.scale_log2e, -mxs));
+            const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), p.scale_log2e, -mxs));
+            sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
+            r[j] = __float_as_uint(e0) + 0x1000u; r[j + 1] = __float_as_uint(e1) + 0x1000u;
+            r[j + 2] = __float_as_uint(e2) + 0x1000u; r[j + 3] = __float_as_uint(e3) + 0x1000u;
+          }
+          tmem_st_32x32(s_addr + c * 32, r);
+        }
+#pragma unroll 1
+        for (int c = full_chunks; c < 6; ++c) {
           uint32_t r[32];
           tmem_ld_32x32(s_addr + c * 32, r);
           tmem_ld_wait();
@@ -183,9 +218,8 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
           for (int j = 0; j < 32; ++j) {
             float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
             if (c * 32 + j >= N) e = 0.f;
-            e = round_tf32(e);
-            sum += e;
-            r[j] = __float_as_uint(e);
+            sum0 += e;
+            r[j] = (c * 32 + j >= N) ? 0u : __float_as_uint(e) + 0x1000u;
           }
           tmem_st_32x32(s_addr + c * 32, r);
         }
@@ -197,12 +231,12 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
           for (int j = 0; j < 16; ++j) {
             float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
             if (192 + j >= N) e = 0.f;
-            e = round_tf32(e);
-            sum += e;
-            r[j] = __float_as_uint(e);
+            sum1 += e;
+            r[j] = (192 + j >= N) ? 0u : __float_as_uint(e) + 0x1000u;
           }
           tmem_st_32x16(s_addr + 192, r);
         }
+        const float sum = (sum0 + sum1) + (sum2 + sum3);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -210,7 +244,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         const float inv = 1.0f / sum;
         if (p.lse && row < N) p.lse[((long long)b * p.H + h) * N + row] = mxs + log2f(sum);   // log2-domain log-sum-exp: P = exp2(S scale log2e - lse)
         // optional pass 3: normalised probabilities to HBM for the backward (TMEM loads are warp-collective: only the stores are predicated)
-        if (p.save_P) {
+        if (p.save_P) {      // (the TMEM copy carries the rounding increment in its low 13 bits: mask them, as the tensor core does)
           float* prow = p.P + (((long long)b * p.H + h) * N + row) * p.ldp;
           const bool rok = row < N;
 #pragma unroll 1
@@ -221,8 +255,8 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (rok && c * 32 + j < N)    // ldp % 4 == 0 and ldp >= N: a float4 starting below N stays inside the row's padding
-                *reinterpret_cast<float4*>(prow + c * 32 + j) = make_float4(round_tf32(__uint_as_float(r[j]) * inv), round_tf32(__uint_as_float(r[j + 1]) * inv),
-                                                                             round_tf32(__uint_as_float(r[j + 2]) * inv), round_tf32(__uint_as_float(r[j + 3]) * inv));
+                *reinterpret_cast<float4*>(prow + c * 32 + j) = make_float4(round_tf32(__uint_as_float(r[j] & 0xffffe000u) * inv), round_tf32(__uint_as_float(r[j + 1] & 0xffffe000u) * inv),
+                                                                             round_tf32(__uint_as_float(r[j + 2] & 0xffffe000u) * inv), round_tf32(__uint_as_float(r[j + 3] & 0xffffe000u) * inv));
             }
           }
           uint32_t r[16];
@@ -231,8 +265,8 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (rok && 192 + j < N)
-              *reinterpret_cast<float4*>(prow + 192 + j) = make_float4(round_tf32(__uint_as_float(r[j]) * inv), round_tf32(__uint_as_float(r[j + 1]) * inv),
-                                                                       round_tf32(__uint_as_float(r[j + 2]) * inv), round_tf32(__uint_as_float(r[j + 3]) * inv));
+              *reinterpret_cast<float4*>(prow + 192 + j) = make_float4(round_tf32(__uint_as_float(r[j] & 0xffffe000u) * inv), round_tf32(__uint_as_float(r[j + 1] & 0xffffe000u) * inv),
+                                                                       round_tf32(__uint_as_float(r[j + 2] & 0xffffe000u) * inv), round_tf32(__uint_as_float(r[j + 3] & 0xffffe000u) * inv));
           }
         }
         // epilogue: O_t / rowsum -> ctx
@@ -491,7 +525,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
       if (PHASE == 2) {                              // per-query statistics of this head, indexed by score column
         named_bar_sync(1, 256);
         s_lse[tid2] = nx_lse;
-        s_D[tid2] = nx_D;
+        s_D[tid2] = nx_D * p.scale;
         named_bar_sync(1, 256);
         fetch(hd + gridDim.x, 0);
       }
@@ -499,7 +533,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         const int row = t * 128 + q * 32 + lane;     // phase 1: query row ; phase 2: key row
         float lse_r = INFINITY, D_r = 0.f;
         if (PHASE == 1) {
-          lse_r = nx_lse; D_r = nx_D;
+          lse_r = nx_lse; D_r = nx_D * p.scale;     // dS = scale P (dP - D) = P (scale dP - scale D)
           if (t + 1 < ntiles) fetch(hd, t + 1); else fetch(hd + gridDim.x, 0);
         }
         mbar_wait(sc_full, ia & 1u);
@@ -514,16 +548,19 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
+              // P and dS feed TMEM-sourced MMAs, which truncate to TF32: + half a TF32 ulp on the bit pattern turns that into round-to-nearest
+              // (one integer add instead of cvt.rna's three instructions; this loop is issue-bound).  No validity test on the score columns:
+              // columns >= N multiply zero-filled rows of K (phase 1), and rows / columns >= N carry lse = +inf, i.e. P = 0.
               float pr, ds;
               if (PHASE == 1) {
-                pr = (col0 + j < N) ? ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r)) : 0.f;
-                ds = pr * (__uint_as_float(ry[j]) - D_r) * p.scale;
+                pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r));
+                ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -D_r);
               } else {
                 pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
-                ds = pr * (__uint_as_float(ry[j]) - s_D[col0 + j]) * p.scale;
-                rx[j] = __float_as_uint(round_tf32(pr));
+                ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -s_D[col0 + j]);
+                rx[j] = __float_as_uint(pr) + 0x1000u;
               }
-              ry[j] = __float_as_uint(round_tf32(ds));
+              ry[j] = __float_as_uint(ds) + 0x1000u;
             }
             if (PHASE == 2) tmem_st_32x32(lane_addr + kX + col0, rx);
             tmem_st_32x32(lane_addr + kY + col0, ry);
@@ -534,16 +571,19 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
+              // P and dS feed TMEM-sourced MMAs, which truncate to TF32: + half a TF32 ulp on the bit pattern turns that into round-to-nearest
+              // (one integer add instead of cvt.rna's three instructions; this loop is issue-bound).  No validity test on the score columns:
+              // columns >= N multiply zero-filled rows of K (phase 1), and rows / columns >= N carry lse = +inf, i.e. P = 0.
               float pr, ds;
               if (PHASE == 1) {
-                pr = (col0 + j < N) ? ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r)) : 0.f;
-                ds = pr * (__uint_as_float(ry[j]) - D_r) * p.scale;
+                pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -lse_r));
+                ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -D_r);
               } else {
                 pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
-                ds = pr * (__uint_as_float(ry[j]) - s_D[col0 + j]) * p.scale;
-                rx[j] = __float_as_uint(round_tf32(pr));
+                ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -s_D[col0 + j]);
+                rx[j] = __float_as_uint(pr) + 0x1000u;
               }
-              ry[j] = __float_as_uint(round_tf32(ds));
+              ry[j] = __float_as_uint(ds) + 0x1000u;
             }
             if (PHASE == 2) tmem_st_32x8(lane_addr + kX + col0, rx);
             tmem_st_32x8(lane_addr + kY + col0, ry);
