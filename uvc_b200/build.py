@@ -54,7 +54,7 @@ def build_library(force=False, verbose=False, jobs=None):
     for s in srcs:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-DUVC_BUILD_DLL", "-I", INCLUDE, "-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("UVC_NVCC_EXTRA", "").split() + ["-DUVC_BUILD_DLL", "-I", INCLUDE, "-c", s, "-o", o]   # bring-up only
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -21,26 +21,38 @@ int attn_ldp(int N) { return (N + 3) / 4 * 4; }
 //   P_t = exp(S_t - max) eight softmax warps (four per query tile; warp w owns TMEM lanes 32 (w % 4) ..): each thread owns one query row,
 //                        reads it with tcgen05.ld, writes the un-normalised TF32-rounded probabilities back IN PLACE with tcgen05.st
 //   O_t = P_t V          tcgen05.mma with the A operand read straight from TMEM (the P just written), B = V (MN-major) from shared memory
-//   ctx = O_t / rowsum   epilogue by the same warps: tcgen05.ld, scale, TF32 rounding, 128-bit stores into [B*N, H*d]
+//   ctx = O_t / rowsum   epilogue by the same warps: tcgen05.ld, scale, TF32 rounding, then 32 x 32 blocks through swizzled shared memory and a
+//                        TMA store per warp (a thread owns a row: direct 128-bit stores hit 32 different lines per instruction and kept the
+//                        LSU busy for ~1.6 us per head)
 //
 // With save_P the normalised probabilities are also written to HBM for the (still GEMM-composed) backward; the teacher / inference
 // forward skips that and moves only qkv in and ctx out (the algorithmic minimum: 4 * B*N * 4C bytes).
-// TMEM columns: S0 [0,208)  S1 [208,416)  O [416,480) (one accumulator, tiles take turns).  Shared memory: Q 64 KB, K 52 KB, V 52 KB.
+// TMEM columns: S0 [0,208)  S1 [208,416)  O [416,480) (one accumulator, tiles take turns).  Shared memory: Q 64 KB, K 52 KB, V 52 KB, 32 KB ctx staging.
+// All three operands are single-buffered (fp32 staging leaves no room for more), so the TMA warp also prefetches the NEXT head's boxes into L2
+// when it loads the current one: the load that follows a freed buffer then pays L2 latency, not DRAM latency.
 // ====================================================================================================================
 constexpr int kANK = 208;                     // key rows staged / score columns (N <= 208)
 constexpr int kAThreads = 320;                // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax / epilogue
 constexpr int kAQBytes = 2 * 2 * 128 * 128;   // 2 query tiles x 2 k-blocks x 128 rows x 128 B
 constexpr int kAKBytes = 2 * kANK * 128;      // 2 k-blocks x 208 rows x 128 B
 constexpr int kAVBytes = 2 * kANK * 128;      // 2 groups of 32 head-dims x 208 tokens x 128 B
-constexpr int kASmem = kAQBytes + kAKBytes + kAVBytes + 1024;
+constexpr int kAStage = 8 * 4096;             // per softmax warp: 32 rows x 32 columns of ctx staged for a TMA store
+constexpr int kASmem = kAQBytes + kAKBytes + kAVBytes + kAStage + 1024;
 
 struct alignas(64) AttnFwdParams {
-  CUtensorMap tmQ, tmK, tmV;
+  CUtensorMap tmQ, tmK, tmV, tmO;
   float* P; float* ctx; float* lse;
   long long ldp;
   int B, H, N, C, ntiles, save_P;
   float scale_log2e;
 };
+
+#ifdef UVC_ATTN_TRACE     // bring-up only (UVC_NVCC_EXTRA=-DUVC_ATTN_TRACE): per-warp event clocks of CTA 0 for heads 0..3
+__device__ long long g_attn_trace[10 * 4 * 8];
+#define ATR(ev) do { if (blockIdx.x == 0 && lane == 0 && it < 4) g_attn_trace[(warp * 4 + it) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define ATR(ev) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -59,7 +71,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
   auto p_ready = [&](int t) { return bar0 + 80 + 8u * t; };
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV);
+    tma_prefetch_desc(&p.tmQ); tma_prefetch_desc(&p.tmK); tma_prefetch_desc(&p.tmV); tma_prefetch_desc(&p.tmO);
     mbar_init(qk_full, 1); mbar_init(v_full, 1); mbar_init(qk_empty, 1); mbar_init(v_empty, 1);
     for (int t = 0; t < 2; ++t) { mbar_init(o_full(t), 1); mbar_init(o_empty(t), 4); mbar_init(s_full(t), 1); mbar_init(p_ready(t), 4); }
     fence_barrier_init();
@@ -78,18 +90,29 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
     uint32_t it = 0;
     for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
       const int b = hd / p.H, h = hd % p.H;
+      const int hn = hd + (int)gridDim.x, bn = hn / p.H, hh = hn % p.H;
       mbar_wait(qk_empty, (it & 1u) ^ 1u);
+      ATR(0);
       if (elect_one()) {
         mbar_expect_tx(qk_full, (uint32_t)(ntiles * 2 * 128 * 128 + kAKBytes));
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < 2; ++kb) tma_load_4d(sQ + t * 32768 + kb * 16384, &p.tmQ, qk_full, kb * 32, t * 128, h, b);
         for (int kb = 0; kb < 2; ++kb) tma_load_4d(sK + kb * (kANK * 128), &p.tmK, qk_full, kb * 32, 0, h, b);
+        if (hn < nheads) {                           // next head of this CTA: pull its Q / K boxes into L2 a full period ahead
+          for (int c = 0; c < 2; ++c) {
+            for (int t = 0; t < ntiles; ++t) tma_prefetch_l2_4d(&p.tmQ, c * 32, t * 128, hh, bn);
+            tma_prefetch_l2_4d(&p.tmK, c * 32, 0, hh, bn);
+          }
+        }
       }
       __syncwarp();
       mbar_wait(v_empty, (it & 1u) ^ 1u);
+      ATR(1);
       if (elect_one()) {
         mbar_expect_tx(v_full, kAVBytes);
         for (int c = 0; c < 2; ++c) tma_load_4d(sV + c * (kANK * 128), &p.tmV, v_full, c * 32, 0, h, b);
+        if (hn < nheads)
+          for (int c = 0; c < 2; ++c) tma_prefetch_l2_4d(&p.tmV, c * 32, 0, hh, bn);
       }
       __syncwarp();
     }
@@ -99,34 +122,43 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
     constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // O = P V (B MN-major)
     const uint32_t k_hi = umma_desc_hi(1024, 2), v_hi = umma_desc_hi(512, 1);
     const uint32_t q_lo0 = umma_desc_lo(sQ, 16), k_lo0 = umma_desc_lo(sK, 16), v_lo0 = umma_desc_lo(sV, kANK * 128);
-    uint32_t it = 0;
-    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
-      const uint32_t ph = it & 1u;
-      mbar_wait(qk_full, ph);
-      tc_fence_after();
-      for (int t = 0; t < ntiles; ++t) {
-        // S_t / P_t of the previous head must be fully consumed: group t arrives on o_empty[t] after its last TMEM read of that head
-        mbar_wait(o_empty(t), ph ^ 1u);
-        tc_fence_after();
-        if (elect_one()) {
+    // Issue order (the tensor pipe executes in order):  S(0,0) S(0,1) | O(h,0) S(h+1,0) O(h,1) S(h+1,1) | ...
+    // The score MMA of the NEXT head for tile t goes out right behind the output MMA that consumes P_t, so group t finds its next scores ready
+    // when it returns from the epilogue instead of waiting behind the other tile's output MMA (the two groups end up half a period apart).
+    // Hazards: S_t/P_t is rewritten only after the output MMA that reads it (same pipe, in order) and after group t's last TMEM read of it
+    // (p_ready[t]); the single O accumulator is handed from tile to tile through o_empty[].
+    auto issue_scores = [&](int t) {
+      if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t kb = kk >> 2, k4 = kk & 3;
-            umma_tf32_lh(tmem_base + t * kANK, q_lo0 + ((t * 32768 + kb * 16384) >> 4) + k4 * 2, k_hi, k_lo0 + ((kb * (kANK * 128)) >> 4) + k4 * 2, k_hi, idesc1, kk ? 1u : 0u);
-          }
-          umma_commit(s_full(t));
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t kb = kk >> 2, k4 = kk & 3;
+          umma_tf32_lh(tmem_base + t * kANK, q_lo0 + ((t * 32768 + kb * 16384) >> 4) + k4 * 2, k_hi, k_lo0 + ((kb * (kANK * 128)) >> 4) + k4 * 2, k_hi, idesc1, kk ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit(s_full(t));
       }
+      __syncwarp();
+    };
+    uint32_t it = 0;
+    if ((int)blockIdx.x < nheads) {
+      mbar_wait(qk_full, 0);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) issue_scores(t);
       if (elect_one()) umma_commit(qk_empty);       // Q and K staging may be refilled for the next head
       __syncwarp();
+    }
+    for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const bool more = hd + (int)gridDim.x < nheads;
       mbar_wait(v_full, ph);
+      ATR(0);
       tc_fence_after();
       for (int t = 0; t < ntiles; ++t) {
-        mbar_wait(p_ready(t), ph);                  // P_t is in TMEM
-        // the single O accumulator: its previous user (the other tile of this head, or the last tile of the previous head, whose
-        // o_empty phase was already observed above) must have read it out
+        mbar_wait(p_ready(t), ph);                  // P_t is in TMEM and group t no longer reads S_t
+        ATR(1 + 3 * t);
+        // the single O accumulator: its previous user must have read it out (previous tile of this head, or the last tile of the previous head)
         if (t > 0) mbar_wait(o_empty(t - 1), ph);
+        else if (it > 0) mbar_wait(o_empty(ntiles - 1), ph ^ 1u);
+        ATR(2 + 3 * t);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll 2
@@ -135,6 +167,15 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
           umma_commit(o_full(t));
         }
         __syncwarp();
+        if (more) {
+          if (t == 0) { mbar_wait(qk_full, ph ^ 1u); tc_fence_after(); }
+          ATR(3 + 3 * t);
+          issue_scores(t);
+          if (t == ntiles - 1) {
+            if (elect_one()) umma_commit(qk_empty);
+            __syncwarp();
+          }
+        }
       }
       if (elect_one()) umma_commit(v_empty);
       __syncwarp();
@@ -148,11 +189,13 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
     const uint32_t s_addr = lane_addr + t * kANK;
     const int row = t * 128 + q * 32 + lane;         // query row inside the head
     const int N = p.N;
+    const uint32_t stage = sV + kAVBytes + (uint32_t)ew * 4096u + (uint32_t)lane * 128u;   // this thread's 128-byte row of the warp's block
     if (t < ntiles) {
       uint32_t it = 0;
       for (int hd = blockIdx.x; hd < nheads; hd += gridDim.x, ++it) {
         const int b = hd / p.H, h = hd % p.H;
         mbar_wait(s_full(t), it & 1u);
+        ATR(0);
         tc_fence_after();
         // pass 1: row maximum over the valid key columns (columns >= N hold Q . 0 = 0 from the zero-filled key rows).  Chunks that lie
         // entirely below N (all six for N >= 192) run without the per-column validity test: this loop and the next are issue-bound.
@@ -190,6 +233,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         // truncates the low 13 mantissa bits of a TF32 operand, so adding half a TF32 ulp to the bit pattern (e is in [0, 1]: no overflow)
         // makes that truncation a round-to-nearest: one integer add per element instead of the three-instruction cvt.rna sequence.
         // The row sum uses the unrounded e: it differs from the sum of the rounded values by a zero-mean 2^-12 / sqrt(N) relative error.
+        ATR(1);
         const float mxs = mx * p.scale_log2e;
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll 1
@@ -240,7 +284,9 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready(t));
+        // p_ready also releases S_t for the next head's score MMA: with save_P the third pass below still reads it, so the arrive moves behind it
+        if (!p.save_P && lane == 0) mbar_arrive(p_ready(t));
+        ATR(2);
         const float inv = 1.0f / sum;
         if (p.lse && row < N) p.lse[((long long)b * p.H + h) * N + row] = mxs + log2f(sum);   // log2-domain log-sum-exp: P = exp2(S scale log2e - lse)
         // optional pass 3: normalised probabilities to HBM for the backward (TMEM loads are warp-collective: only the stores are predicated)
@@ -269,8 +315,14 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
                                                                        round_tf32(__uint_as_float(r[j + 2] & 0xffffe000u) * inv), round_tf32(__uint_as_float(r[j + 3] & 0xffffe000u) * inv));
           }
         }
+        if (p.save_P) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_ready(t));
+        }
         // epilogue: O_t / rowsum -> ctx
         mbar_wait(o_full(t), it & 1u);
+        ATR(3);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(lane_addr + 416, o0);
@@ -279,18 +331,32 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty(t));
-        if (row < N) {
-          float* crow = p.ctx + ((long long)b * N + row) * p.C + h * 64;
+        ATR(4);
+        if (t * 128 + q * 32 < N) {                  // warp-uniform; rows >= N inside the block are clipped by the tensor map
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(crow + j) = make_float4(round_tf32(__uint_as_float(o0[j]) * inv), round_tf32(__uint_as_float(o0[j + 1]) * inv),
-                                                               round_tf32(__uint_as_float(o0[j + 2]) * inv), round_tf32(__uint_as_float(o0[j + 3]) * inv));
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t* o = half ? o1 : o0;
+            if (lane == 0) tma_store_wait_read0();   // the previous store out of this block has read it
+            __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(crow + 32 + j) = make_float4(round_tf32(__uint_as_float(o1[j]) * inv), round_tf32(__uint_as_float(o1[j + 1]) * inv),
-                                                                    round_tf32(__uint_as_float(o1[j + 2]) * inv), round_tf32(__uint_as_float(o1[j + 3]) * inv));
+            for (int g = 0; g < 8; ++g) {            // 16-byte granule g of row `lane` sits at granule g ^ (row & 7): the 128-byte TMA swizzle
+              const uint32_t v0 = (__float_as_uint(__uint_as_float(o[4 * g]) * inv) + 0x1000u) & 0xffffe000u;
+              const uint32_t v1 = (__float_as_uint(__uint_as_float(o[4 * g + 1]) * inv) + 0x1000u) & 0xffffe000u;
+              const uint32_t v2 = (__float_as_uint(__uint_as_float(o[4 * g + 2]) * inv) + 0x1000u) & 0xffffe000u;
+              const uint32_t v3 = (__float_as_uint(__uint_as_float(o[4 * g + 3]) * inv) + 0x1000u) & 0xffffe000u;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)((g ^ (lane & 7)) << 4)), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmO, stage, half * 32, t * 128 + q * 32, h, b);   // lane 0's row address is the block base
+              tma_store_commit();
+            }
+          }
         }
+        ATR(5);
       }
+      if (lane == 0) tma_store_wait_all();
     }
   }
   tc_fence_before();
@@ -677,6 +743,9 @@ static int attention_fwd_fused(const float* qkv, float* P, float* ctx, float* ls
   if ((rc = encode_tmap_4d(&kp.tmQ, qkv, dims, strides, boxq, false, "attn Q"))) return rc;
   if ((rc = encode_tmap_4d(&kp.tmK, qkv + C, dims, strides, boxk, false, "attn K"))) return rc;
   if ((rc = encode_tmap_4d(&kp.tmV, qkv + 2 * C, dims, strides, boxk, true, "attn V"))) return rc;
+  const unsigned long long ostrides[3] = {(unsigned long long)C * 4, 64 * 4, (unsigned long long)N * C * 4};
+  const unsigned int boxo[4] = {32, 32, 1, 1};
+  if ((rc = encode_tmap_4d(&kp.tmO, ctx, dims, ostrides, boxo, false, "attn ctx"))) return rc;
   kp.P = P; kp.ctx = ctx; kp.lse = lse; kp.ldp = attn_ldp(N);
   kp.B = B; kp.H = H; kp.N = N; kp.C = (int)C; kp.ntiles = (N + 127) / 128; kp.save_P = P != nullptr;
   kp.scale_log2e = scale * 1.4426950408889634f;
@@ -692,6 +761,12 @@ static int attention_fwd_fused(const float* qkv, float* P, float* ctx, float* ls
   attn_fwd_kernel<<<grid, kAThreads, kASmem, st>>>(kp);
   return check_launch("attn_fwd_kernel");
 }
+
+#ifdef UVC_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int uvc_attn_trace_read(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(long long) * 10 * 4 * 8);
+}
+#endif
 
 bool attn_fused_ok(int N, int d) { return attn_fused_mode() != 0 && d == 64 && N <= kANK; }
 
