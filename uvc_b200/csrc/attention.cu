@@ -423,6 +423,12 @@ struct alignas(64) AttnBwdParams {
   float scale, scale_log2e;
 };
 
+#ifdef UVC_ATTN_TRACE
+#define BTR(ev) do { if (blockIdx.x == 0 && lane == 0 && ia >= 2 && ia < 6) g_attn_trace[(warp * 4 + (ia - 2)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define BTR(ev) do { } while (0)
+#endif
+
 template <int PHASE>
 __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -460,6 +466,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
       const int b = hd / p.H, h = hd % p.H;
       for (int t = 0; t < ntiles; ++t, ++ia) {
         mbar_wait(a_empty, (ia & 1u) ^ 1u);
+        BTR(0);
         if (elect_one()) {
           mbar_expect_tx(a_full, 2 * kBABytes);
           for (int kb = 0; kb < 2; ++kb) {
@@ -471,6 +478,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         if (PHASE == 2 || t == 0) {
           mbar_wait(bs_empty, (ibs & 1u) ^ 1u);                    // score MMAs that read the previous contents are done
           if (PHASE == 2) mbar_wait(bo_empty, (ibo & 1u) ^ 1u);    // same memory was last used by the output MMAs of the previous tile
+          BTR(1);
           if (elect_one()) {
             mbar_expect_tx(bs_full, 2 * kBBBytes);
             for (int kb = 0; kb < 2; ++kb) {
@@ -493,6 +501,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
           }
         } else {
           mbar_wait(bs_empty, (ibs - 1u) & 1u);                    // this tile's score MMAs have consumed the K-major copies: restage MN-major
+          BTR(2);
           if (elect_one()) {
             mbar_expect_tx(bo_full, 2 * kBBBytes);
             for (int c = 0; c < 2; ++c) {
@@ -517,8 +526,11 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
       for (int t = 0; t < ntiles; ++t, ++ia) {
         const uint32_t ph = ia & 1u;
         mbar_wait(a_full, ph);
+        BTR(0);
         if (PHASE == 2 || t == 0) { mbar_wait(bs_full, ibs & 1u); ++ibs; }
+        BTR(1);
         mbar_wait(acc_empty, ph ^ 1u);               // previous tile's epilogue has drained X / Y / accumulators
+        BTR(2);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -537,7 +549,9 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         }
         __syncwarp();
         mbar_wait(el_done, ph);                      // dS (and P^T) are in TMEM
+        BTR(3);
         if (PHASE == 2 || t == 0) { mbar_wait(bo_full, ibo & 1u); ++ibo; }
+        BTR(4);
         tc_fence_after();
         if (PHASE == 1) {
           if (elect_one()) {
@@ -555,6 +569,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
           }
           __syncwarp();
           mbar_wait(mid, ph);                        // P^T consumed: its first 64 columns become the dK accumulator
+          BTR(5);
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll 2
@@ -603,6 +618,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
           if (t + 1 < ntiles) fetch(hd, t + 1); else fetch(hd + gridDim.x, 0);
         }
         mbar_wait(sc_full, ia & 1u);
+        BTR(0);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -659,8 +675,10 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(el_done);
+        BTR(1);
         // epilogue: this warp's 32 rows x its 32-column half of the 64-wide outputs
         mbar_wait(acc_full, ia & 1u);
+        BTR(2);
         tc_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32(lane_addr + kAcc + hh * 32, o0);
@@ -669,6 +687,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty);
+        BTR(3);
         if (p.db0) {
           // qkv bias gradient = column sums of dq / dk / dv: a 32 x 32 transpose-reduce over the warp (31 shuffles) leaves column `lane` in each lane
           float v[32];
@@ -683,19 +702,20 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
             atomicAdd(p.db1 + h * 64 + hh * 32 + lane, v[0]);
           }
         }
+        BTR(4);
         if (row < N) {
-          const long long off = ((long long)b * N + row) * p.ldo + h * 64 + hh * 32;
+          const long long off = ((long long)b * N + row) * p.ldo + h * 64 + hh * 32;      // 128-byte aligned: ldo and the head offsets are multiples of 32 floats
+          auto rnd = [](uint32_t u) { return __uint_as_float((u + 0x1000u) & 0xffffe000u); };    // round to TF32 (finite values)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(p.out0 + off + j) = make_float4(round_tf32(__uint_as_float(o0[j])), round_tf32(__uint_as_float(o0[j + 1])),
-                                                                       round_tf32(__uint_as_float(o0[j + 2])), round_tf32(__uint_as_float(o0[j + 3])));
+          for (int j = 0; j < 32; j += 8)
+            st_global_v8(p.out0 + off + j, rnd(o0[j]), rnd(o0[j + 1]), rnd(o0[j + 2]), rnd(o0[j + 3]), rnd(o0[j + 4]), rnd(o0[j + 5]), rnd(o0[j + 6]), rnd(o0[j + 7]));
           if (PHASE == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.out1 + off + j) = make_float4(round_tf32(__uint_as_float(o1[j])), round_tf32(__uint_as_float(o1[j + 1])),
-                                                                         round_tf32(__uint_as_float(o1[j + 2])), round_tf32(__uint_as_float(o1[j + 3])));
+            for (int j = 0; j < 32; j += 8)
+              st_global_v8(p.out1 + off + j, rnd(o1[j]), rnd(o1[j + 1]), rnd(o1[j + 2]), rnd(o1[j + 3]), rnd(o1[j + 4]), rnd(o1[j + 5]), rnd(o1[j + 6]), rnd(o1[j + 7]));
           }
         }
+        BTR(5);
       }
     }
   }
@@ -835,6 +855,9 @@ int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, co
   kp.db0 = dqkv_bias; kp.db1 = nullptr;
   attn_bwd_kernel<1><<<grid, kAThreads, smem1, st>>>(kp);
   if ((rc = check_launch("attn_bwd_kernel<1>"))) return rc;
+#ifdef UVC_ATTN_TRACE
+  if (getenv("UVC_TRACE_PHASE1")) return UVC_OK;
+#endif
   // phase 2: dK, dV
   if ((rc = attn_tmap(&kp.tmA0, k, ld3, B, H, N, 128, false, "attn bwd K tile"))) return rc;
   if ((rc = attn_tmap(&kp.tmA1, v, ld3, B, H, N, 128, false, "attn bwd V tile"))) return rc;
