@@ -775,12 +775,16 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || f16 || a.D16 || !a.D;   // features only the CTA-pair kernel has
   UVC_REQUIRE(!f16 || (!a.A.mn_major && !a.B.mn_major && a.splits == 1), UVC_ERR_BAD_ARG, "gemm: fp16 operands must be K-major, without split-K");
   UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: fp16 operands / D16 / UVC_EPI_COLSUM with GELU or residual epilogues need unbatched, 16 B-aligned operands and N % 4 == 0");
-  if ((mode > 0 || need_v2) && v2_legal(a) && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
+  // Split-K weight gradients (few output tiles, K = all tokens) stay on the 128 x 128 kernel: its tiles fit the C-multiple weight shapes without
+  // padding and tiles x splits fills one wave of 2 CTAs per SM; measured on the four DeiT-Small shapes it is 0-30 % faster than the CTA-pair
+  // kernel there (qkv_w 47 vs 69 us, fc1_w 55 vs 61 us; tests/bringup/wgrad_perf.py).
+  const bool splitk_wgrad = a.splits > 1 && (a.flags & UVC_EPI_ATOMIC) && mode != 2 && !need_v2;
+  if ((mode > 0 || need_v2) && v2_legal(a) && !splitk_wgrad && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
     // split-K (caller allows it by passing splits > 1 with UVC_EPI_ATOMIC): the persistent kernel wants ~2 units per SM pair
     if (splits > 1 && !getenv("UVC_GEMM_V2_KEEP_SPLITS")) {
       const int bn0 = gemm_v2_force_bn() ? gemm_v2_force_bn() : 128;
       const int tiles2 = ((a.M + 255) / 256) * ((a.N + bn0 - 1) / bn0);
-      int sp = (2 * pairs + tiles2 / 2) / tiles2;
+      int sp = (2 * pairs) / tiles2;               // floor: one unit over two full waves costs a third wave
       if (sp > nkb / 8) sp = nkb / 8;              // keep >= 8 k-blocks per slice
       splits = sp < 1 ? 1 : sp;
     }
