@@ -86,8 +86,11 @@ enum {
                               tensor core truncates its inputs, rounding here keeps the error unbiased) */
   UVC_EPI_COLSUM = 64,     /* colsum[col] += sum_rows v[row,col] (before TF32 rounding): the bias gradient of the Linear whose
                               output gradient this GEMM produces, fused so the tensor is not re-read (fp32 atomics) */
-  UVC_GEMM_F16 = 128       /* A and B hold fp16 values (K-major, ld in fp16 elements, ld % 8 == 0): tcgen05.mma kind::f16 with fp32
+  UVC_GEMM_F16 = 128,      /* A and B hold fp16 values (K-major, ld in fp16 elements, ld % 8 == 0): tcgen05.mma kind::f16 with fp32
                               accumulation -- the 10 mantissa bits of TF32 at half the operand bytes.  Unbatched, M >= 1, K-major only. */
+  UVC_EPI_AUX_F16 = 256    /* `aux` points to fp16 values (ldaux in fp16 elements, ldaux % 4 == 0, 8 B-aligned): the gelu' factors are in
+                              [-0.13, 1.13] and the product they enter is rounded to TF32 anyway, so 11 significant bits lose nothing and
+                              the GELU pair of epilogues moves half the aux bytes.  CTA-pair kernel only (unbatched operands). */
 };
 
 typedef struct {

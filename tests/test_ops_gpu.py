@@ -62,6 +62,21 @@ def test_gemm_epilogues(ops):
     assert rel(D, (A @ B.t()) * u) < TF32_TOL
 
 
+def test_gemm_gelu_pair_with_fp16_aux(ops):
+    """UVC_EPI_AUX_F16: the forward epilogue stores gelu'(pre-activation) as fp16, the backward epilogue multiplies by it (ragged M, N)."""
+    M, N, K = 1000, 772, 192
+    A, B, bias = rn(M, K), rn(N, K) * 0.1, rn(N)
+    pre = A @ B.t() + bias
+    D = torch.empty(M, N, device="cuda"); aux = torch.zeros(M, N, device="cuda", dtype=torch.float16)
+    ops.gemm(A, B, D, M, N, K, bias=bias, aux=aux, flags=ops.EPI_GELU)
+    pp = pre.clone().requires_grad_(True); F.gelu(pp).sum().backward()
+    assert rel(D, F.gelu(pre)) < TF32_TOL and rel(aux.float(), pp.grad) < TF32_TOL
+    G, W = rn(M, K, seed=5), rn(N, K, seed=6) * 0.1                      # dh = (G W^T) .* gelu'
+    dh = torch.empty(M, N, device="cuda")
+    ops.gemm(G, W, dh, M, N, K, aux=aux, flags=ops.EPI_GELU_BWD)
+    assert rel(dh, (G @ W.t()) * pp.grad) < TF32_TOL
+
+
 def test_gemm_rejects_bad_arguments(ops):
     from uvc_b200._lib import UvcError
     A, B = rn(16, 6), rn(16, 6)          # ld = 6 is not a multiple of 4

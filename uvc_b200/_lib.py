@@ -93,7 +93,7 @@ EXPORTS = [
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
-EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM, GEMM_F16 = 1, 2, 4, 8, 16, 32, 64, 128
+EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM, GEMM_F16, EPI_AUX_F16 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 _lib = None
 

@@ -37,6 +37,7 @@ struct alignas(64) GemmKParams {
   int a_mn, b_mn;
   int a_use1, a_use2, b_use1, b_use2;   // operand varies with batch index i1 / i2 (else coordinate 0)
   int f16;                              // v2: A and B are fp16 in memory (K-major), MMA kind::f16
+  int aux16;                            // v2: aux holds fp16 values (UVC_EPI_AUX_F16)
   int a_grp, b_grp;                     // v2: MN-major operand described by a grouped tensor map (one TMA op per stage)
   int m_tiles, n_tiles, units;          // v2 (persistent CTA-pair kernel): 256-row x BN-column tiles, units = tiles * splits
 };
@@ -500,11 +501,22 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
           float* dptr = p.D + roff * p.ldd + gcol;
           const float* rptr = p.R + roff * p.ldr + gcol;
           float* xptr = p.aux + roff * p.ldaux + gcol;
+          __half* xptr16 = reinterpret_cast<__half*>(p.aux) + roff * p.ldaux + gcol;     // UVC_EPI_AUX_F16 view of the same argument
           float4 rr[8];
-          if (MODE == kEpiGeluBwd) {                   // gelu'(pre-activation) factors, loaded up front (8 independent 128-bit loads in flight)
+          if (MODE == kEpiGeluBwd) {                   // gelu'(pre-activation) factors, loaded up front (8 independent loads in flight)
+            if (p.aux16) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(xptr + (long long)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int i = 0; i < 8; ++i) {
+                uint2 u = make_uint2(0u, 0u);
+                if (colok && i * 4 < rows_left) u = *reinterpret_cast<const uint2*>(xptr16 + (long long)i * 4 * p.ldaux);
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                rr[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(xptr + (long long)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           } else if (do_res) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -521,7 +533,10 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             if (MODE == kEpiGelu) {
               float4 dg;                                 // aux receives gelu'(pre-activation): the same exponential gives both, and the backward
               gelu_both(v.x, v.x, dg.x); gelu_both(v.y, v.y, dg.y); gelu_both(v.z, v.z, dg.z); gelu_both(v.w, v.w, dg.w);   // epilogue becomes a multiply
-              if (p.aux) *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = dg;
+              if (p.aux) {
+                if (p.aux16) *reinterpret_cast<uint2*>(xptr16 + (long long)i * 4 * p.ldaux) = pack_half4(dg.x, dg.y, dg.z, dg.w);
+                else *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = dg;
+              }
             }
             if (MODE == kEpiGeluBwd) {
               v.x *= rr[i].x; v.y *= rr[i].y; v.z *= rr[i].z; v.w *= rr[i].w;
@@ -732,7 +747,10 @@ static bool v2_legal(const uvc_gemm_args& a) {
   if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
   if ((a.flags & UVC_EPI_COLSUM) && !al16(a.colsum)) return false;
   if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
-  if ((a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux && ((a.ldaux & 3) || !al16(a.aux))) return false;
+  if ((a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux) {
+    if (a.flags & UVC_EPI_AUX_F16) { if ((a.ldaux & 3) || (reinterpret_cast<uintptr_t>(a.aux) & 7)) return false; }
+    else if ((a.ldaux & 3) || !al16(a.aux)) return false;
+  }
   return true;
 }
 
@@ -772,7 +790,8 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const int pairs = sm_pairs();
   int bn2 = 0;
   const bool f16 = (a.flags & UVC_GEMM_F16) != 0;
-  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || f16 || a.D16 || !a.D;   // features only the CTA-pair kernel has
+  const bool aux16 = (a.flags & UVC_EPI_AUX_F16) && (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux;
+  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || f16 || a.D16 || !a.D || aux16;   // features only the CTA-pair kernel has
   UVC_REQUIRE(!f16 || (!a.A.mn_major && !a.B.mn_major && a.splits == 1), UVC_ERR_BAD_ARG, "gemm: fp16 operands must be K-major, without split-K");
   UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: fp16 operands / D16 / UVC_EPI_COLSUM with GELU or residual epilogues need unbatched, 16 B-aligned operands and N % 4 == 0");
   // Split-K weight gradients (few output tiles, K = all tokens) stay on the 128 x 128 kernel: its tiles fit the C-multiple weight shapes without
@@ -794,6 +813,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.a_grp = kp.b_grp = 0;
   int rc = UVC_OK;
   kp.f16 = f16 ? 1 : 0;
+  kp.aux16 = aux16 ? 1 : 0;
   kp.D16 = a.D16; kp.ldd16 = a.ldd16;
   if (f16) {
     if ((rc = make_tmap_f16(&kp.tmA, a.A, a.M, a.K, BM, "A"))) return rc;

@@ -90,7 +90,7 @@ void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
       LayerWs& L = w->layer[l];
       L.mean1 = b.f(M); L.rstd1 = b.f(M); L.mean2 = b.f(M); L.rstd2 = b.f(M);
       L.ln1 = b.f(M * C); L.qkv = b.f(M * 3 * C); L.P = psz ? b.f(psz) : nullptr; L.lse = lsz ? b.f(lsz) : nullptr; L.ctx = b.f(M * C);
-      L.x1 = b.f(M * C); L.ln2 = b.f(M * C); L.hpre = b.f(M * Fh); L.h = b.f(M * Fh);
+      L.x1 = b.f(M * C); L.ln2 = b.f(M * C); L.hpre = b.f((M * Fh + 1) / 2); L.h = b.f(M * Fh);   // hpre: gelu' as fp16
       L.t = b.f(M * C); L.xout = b.f(M * C);
     }
     w->g_a = b.f(M * C); w->g_b = b.f(M * C); w->g_c = b.f(M * C);
@@ -228,7 +228,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
       UVC_TRY(attention_fwd(L.qkv, L.P, L.ctx, D.B, D.H, D.ntok, D.d, scale, st, save && L.P != nullptr, save ? L.lse : nullptr));   // fused path: probabilities never reach HBM
       UVC_TRY(linear_fwd(L.ctx, C, w.wr.proj_w[l], p.proj_b, L.x1, C, M, C, C, st, 0, nullptr, x, C));     // x1 = x + proj(ctx)
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, L.ln2, C, L.mean2, L.rstd2, M, C, st, 1));
-      UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32, L.hpre));   // h = gelu(fc1); hpre holds gelu'(fc1) for the backward
+      UVC_TRY(linear_fwd(L.ln2, C, w.wr.fc1_w[l], p.fc1_b, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU | UVC_EPI_ROUND_TF32 | UVC_EPI_AUX_F16, L.hpre));   // h = gelu(fc1); hpre holds gelu'(fc1) (fp16) for the backward
       if (a.blend) {
         UVC_TRY(linear_fwd(L.h, Fh, w.wr.fc2_w[l], p.fc2_b, L.t, C, M, C, Fh, st, 0, nullptr, L.x1, C));    // t = x1 + fc2(h)
         UVC_TRY(blend_fwd(L.t, x, a.blend + 2 * l, L.xout, (long long)M * C, st));                            // x <- d1 t + d0 x
@@ -303,7 +303,7 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
       // Bias gradients are column sums of tensors other kernels stream anyway, so they ride along instead of costing a pass each:
       //   fc1_b <- epilogue of the fc2 dgrad GEMM (sums dhpre), fc2_b / proj_b <- the LN2 backward (sums its residual input dt / its output dx1).
       UVC_TRY(linear_wgrad(dt, C, L.h, Fh, gp.fc2_w, nullptr, M, C, Fh, st, d1));
-      UVC_TRY(linear_dgrad(dt, C, w.wr.fc2_w[l], w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD | UVC_EPI_ROUND_TF32, L.hpre, Fh, gp.fc1_b, d1));     // dhpre
+      UVC_TRY(linear_dgrad(dt, C, w.wr.fc2_w[l], w.dh, Fh, M, C, Fh, st, UVC_EPI_GELU_BWD | UVC_EPI_ROUND_TF32 | UVC_EPI_AUX_F16, L.hpre, Fh, gp.fc1_b, d1));     // dhpre
       UVC_TRY(linear_wgrad(w.dh, Fh, L.ln2, C, gp.fc1_w, nullptr, M, Fh, C, st));
       UVC_TRY(linear_dgrad(w.dh, Fh, w.wr.fc1_w[l], spare2, C, M, Fh, C, st));                                          // dln2
       // dx1 = dt + LN2'(dln2)

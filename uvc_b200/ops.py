@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GEMM_F16, GemmArgs, Operand  # noqa: F401
+from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GEMM_F16, EPI_AUX_F16, GemmArgs, Operand  # noqa: F401
 
 
 def _stream():
@@ -54,6 +54,8 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
         flags |= EPI_RESIDUAL
     if aux is not None:
         a.aux = aux.data_ptr(); a.ldaux = int(ldaux if ldaux is not None else aux.stride(-2)); a.aux_bs1, a.aux_bs2 = int(aux_bs[0]), int(aux_bs[1])
+        if aux.dtype == torch.float16:
+            flags |= EPI_AUX_F16
     a.alpha, a.beta = float(alpha), float(beta)
     a.alpha_dev = alpha_dev.data_ptr() if alpha_dev is not None else None
     a.beta_dev = beta_dev.data_ptr() if beta_dev is not None else None
