@@ -166,7 +166,7 @@ def test_token_gate_mode2_indices_exact():
     xc = x.cuda()
     k, tau = int(0.9 * 196), 0.7
     torch.manual_seed(123)
-    mask = token_gate_mask(m, xc, None, tau, k)
+    _, mask = token_gate_mask(m, xc, None, tau, k)
     assert mask.shape == (B, 196)
     hard = (mask.detach() > 0.5)
     assert (hard[:, 0]).all() and ((hard.sum(1) == k) | (hard.sum(1) == k + 1)).all()
@@ -185,6 +185,20 @@ def test_token_gate_mode2_indices_exact():
     with torch.no_grad():
         lo = vo.forward(sd, x, depth, H, token_mask=hard.float().cpu())
     assert rel(logits, lo) < LOGIT_TOL
+    # backward: the patch conv ran once (engine `pe_in`); its gradients must sit in the flat arena slots AND equal the oracle's under the same mask
+    r = torch.randn(B, 1000, generator=torch.Generator().manual_seed(2)) * 0.1
+    m.zero_grad(set_to_none=True)
+    (logits * r.cuda()).sum().backward()
+    sdo = {kk: v.clone().requires_grad_(v.is_floating_point()) for kk, v in sd.items()}
+    (vo.forward(sdo, x, depth, H, token_mask=hard.float().cpu()) * r).sum().backward()
+    gw = m.patch_embed.proj.weight.grad
+    es = m._tables()
+    assert gw.data_ptr() == es.grad_views[0].data_ptr() and m.patch_embed.proj.bias.grad.data_ptr() == es.grad_views[1].data_ptr()
+    # (the straight-through mask also sends a gradient through the scorer into the patch conv; it is ~1e-3 of the main path here)
+    go = sdo["patch_embed.proj.weight"].grad.flatten()
+    cos = float(torch.dot(gw.flatten().cpu(), go) / (gw.norm().cpu() * go.norm()))
+    print(f"token-gate patch_w grad: cosine vs fixed-mask oracle {cos:.4f}")
+    assert cos > 0.95 and rel(m.blocks[0].attn.qkv.weight.grad, sdo["blocks.0.attn.qkv.weight"].grad) < 5e-3
 
 
 def test_full_size_properties():

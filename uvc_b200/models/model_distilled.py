@@ -234,6 +234,8 @@ class _VitFunction(torch.autograd.Function):
         grads, d_blend, d_ps, d_tm, d_pe = ctx.model._engine_backward(ctx.B, dlogits.contiguous(), blend, patch_scale, token_mask, ctx.skip,
                                                                       ctx.pe_mode)
         out = [g if (g is not None and req) else None for g, req in zip(grads, ctx.param_requires)]
+        if ctx.pe_mode:
+            out[0] = out[1] = None      # patch conv ran outside the engine: whoever produced the embeddings owns those two gradients
         return (None, d_pe, d_blend, d_ps, d_tm, None, *out)
 
 
@@ -469,7 +471,8 @@ class DistilledVisionTransformer(VisionTransformer):
             patch_scale = pg.contiguous()
         if tau > 0:
             from .token_gate import token_gate_mask
-            token_mask = token_gate_mask(self, x, patch_scale, tau, int(ratio * np_))
+            pe, token_mask = token_gate_mask(self, x, patch_scale, tau, int(ratio * np_))
+            x = pe.contiguous()                      # [B, np, C]: the engine takes the embeddings as `pe_in`
         blend, skip = self._block_gates()
         params = [p for _, p in _engine_param_list(self)]
         logits = _VitFunction.apply(self, x, blend, patch_scale, token_mask, skip, *params)
