@@ -230,7 +230,7 @@ def run_gpu(a):
         out = step(bx, by)                      # consumes bx in place (mixup)
         done[i % 2] = torch.cuda.Event(); done[i % 2].record(cur)
         loss = float(out["loss"].item())        # device -> host read of the step's result (the ADMM state came back inside step())
-        d2h[0] = 4 + 4 * (1 + out["s"].size + out["r"].size + (out["gating"].size if out["gating"] is not None else 0))
+        d2h[0] = 4 + 4 * (1 + out["s"].size + out["r"].size + (out["gating"].size if out["gating"] is not None else 0))   # resolves the step's deferred ADMM read-back
         return loss
     for i in range(min(3, a.warmup)):
         e2e_step(i)

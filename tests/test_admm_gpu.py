@@ -108,6 +108,11 @@ def test_admm_warmup_returns_resource_only():
     # real / expected FLOPs prints (joint_train.py:509)
     hard = float(mm.run_resource_fn(gumbel_hard=True))
     assert abs(hard - 1.0) < 1e-6
+    # lazy=True (the hot loop's variant): same values, fetched through one deferred pinned-memory copy instead of a synchronous one
+    import numpy as np
+    cur2, s2, r2, g2, _ = uvc_optimizer(FakeOpt(1e-3), mm, s_opt, r_opt, g_opt, dual_opt, args, {}, [], flops_list, 0.5, 1, 50, [], lazy=True)
+    assert abs(float(cur2) - cur) < 1e-6 and np.array_equal(np.asarray(s2), mm.s.detach().cpu().numpy()) and np.asarray(r2).shape == r_np.shape
+    assert g2.tolist() == mm.block_skip_gating.detach().cpu().numpy().tolist() and s2.size == s_np.size
 
 
 @pytest.mark.parametrize("model_type,depth", [("deit_small_patch16_224", 12), ("deit_base_patch16_224", 2)])

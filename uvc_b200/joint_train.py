@@ -189,6 +189,8 @@ class Stage1Step:
         self.global_step = 0
         self.gating_grad_list = []
         self.uvc_fn = uvc_optimizer if args.enable_pruning else uvc_optimizer_gating
+        # the ADMM step's host return values are only printed every log_interval steps: fetch them lazily (no device sync per step)
+        self.uvc_kw = {"lazy": True} if args.enable_pruning else {}
         self.last = {}
         self._timing = [] if os.environ.get("UVC_STEP_TIMING") else None
 
@@ -238,7 +240,7 @@ class Stage1Step:
             minimax_model.update_gating()
             cur_resource, s_data, r_data, gating_data, self.gating_grad_list = self.uvc_fn(
                 self.optimizer, minimax_model, s_optimizer, r_optimizer, gating_optimizer, dual_optimizer, args, {"global_step": self.global_step},
-                [], flops_list, args.z_grad_clip, self.global_step, args.gating_interval, self.gating_grad_list)
+                [], flops_list, args.z_grad_clip, self.global_step, args.gating_interval, self.gating_grad_list, **self.uvc_kw)
             out.update(cur_resource=cur_resource, s=s_data, r=r_data, gating=gating_data)
         self._mark("admm")
         self.optimizer.zero_grad()
@@ -314,7 +316,7 @@ def train(args, model, uvc_args=None, mixup_fn=None, criterion=None):
                 if args.local_rank in [-1, 0]:
                     dt = time.time() - t0
                     print(f"Stage [{epoch} / {args.num_epochs} Epochs] [{step_fn.global_step} Steps] [LR: {scheduler.get_last_lr()[0]:.6f} | Loss: {losses.val:.3f} | "
-                          f"Flops: {out.get('cur_resource', 1.0)*100:.2f}%] {(step + 1) * x.shape[0] * get_world_size() / dt:.1f} img/s")
+                          f"Flops: {float(out.get('cur_resource', 1.0))*100:.2f}%] {(step + 1) * x.shape[0] * get_world_size() / dt:.1f} img/s")
             if args.uvc_train and step_fn.global_step % args.log_interval == 0 and args.local_rank in [-1, 0]:
                 s_list.append(out["s"].tolist()); r_list.append(out["r"].tolist())
                 if out.get("gating") is not None:

@@ -32,9 +32,63 @@ def _sgd_lr(opt, what):
     return float(opt.param_groups[0]['lr'])
 
 
+class _Snapshot:
+    """One asynchronous device->host copy into pinned memory (torch's caching host allocator recycles the buffer) + the event that fences it."""
+
+    def __init__(self, flat):
+        self.host = torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True)
+        self.host.copy_(flat, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self._np = None
+
+    def numpy(self):
+        if self._np is None:
+            self.event.synchronize()
+            self._np = self.host.numpy()
+        return self._np
+
+
+class Deferred:
+    """A host value that is fetched from its snapshot when first needed."""
+
+    def __init__(self, snap, pick):
+        self._snap, self._pick, self._val = snap, pick, None
+
+    def get(self):
+        if self._val is None:
+            self._val = self._pick(self._snap.numpy())
+        return self._val
+
+    def __float__(self):
+        return float(self.get())
+
+    def __array__(self, dtype=None, copy=None):
+        import numpy as np
+        a = np.asarray(self.get())
+        return a.astype(dtype) if dtype is not None else a
+
+    def tolist(self):
+        v = self.get()
+        return v.tolist() if hasattr(v, "tolist") else v
+
+    @property
+    def size(self):
+        return self.get().size
+
+    @property
+    def shape(self):
+        return self.get().shape
+
+
 def uvc_optimizer(optimizer, minimax_model, s_optimizer, r_optimizer, gating_optimizer, dual_optimizer, args, infos, save_budgets,
-                  flops_list, z_grad_clip, global_step, gating_interval, gating_grad_list):
-    """-> (cur_resource: float, s: np[L,2], r: np[L,H], gating: np[L,2] | None, gating_grad_list)   (reference :37-144)"""
+                  flops_list, z_grad_clip, global_step, gating_interval, gating_grad_list, lazy=False):
+    """-> (cur_resource: float, s: np[L,2], r: np[L,H], gating: np[L,2] | None, gating_grad_list)   (reference :37-144)
+
+    lazy=True (not in the reference; used by the hot loop): the four host values come back as `Deferred` handles over ONE asynchronous
+    copy into pinned memory, resolved on first use (float(), np.asarray(), .tolist()).  The reference's signature forces a device->host
+    synchronisation in every step although the values are only printed every `log_interval` steps; without it the host runs a step ahead
+    and the GPU never waits for launches."""
     mm = minimax_model
     d = mm._dev
     warmup = bool(mm.model.enable_warmup)
@@ -83,6 +137,11 @@ def uvc_optimizer(optimizer, minimax_model, s_optimizer, r_optimizer, gating_opt
     parts = [cur, mm.s.detach().reshape(-1), mm.r.detach().reshape(-1)]
     if gate is not None:
         parts.append(gate.detach().reshape(-1))
+    if lazy:
+        snap = _Snapshot(torch.cat(parts))
+        return (Deferred(snap, lambda h: float(h[0])), Deferred(snap, lambda h: h[1:1 + 2 * L].reshape(L, 2).copy()),
+                Deferred(snap, lambda h: h[1 + 2 * L:1 + 2 * L + L * H].reshape(L, H).copy()),
+                Deferred(snap, lambda h: h[1 + 2 * L + L * H:].reshape(L, 2).copy()) if gate is not None else None, buf)
     host = torch.cat(parts).cpu().numpy()
     cur_resource = float(host[0])
     s_np = host[1:1 + 2 * L].reshape(L, 2).copy()
