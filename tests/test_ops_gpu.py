@@ -77,6 +77,20 @@ def test_gemm_gelu_pair_with_fp16_aux(ops):
     assert rel(dh, (G @ W.t()) * pp.grad) < TF32_TOL
 
 
+def test_fused_attention_propagates_nan(ops):
+    """A NaN in q must come out as NaN in ctx and lse (the integer TF32 rounding of the TMEM operands must not launder it into a zero)."""
+    B, H, N, d = 2, 3, 197, 64
+    qkv = ops.round_tf32(rn(B * N, 3 * H * d))
+    qkv[5, 64 + 3] = float("nan")                    # image 0, token 5, head 1 of q
+    ctx, lse = ops.attention_fwd_lse(qkv, B, H, N, d)
+    assert torch.isnan(ctx[5, 64:128]).all() and torch.isnan(lse.view(B, H, N)[0, 1, 5])
+    assert not torch.isnan(ctx[6]).any() and not torch.isnan(ctx[5, :64]).any()
+    qkv2 = ops.round_tf32(rn(B * N, 3 * H * d))
+    qkv2[7, H * d + 2 * 64 + 1] = float("nan")       # image 0, key token 7, head 2: every query of that head sees it
+    ctx2, _ = ops.attention_fwd_lse(qkv2, B, H, N, d)
+    assert torch.isnan(ctx2[:N, 128:192]).all() and not torch.isnan(ctx2[N:]).any()
+
+
 def test_gemm_rejects_bad_arguments(ops):
     from uvc_b200._lib import UvcError
     A, B = rn(16, 6), rn(16, 6)          # ld = 6 is not a multiple of 4

@@ -31,6 +31,14 @@ int attn_ldp(int N) { return (N + 3) / 4 * 4; }
 // All three operands are single-buffered (fp32 staging leaves no room for more), so the TMA warp also prefetches the NEXT head's boxes into L2
 // when it loads the current one: the load that follows a freed buffer then pays L2 latency, not DRAM latency.
 // ====================================================================================================================
+// Bit pattern for a TMEM-sourced TF32 operand: the tensor core truncates the low 13 mantissa bits, so adding half a TF32 ulp first makes that
+// truncation a round-to-nearest (2 instructions instead of cvt.rna's 3; the passes that call this are issue-bound).  The signed max keeps the
+// hardware's canonical NaN (0x7fffffff, where the add would wrap into the sign bit) a NaN, so a diverged run still shows up downstream.
+__device__ __forceinline__ uint32_t tf32_up(float x) {
+  const uint32_t u = __float_as_uint(x), v = u + 0x1000u;      // unsigned add: no signed-overflow assumptions for the compiler to exploit
+  return (uint32_t)max((int)v, (int)u);
+}
+
 constexpr int kANK = 208;                     // key rows staged / score columns (N <= 208)
 constexpr int kAThreads = 320;                // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 softmax / epilogue
 constexpr int kAQBytes = 2 * 2 * 128 * 128;   // 2 query tiles x 2 k-blocks x 128 rows x 128 B
@@ -248,8 +256,8 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
             const float e2 = ex2_approx(fmaf(__uint_as_float(r[j + 2]), p.scale_log2e, -mxs));
             const float e3 = ex2_approx(fmaf(__uint_as_float(r[j + 3]), p.scale_log2e, -mxs));
             sum0 += e0; sum1 += e1; sum2 += e2; sum3 += e3;
-            r[j] = __float_as_uint(e0) + 0x1000u; r[j + 1] = __float_as_uint(e1) + 0x1000u;
-            r[j + 2] = __float_as_uint(e2) + 0x1000u; r[j + 3] = __float_as_uint(e3) + 0x1000u;
+            r[j] = tf32_up(e0); r[j + 1] = tf32_up(e1);
+            r[j + 2] = tf32_up(e2); r[j + 3] = tf32_up(e3);
           }
           tmem_st_32x32(s_addr + c * 32, r);
         }
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
             float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
             if (c * 32 + j >= N) e = 0.f;
             sum0 += e;
-            r[j] = (c * 32 + j >= N) ? 0u : __float_as_uint(e) + 0x1000u;
+            r[j] = (c * 32 + j >= N) ? 0u : tf32_up(e);
           }
           tmem_st_32x32(s_addr + c * 32, r);
         }
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
             float e = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2e, -mxs));
             if (192 + j >= N) e = 0.f;
             sum1 += e;
-            r[j] = (192 + j >= N) ? 0u : __float_as_uint(e) + 0x1000u;
+            r[j] = (192 + j >= N) ? 0u : tf32_up(e);
           }
           tmem_st_32x16(s_addr + 192, r);
         }
@@ -340,10 +348,10 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_fwd_kernel(const __grid_con
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < 8; ++g) {            // 16-byte granule g of row `lane` sits at granule g ^ (row & 7): the 128-byte TMA swizzle
-              const uint32_t v0 = (__float_as_uint(__uint_as_float(o[4 * g]) * inv) + 0x1000u) & 0xffffe000u;
-              const uint32_t v1 = (__float_as_uint(__uint_as_float(o[4 * g + 1]) * inv) + 0x1000u) & 0xffffe000u;
-              const uint32_t v2 = (__float_as_uint(__uint_as_float(o[4 * g + 2]) * inv) + 0x1000u) & 0xffffe000u;
-              const uint32_t v3 = (__float_as_uint(__uint_as_float(o[4 * g + 3]) * inv) + 0x1000u) & 0xffffe000u;
+              const uint32_t v0 = __float_as_uint(round_tf32(__uint_as_float(o[4 * g]) * inv));
+              const uint32_t v1 = __float_as_uint(round_tf32(__uint_as_float(o[4 * g + 1]) * inv));
+              const uint32_t v2 = __float_as_uint(round_tf32(__uint_as_float(o[4 * g + 2]) * inv));
+              const uint32_t v3 = __float_as_uint(round_tf32(__uint_as_float(o[4 * g + 3]) * inv));
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)((g ^ (lane & 7)) << 4)), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
             }
             fence_proxy_async();
@@ -640,9 +648,9 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
               } else {
                 pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
                 ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -s_D[col0 + j]);
-                rx[j] = __float_as_uint(pr) + 0x1000u;
+                rx[j] = tf32_up(pr);
               }
-              ry[j] = __float_as_uint(ds) + 0x1000u;
+              ry[j] = tf32_up(ds);
             }
             if (PHASE == 2) tmem_st_32x32(lane_addr + kX + col0, rx);
             tmem_st_32x32(lane_addr + kY + col0, ry);
@@ -663,9 +671,9 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
               } else {
                 pr = ex2_approx(fmaf(__uint_as_float(rx[j]), p.scale_log2e, -s_lse[col0 + j]));
                 ds = pr * fmaf(__uint_as_float(ry[j]), p.scale, -s_D[col0 + j]);
-                rx[j] = __float_as_uint(pr) + 0x1000u;
+                rx[j] = tf32_up(pr);
               }
-              ry[j] = __float_as_uint(ds) + 0x1000u;
+              ry[j] = tf32_up(ds);
             }
             if (PHASE == 2) tmem_st_32x8(lane_addr + kX + col0, rx);
             tmem_st_32x8(lane_addr + kY + col0, ry);
@@ -705,7 +713,8 @@ __global__ void __launch_bounds__(kAThreads, 1) attn_bwd_kernel(const __grid_con
         BTR(4);
         if (row < N) {
           const long long off = ((long long)b * N + row) * p.ldo + h * 64 + hh * 32;      // 128-byte aligned: ldo and the head offsets are multiples of 32 floats
-          auto rnd = [](uint32_t u) { return __uint_as_float((u + 0x1000u) & 0xffffe000u); };    // round to TF32 (finite values)
+          auto rnd = [](uint32_t u) { return round_tf32(__uint_as_float(u)); };    // cvt.rna: keeps NaN / inf (the integer shortcut used for
+                                                                                    // the TMEM operands would turn a NaN into -0 here and hide a diverged run)
 #pragma unroll
           for (int j = 0; j < 32; j += 8)
             st_global_v8(p.out0 + off + j, rnd(o0[j]), rnd(o0[j + 1]), rnd(o0[j + 2]), rnd(o0[j + 3]), rnd(o0[j + 4]), rnd(o0[j + 5]), rnd(o0[j + 6]), rnd(o0[j + 7]));
