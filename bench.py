@@ -173,12 +173,14 @@ def run_gpu(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    def timed(fn, n, fin=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
             fn(i)
+        if fin is not None:
+            fin()                               # host work that belongs to the last step (its result read-back)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -229,13 +231,28 @@ def run_gpu(a):
         bx, by = bufs[i % 2]
         out = step(bx, by)                      # consumes bx in place (mixup)
         done[i % 2] = torch.cuda.Event(); done[i % 2].record(cur)
-        loss = float(out["loss"].item())        # device -> host read of the step's result (the ADMM state came back inside step())
-        d2h[0] = 4 + 4 * (1 + out["s"].size + out["r"].size + (out["gating"].size if out["gating"] is not None else 0))   # resolves the step's deferred ADMM read-back
-        return loss
+        # device -> host read of EVERY step's result (loss + the ADMM state the reference API returns), issued now as an asynchronous copy into
+        # pinned memory and consumed one step later, the way a training loop logs without stalling the launch queue
+        lh = loss_host[i % 2]
+        lh.copy_(out["loss"].detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event(); ev.record(cur)
+        resolve()
+        pending.append((ev, lh, out))
+
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending, losses = [], []
+
+    def resolve():
+        while pending:
+            ev, lh, out = pending.pop(0)
+            ev.synchronize()
+            losses.append(float(lh.item()))
+            d2h[0] = 4 + 4 * (1 + out["s"].size + out["r"].size + (out["gating"].size if out["gating"] is not None else 0))   # resolves the deferred ADMM read-back
     for i in range(min(3, a.warmup)):
         e2e_step(i)
+    resolve()
     w2 = time.time()
-    ms_e2e = timed(e2e_step, a.steps)
+    ms_e2e = timed(e2e_step, a.steps, fin=resolve)
     w3 = time.time()
     clk = clocks.stop([(w0, w1, "timed region"), (w2, w3, "end-to-end leg (timed region too short for a sample)")]) if rank == 0 else None
 
@@ -277,7 +294,9 @@ def run_gpu(a):
                    "parallelism": f"dp{world}", "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush"},
         "clocks": clk,
         "e2e": {"value": round(imgs / (ms_e2e / 1e3), 1), "unit": "images/sec", "ms_per_step": round(ms_e2e / a.steps, 3),
-                "h2d_bytes_per_step": int(x_host[0].numel() * 4 + y_host[0].numel() * 8), "d2h_bytes_per_step": int(d2h[0])},
+                "h2d_bytes_per_step": int(x_host[0].numel() * 4 + y_host[0].numel() * 8), "d2h_bytes_per_step": int(d2h[0]),
+                "readback": "every step's loss and ADMM state are copied to pinned host memory asynchronously and consumed one step later; the "
+                            "last step's read-back is inside the timed region", "last_loss": round(losses[-1], 4) if losses else None},
         "gpu_launches": launches,
         "step_tflops_per_gpu": round(step_flops / (ms / a.steps / 1e3) / 1e12, 1),
         "roofline": {"bound": "tensor", "kernel": "uvc::gemm2_tf32_kernel (persistent CTA pairs, tcgen05.mma cta_group::2 kind::tf32)",
