@@ -61,3 +61,34 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception) as e:
         m(torch.zeros(1, 3, 224, 224))
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+def test_epilogue_flag_values_match_the_header():
+    """The UVC_EPI_* / UVC_GEMM_* enum of include/uvc_b200.h and the constants the ctypes binding passes must agree bit for bit."""
+    text = open(os.path.join(ROOT, "include", "uvc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    vals = {k: int(v) for k, v in re.findall(r"\b(UVC_(?:EPI|GEMM)_\w+)\s*=\s*(\d+)", text)}
+    want = {"UVC_EPI_BIAS": _lib.EPI_BIAS, "UVC_EPI_GELU": _lib.EPI_GELU, "UVC_EPI_GELU_BWD": _lib.EPI_GELU_BWD, "UVC_EPI_RESIDUAL": _lib.EPI_RESIDUAL,
+            "UVC_EPI_ATOMIC": _lib.EPI_ATOMIC, "UVC_EPI_ROUND_TF32": _lib.EPI_ROUND_TF32, "UVC_EPI_COLSUM": _lib.EPI_COLSUM,
+            "UVC_GEMM_F16": _lib.GEMM_F16, "UVC_EPI_AUX_F16": _lib.EPI_AUX_F16}
+    assert vals == want
+    assert len(set(want.values())) == len(want) and all(v & (v - 1) == 0 for v in want.values())      # distinct single bits
+
+
+def test_deferred_host_values_resolve_lazily():
+    """uvc_optimizer(lazy=True) hands back Deferred handles; they must resolve once, through float() / np.asarray() / .tolist() / .size."""
+    import numpy as np
+    from uvc_b200.uvc_optimizer import Deferred
+
+    class Snap:
+        calls = 0
+
+        def numpy(self):
+            Snap.calls += 1
+            return np.arange(7, dtype=np.float32)
+    s = Snap()
+    cur, arr = Deferred(s, lambda h: float(h[0] + 0.5)), Deferred(s, lambda h: h[1:7].reshape(3, 2).copy())
+    assert Snap.calls == 0                                    # nothing fetched until first use
+    assert float(cur) == 0.5 and arr.size == 6 and arr.shape == (3, 2)
+    assert np.asarray(arr).tolist() == arr.tolist() == [[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]
+    assert f"{float(cur) * 100:.1f}" == "50.0"
