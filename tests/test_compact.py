@@ -1,0 +1,132 @@
+"""Stage-2 physical compaction, host side (uvc_b200/compact.py): the layout compiler and the compact checkpoint must give
+exactly the masked-dense forward the reference computes in Stage 2 (`weight.data *= mask` + hard block skip, post_train.py:228-231,
+models/model_distilled.py:496-500).  On CPU the runner's operators are swapped for plain-torch ones with the same signatures (the index
+bookkeeping is what is under test here); the GPU test runs the same runner on the sm_100a operators against the whole-model engine."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fixtures as fx, vit_oracle as vo
+from uvc_b200 import compact as cp
+
+
+class TorchOps:
+    """uvc_b200.ops look-alike (only what CompactViT calls)."""
+    EPI_GELU, EPI_ROUND_TF32 = 2, 32
+
+    @staticmethod
+    def round_tf32(t):
+        return t
+
+    @staticmethod
+    def im2col16(x, patch=16, round_tf32=False):
+        return F.unfold(x, kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, x.shape[1] * patch * patch)
+
+    @staticmethod
+    def linear(x, w, bias=None, out=None, flags=0, R=None):
+        y = F.linear(x, w, bias)
+        if flags & TorchOps.EPI_GELU:
+            y = F.gelu(y)
+        return y + R if R is not None else y
+
+    @staticmethod
+    def layernorm_fwd(x, gamma, beta, eps, y=None, ldx=None, M=None, save_stats=True, round_tf32=False):
+        C_ = gamma.numel()
+        if ldx is not None and ldx != C_:
+            x = x.reshape(-1)[: (M - 1) * ldx + C_].as_strided((M, C_), (ldx, 1))
+        return F.layer_norm(x.reshape(-1, C_), (C_,), gamma, beta, eps), None, None
+
+    @staticmethod
+    def assemble_tokens(pe, cls, pos, pscale=None, tmask=None):
+        if pscale is not None:
+            pe = pe * pscale.view(1, -1, 1)
+        B = pe.shape[0]
+        return torch.cat([cls.view(1, 1, -1).expand(B, -1, -1), pe], 1) + pos.unsqueeze(0)
+
+    @staticmethod
+    def attention_fwd(qkv, B, H, N, d, scale=None, save_P=True):
+        q, k, v = qkv.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+        p = ((q @ k.transpose(-2, -1)) * d ** -0.5).softmax(-1)
+        return (p @ v).transpose(1, 2).reshape(B * N, H * d), None
+
+
+def pruned_checkpoint(model_type="deit_tiny_patch16_224", depth=4, seed=3):
+    sd, dims = fx.make_state_dict(model_type, depth, seed=seed)
+    H, C_ = dims["num_heads"], dims["embed_dim"]
+    Fh = 4 * C_
+    g = fx._gen(seed, "prune")
+    for l in range(depth):
+        pre = f"blocks.{l}."
+        m1, m3, m2 = torch.ones(C_, C_), torch.ones(C_, Fh), torch.ones(Fh, C_)
+        if l == 0:       # one whole head, 16 dims inside another head, 301 neurons
+            m1[:, 64:128] = 0
+            m1[:, torch.randperm(64, generator=g)[:16]] = 0
+            dead = torch.randperm(Fh, generator=g)[:301]
+            m3[:, dead] = 0; m2[dead, :] = 0
+        if l == 2:       # degenerate block: every head and every neuron pruned (only the biases survive)
+            m1[:] = 0; m3[:] = 0; m2[:] = 0
+        sd[pre + "attn.proj.mask"], sd[pre + "mlp.fc2.mask"], sd[pre + "mlp.fc1.mask"] = m1, m3, m2
+    sd["block_skip_gating"][1] = torch.tensor([1.0, -1.0])          # block 1 hard-skipped
+    return sd, dims
+
+
+def masked_dense(sd):
+    out = dict(sd)
+    for k in list(sd):
+        if k.endswith(".mask"):
+            out[k[:-4] + "weight"] = sd[k[:-4] + "weight"] * sd[k]
+    return out
+
+
+def test_layout_and_compact_forward_equal_masked_dense():
+    sd, dims = pruned_checkpoint()
+    H = dims["num_heads"]
+    lay = cp.compile_layout(sd, H)
+    assert lay["blocks"][1] is None and lay["blocks"][0]["heads"] == [0, 2] and lay["blocks"][0]["dims"] == [48, 64]
+    assert lay["blocks"][0]["neurons"].numel() == 768 - 301 and lay["blocks"][2]["heads"] == [] and lay["blocks"][2]["neurons"].numel() == 0
+    assert lay["blocks"][3]["heads"] == [0, 1, 2] and lay["blocks"][3]["neurons"].numel() == 768
+    comp = cp.compact_state_dict(sd, lay)
+    csd = comp["state_dict"]
+    assert csd["blocks.0.attn.qkv.weight"].shape == (3 * 2 * 64, 192) and csd["blocks.0.attn.proj.weight"].shape == (192, 128)
+    assert csd["blocks.0.mlp.fc1.weight"].shape[0] == csd["blocks.0.mlp.fc2.weight"].shape[1] == 472      # 467 live, padded to a multiple of 8
+    assert not any(k.startswith("blocks.1.") for k in csd)
+    m = cp.macs(lay)
+    assert 0.40 < m["ratio"] < 0.50                                          # 2 of 4 blocks gone or empty, one thinned
+    x, _ = fx.make_batch(3, seed=11)
+    with torch.no_grad():
+        want = vo.forward(masked_dense(sd), x, 4, H, skip=[False, True, False, False])
+        got = cp.CompactViT(comp, backend=TorchOps)(x)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+def test_unpruned_checkpoint_compacts_to_itself():
+    sd, dims = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=5)
+    lay = cp.compile_layout(sd, dims["num_heads"])                            # no masks, default gates: nothing to remove
+    comp = cp.compact_state_dict(sd, lay)
+    assert cp.macs(lay)["ratio"] == 1.0
+    for k, v in comp["state_dict"].items():
+        assert torch.equal(v, sd[k]), k
+    x, _ = fx.make_batch(2, seed=12)
+    with torch.no_grad():
+        assert torch.allclose(cp.CompactViT(comp, backend=TorchOps)(x), vo.forward(sd, x, 2, dims["num_heads"]), atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_compact_runner_on_gpu_matches_engine_masked_dense():
+    """Same runner on the sm_100a operators vs the whole-model engine on the masked-dense checkpoint (DeiT-Small width, 4 blocks)."""
+    from functools import partial
+    from uvc_b200.models.model_distilled import DistilledVisionTransformer
+    sd, dims = pruned_checkpoint("deit_small_patch16_224", 4, seed=4)
+    H = dims["num_heads"]
+    comp = cp.compact_state_dict(sd, cp.compile_layout(sd, H))
+    x, _ = fx.make_batch(4, seed=13)
+    got = cp.CompactViT(comp).cuda()(x.cuda())
+    with torch.no_grad():
+        want = vo.forward(masked_dense(sd), x, 4, H, skip=[False, True, False, False])
+    m = DistilledVisionTransformer(enable_dist=0, patch_size=16, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                                   drop_rate=0, embed_dim=dims["embed_dim"], depth=4, num_heads=H)
+    m.load_state_dict({k: v for k, v in masked_dense(sd).items() if not k.endswith(".mask")}, strict=False)
+    with torch.no_grad():
+        eng, _ = m.cuda().eval()(x.cuda())
+    rel = lambda a, b: float((a.cpu() - b.cpu()).abs().max() / b.abs().max())
+    assert rel(got, want) < 1e-3 and rel(got, eng) < 1e-3
