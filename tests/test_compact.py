@@ -111,6 +111,20 @@ def test_unpruned_checkpoint_compacts_to_itself():
         assert torch.allclose(cp.CompactViT(comp, backend=TorchOps)(x), vo.forward(sd, x, 2, dims["num_heads"]), atol=2e-5)
 
 
+def test_export_cli_round_trip(tmp_path, capsys):
+    sd, dims = pruned_checkpoint()
+    src, dst = str(tmp_path / "stage2.pth.tar"), str(tmp_path / "compact.pt")
+    torch.save({"model": {"module." + k: v for k, v in sd.items()}}, src)             # DDP-prefixed, wrapped: what the loops can write
+    cp.main(["--checkpoint", src, "--out", dst, "--model_type", "deit_tiny_patch16_224"])
+    assert "compact" in capsys.readouterr().out
+    comp = torch.load(dst, map_location="cpu", weights_only=False)
+    x, _ = fx.make_batch(2, seed=14)
+    with torch.no_grad():
+        want = vo.forward(masked_dense(sd), x, 4, dims["num_heads"], skip=[False, True, False, False])
+        got = cp.CompactViT(comp, backend=TorchOps)(x)
+    assert (got - want).abs().max() <= 2e-5 * want.abs().max()
+
+
 @pytest.mark.gpu
 def test_compact_runner_on_gpu_matches_engine_masked_dense():
     """Same runner on the sm_100a operators vs the whole-model engine on the masked-dense checkpoint (DeiT-Small width, 4 blocks)."""

@@ -163,3 +163,32 @@ class CompactViT(torch.nn.Module):
                 xs = x1 + sd[pre + "mlp.fc2.bias"]
         cls_ln, _, _ = o.layernorm_fwd(xs, sd["norm.weight"], sd["norm.bias"], self.eps, ldx=N * C_, M=B, save_stats=False, round_tf32=True)
         return o.linear(cls_ln, sd["head.weight"], sd["head.bias"])
+
+
+def export(checkpoint_path, out_path, num_heads):
+    """Stage-1 / Stage-2 checkpoint (state dict with `.mask` buffers and `block_skip_gating`) -> compact checkpoint file.  Returns the MAC summary."""
+    ck = torch.load(checkpoint_path, map_location="cpu")
+    for key in ("model", "state_dict_ema", "state_dict"):
+        if isinstance(ck, dict) and key in ck and isinstance(ck[key], dict):
+            ck = ck[key]
+            break
+    ck = {(k[7:] if k.startswith("module.") else k): v for k, v in ck.items()}
+    layout = compile_layout(ck, num_heads)
+    torch.save(compact_state_dict(ck, layout), out_path)
+    return macs(layout)
+
+
+def main(argv=None):
+    import argparse
+    from .models import CONFIGS
+    ap = argparse.ArgumentParser(description="Export a physically compacted checkpoint from a UVC checkpoint (masks + gates).")
+    ap.add_argument("--checkpoint", required=True)
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--model_type", default="deit_small_patch16_224", choices=list(CONFIGS.keys()))
+    a = ap.parse_args(argv)
+    m = export(a.checkpoint, a.out, CONFIGS[a.model_type].num_heads)
+    print(f"dense {m['dense'] / 1e6:.1f} M MACs/image -> compact {m['compact'] / 1e6:.1f} M ({m['ratio'] * 100:.1f} %); wrote {a.out}")
+
+
+if __name__ == "__main__":
+    main()
