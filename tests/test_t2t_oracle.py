@@ -89,3 +89,31 @@ def test_host_front_end_matches_oracle_on_cpu(cases):
     assert (tok - ref).abs().max() <= 2e-5 * ref.abs().max() and int(macs) == int(macs_o)
     with pytest.raises(Exception, match="CUDA"):
         m(x)                                       # no CPU path for the backbone
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(), reason="/root/reference not present on this machine")
+def test_oracle_equals_reference_t2t_modules_live():
+    """Where the reference checkout exists (the build container): the restatement against the UNMODIFIED T2T modules imported in place, on fresh
+    seeds (not only the committed fixture) — tokens_to_token output, logits with hard skipping, and the MAC bookkeeping, bit for bit."""
+    import importlib
+    from oracle import ref_shim
+    ref_shim.load()
+    mod = importlib.import_module("T2TViT.models.t2t_vit")
+    for seed, depth, B in ((101, 2, 2), (202, 3, 1)):
+        sd, _ = fx.make_state_dict("t2t_vit_14", depth, seed=seed)
+        if depth == 3:
+            sd["block_skip_gating"][0] = torch.tensor([0.5, 0.5])            # not strictly greater: skipped (t2t_vit.py:192)
+        m = mod.T2T_ViT(tokens_type='performer', embed_dim=384, depth=depth, num_heads=6, mlp_ratio=3.)
+        m.block_skip_gating.data = sd["block_skip_gating"].clone()
+        m.load_state_dict({k: v for k, v in sd.items() if k != "block_skip_gating"}, strict=False)
+        m.eval()
+        x, _ = fx.make_batch(B, seed=seed)
+        with torch.no_grad():
+            ref_logits, (ref_macs_embed, ref_macs_list) = m(x)
+            ref_tok, _ = m.tokens_to_token(x)
+            tok, macs = vo.t2t_tokens(sd, x)
+            skip = [not bool(sd["block_skip_gating"][i, 1] > sd["block_skip_gating"][i, 0]) for i in range(depth)]
+            out = vo.forward(sd, x, depth, 6, eps=1e-5, skip=skip, tokens=tok)
+        assert torch.equal(tok, ref_tok) and torch.equal(out, ref_logits)
+        assert int(macs) == int(ref_macs_embed)
+        assert [[int(v) for v in r] for r in ref_macs_list] == [vo.block_macs(B, 197, 384, 6, 1152) if not s else [] for s in skip]
