@@ -144,3 +144,27 @@ def test_compact_runner_on_gpu_matches_engine_masked_dense():
         eng, _ = m.cuda().eval()(x.cuda())
     rel = lambda a, b: float((a.cpu() - b.cpu()).abs().max() / b.abs().max())
     assert rel(got, want) < 1e-3 and rel(got, eng) < 1e-3
+
+
+@pytest.mark.gpu
+def test_post_train_compact_eval_adapter_matches_the_model():
+    """post_train's `--compact_eval` path: the adapter built from a live model (its registered `.mask` buffers and gates) returns the model's
+    own eval logits (masks applied, block 1 skipped)."""
+    from functools import partial
+    from uvc_b200.models.model_distilled import DistilledVisionTransformer
+    from uvc_b200.post_train import CompactEval, apply_masks
+    sd, dims = pruned_checkpoint("deit_tiny_patch16_224", 4, seed=6)
+    m = DistilledVisionTransformer(enable_dist=0, patch_size=16, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
+                                   drop_rate=0, embed_dim=dims["embed_dim"], depth=4, num_heads=dims["num_heads"])
+    for _, mod in m.named_modules():
+        if hasattr(mod, "weight"):
+            mod.register_buffer("mask", torch.ones_like(mod.weight))
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    m = m.cuda().eval()
+    apply_masks(m)
+    x, _ = fx.make_batch(5, seed=15)
+    with torch.no_grad():
+        want, _ = m(x.cuda())
+        got, _ = CompactEval(m)(x.cuda(), -1, 0.9)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-3

@@ -116,8 +116,28 @@ def post_training(args, model, mixup_fn=None, criterion=None, lr=None, weight_de
     return best_acc
 
 
+class CompactEval(torch.nn.Module):
+    """The physically compacted model (uvc_b200/compact.py) behind the `(x, tau, ratio) -> (logits, macs)` call the validation loop makes:
+    skipped blocks, fully pruned heads and pruned neurons are not computed at all instead of being multiplied by zeros."""
+
+    def __init__(self, model):
+        super().__init__()
+        from .compact import CompactViT, compact_state_dict, compile_layout
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        layout = compile_layout(sd, model.blocks[0].attn.num_heads)
+        self.runner = CompactViT(compact_state_dict(sd, layout), eps=model.norm.eps).to(model.cls_token.device)
+
+    def forward(self, x, tau=-1, number=0.9):
+        return self.runner(x), None
+
+
 def valid(args, model, writer, test_loader, global_step):
     apply_masks(model)           # post_train.py:228-231
+    if getattr(args, "compact_eval", 0):
+        if args.enable_patch_gating == 2 or getattr(model, "enable_patch_gating", 0) or getattr(model, "enable_jumping", 0):
+            print("--compact_eval: token / patch gates and jumping connections are not in the compact runner; validating the masked-dense model")
+        else:
+            return jt.valid(args, CompactEval(model), writer, test_loader, global_step)
     return jt.valid(args, model, writer, test_loader, global_step)
 
 
@@ -125,6 +145,8 @@ def build_parser():
     p = jt.build_parser()
     p.add_argument("--checkpoint_dir", default=None, type=str, help="Stage-1 checkpoint (state dict with masks and gates)")
     p.add_argument("--epochs", default=120, type=int)
+    p.add_argument("--compact_eval", default=0, type=int,
+                   help="validate through the physically compacted model (skipped blocks / pruned heads / pruned neurons removed; same logits)")
     return p
 
 
