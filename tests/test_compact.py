@@ -99,6 +99,28 @@ def test_layout_and_compact_forward_equal_masked_dense():
     assert (got - want).abs().max() <= 2e-5 * want.abs().max()
 
 
+def test_layout_reproduces_the_reference_budget_of_the_fixed_50_percent_layout():
+    """Known answer (BASELINE.json configs[3]): DeiT-Base with blocks 8 and 10 skipped and, in the live blocks, 3 heads, 16
+    dimensions of every surviving head and 1417 neurons pruned evaluates to rho = 0.5001 under the reference's calc_flops with the deterministic
+    gate.  Only masks, gates and shapes are needed for the layout."""
+    C_, H, Fh, L = 768, 12, 3072, 12
+    sd = {"block_skip_gating": torch.tensor([[-1.0, 1.0]] * L), "blocks.0.attn.proj.weight": torch.empty(C_, C_, device="meta"),
+          "blocks.0.mlp.fc1.weight": torch.empty(Fh, C_, device="meta")}
+    sd["block_skip_gating"][8] = torch.tensor([1.0, -1.0]); sd["block_skip_gating"][10] = torch.tensor([1.0, -1.0])
+    for l in range(L):
+        m1, m3 = torch.ones(1, C_, dtype=torch.uint8), torch.ones(1, Fh, dtype=torch.uint8)       # a mask column is live iff any entry is non-zero
+        m1[:, : 3 * 64] = 0
+        for h in range(3, H):
+            m1[:, h * 64: h * 64 + 16] = 0
+        m3[:, :1417] = 0
+        sd[f"blocks.{l}.attn.proj.mask"], sd[f"blocks.{l}.mlp.fc2.mask"] = m1, m3
+    lay = cp.compile_layout(sd, H)
+    assert sum(b is None for b in lay["blocks"]) == 2 and lay["blocks"][0]["heads"] == list(range(3, 12)) and lay["blocks"][0]["dims"] == [48] * 9
+    m = cp.macs(lay)
+    assert abs(m["budget_ratio"] - 0.5001) < 1e-4
+    assert m["budget_ratio"] < m["ratio"] < 0.53                                   # the runner keeps the 16 zeroed dims per head
+
+
 def test_unpruned_checkpoint_compacts_to_itself():
     sd, dims = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=5)
     lay = cp.compile_layout(sd, dims["num_heads"])                            # no masks, default gates: nothing to remove

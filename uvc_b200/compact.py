@@ -103,7 +103,18 @@ def macs(layout, n_tokens=197, patch_macs=None):
             continue
         h, f = len(b["heads"]), int(b["neurons"].numel())
         comp += N * C_ * 3 * h * d + 2 * h * N * N * d + N * h * d * C_ + 2 * N * C_ * f
-    return {"dense": dense, "compact": comp, "ratio": comp / dense}
+    # the reference's own resource model (uvc_utils.py:409-471) with the deterministic Stage-2 gate: it also credits
+    # the dimensions pruned INSIDE surviving heads (rho_r), which the compact runner does not cut yet
+    budget = embed
+    m01, m23, m45 = N * C_ * 3 * C_ + H * N * N * d, H * N * N * d + N * C_ * C_, 2 * N * C_ * Fh
+    for b in layout["blocks"]:
+        if b is None:
+            continue
+        rho0 = len(b["heads"]) / H
+        rho_r = sum(b["dims"]) / C_
+        rho1 = int(b["neurons"].numel()) / Fh
+        budget += m01 * rho0 + m23 * rho_r + m45 * rho1
+    return {"dense": dense, "compact": comp, "ratio": comp / dense, "budget_ratio": budget / dense}
 
 
 class CompactViT(torch.nn.Module):
