@@ -190,3 +190,28 @@ def test_post_train_compact_eval_adapter_matches_the_model():
         want, _ = m(x.cuda())
         got, _ = CompactEval(m)(x.cuda(), -1, 0.9)
     assert float((got - want).abs().max() / want.abs().max()) < 1e-3
+
+
+def test_clip_norm_closed_form_for_pruned_neurons():
+    """Groundwork for the training side of the compaction: the reference clips over the gradients of MASKED weights too, and
+    those are not zero.  For a pruned neuron n (fc1 row and fc2 column masked) they have a closed form that needs nothing from the pruned part:
+    d fc2.weight[:, n] = gelu(fc1.bias[n]) * colsum(dY) (= gelu(b1[n]) * d fc2.bias) and d fc1.weight[n, :] = 0, d fc1.bias[n] = 0."""
+    torch.manual_seed(0)
+    M, C_, Fh = 37, 16, 40
+    x = torch.randn(M, C_)
+    W2, b1 = torch.randn(Fh, C_, requires_grad=True), torch.randn(Fh, requires_grad=True)
+    W3, b2 = torch.randn(C_, Fh, requires_grad=True), torch.randn(C_, requires_grad=True)
+    dead = torch.tensor([1, 5, 6, 22, 39])
+    m2, m3 = torch.ones(Fh, C_), torch.ones(C_, Fh)
+    m2[dead] = 0; m3[:, dead] = 0
+    with torch.no_grad():                                   # `weight.data *= mask` (post_train.py:357-360): the parameters themselves are zeroed
+        W2.mul_(m2); W3.mul_(m3)
+    y = F.linear(F.gelu(F.linear(x, W2, b1)), W3, b2)
+    r = torch.randn(M, C_)
+    (y * r).sum().backward()
+    want_sq = float((W3.grad[:, dead] ** 2).sum() + (W2.grad[dead] ** 2).sum() + (b1.grad[dead] ** 2).sum())
+    colsum_dy = b2.grad                                     # = colsum(dY): computed by the backward anyway
+    closed_sq = float((colsum_dy ** 2).sum() * (F.gelu(b1.detach()[dead]) ** 2).sum())
+    assert abs(want_sq - closed_sq) <= 1e-5 * want_sq
+    assert float(W2.grad[dead].abs().max()) == 0.0 and float(b1.grad[dead].abs().max()) == 0.0
+    assert torch.allclose(W3.grad[:, dead], colsum_dy[:, None] * F.gelu(b1.detach()[dead])[None, :], rtol=1e-5, atol=1e-6)
