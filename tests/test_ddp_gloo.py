@@ -25,12 +25,13 @@ class ArenaModel(nn.Module):
         self.flat_param = torch.randn(40, generator=g)
         self.flat_grad = torch.zeros(40)
         self.w = nn.Parameter(self.flat_param[:32].view(4, 8)); self.b = nn.Parameter(self.flat_param[32:36])
+        self.pos = nn.Parameter(self.flat_param[36:40], requires_grad=False)   # frozen arena tenant (like T2T-ViT's sinusoid pos_embed): no .grad
         self.gate = nn.Parameter(torch.randn(3, 2, generator=g))          # lives outside the arena (like block_skip_gating)
         self.w.grad = self.flat_grad[:32].view(4, 8); self.b.grad = self.flat_grad[32:36]
         self.register_buffer("mask", torch.full((4, 8), float(seed)))
 
     def engine_parameters(self):
-        return [self.w, self.b]
+        return [self.w, self.b, self.pos]
 
     def forward(self, x):
         return (x @ self.w.t() + self.b).sum() * self.gate.sum()

@@ -74,8 +74,8 @@ class DistributedDataParallel(nn.Module):
         fg = getattr(m, "flat_grad", None) if getattr(m, "engine_parameters", None) else None
         if fg is not None:
             lo, hi = fg.data_ptr(), fg.data_ptr() + fg.numel() * 4
-            eng = m.engine_parameters()
-            if all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in eng):
+            eng = [p for p in m.engine_parameters() if p.requires_grad]      # frozen arena tenants (T2T's sinusoid pos_embed) have no .grad
+            if eng and all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in eng):
                 self._allreduce_mean(fg)                      # ONE collective for the whole model
                 in_arena = {id(p) for p in eng}
         rest = [p.grad for p in m.parameters() if p.grad is not None and id(p) not in in_arena]
