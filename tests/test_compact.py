@@ -215,3 +215,51 @@ def test_clip_norm_closed_form_for_pruned_neurons():
     assert abs(want_sq - closed_sq) <= 1e-5 * want_sq
     assert float(W2.grad[dead].abs().max()) == 0.0 and float(b1.grad[dead].abs().max()) == 0.0
     assert torch.allclose(W3.grad[:, dead], colsum_dy[:, None] * F.gelu(b1.detach()[dead])[None, :], rtol=1e-5, atol=1e-6)
+
+
+def _tiny_sd(seed, depth=2, C_=128, H=2):
+    """A 2-head, 128-wide model in the reference's key layout (fixtures.param_shapes), small enough for property tests."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in fx.param_shapes(embed_dim=C_, depth=depth, num_heads=H, mlp_ratio=1, num_classes=10).items():
+        if k.endswith("skip_gating"):
+            sd[k] = torch.tensor([-1.0, 1.0]).expand(shp).contiguous()
+        elif "norm" in k and k.endswith("weight"):
+            sd[k] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        else:
+            sd[k] = torch.randn(shp, generator=g) * (0.05 if k.endswith("weight") else 0.02)
+    return sd
+
+
+def test_random_layouts_compact_equals_masked_dense():
+    """Property: for ANY pattern of pruned proj columns / fc2 columns / fc1 rows and skipped blocks, the compact forward equals the masked-dense one."""
+    from hypothesis import given, settings, strategies as st
+    depth, C_, H, Fh = 2, 128, 2, 128
+
+    @settings(max_examples=12, deadline=None)
+    @given(seed=st.integers(0, 10 ** 6), p_col=st.floats(0.0, 1.0), p_neu=st.floats(0.0, 1.0), skip=st.lists(st.booleans(), min_size=depth, max_size=depth),
+           kill_head=st.lists(st.booleans(), min_size=depth * H, max_size=depth * H))
+    def run(seed, p_col, p_neu, skip, kill_head):
+        sd = _tiny_sd(seed, depth, C_, H)
+        g = torch.Generator().manual_seed(seed + 1)
+        for l in range(depth):
+            pre = f"blocks.{l}."
+            keep1 = (torch.rand(C_, generator=g) >= p_col * 0.7).float()
+            for h in range(H):
+                if kill_head[l * H + h]:
+                    keep1[h * 64:(h + 1) * 64] = 0
+            keep3 = (torch.rand(Fh, generator=g) >= p_neu * 0.9).float()
+            sd[pre + "attn.proj.mask"] = keep1.expand(C_, C_).contiguous()
+            sd[pre + "mlp.fc2.mask"] = keep3.expand(C_, Fh).contiguous()
+            sd[pre + "mlp.fc1.mask"] = keep3.view(Fh, 1).expand(Fh, C_).contiguous()
+            if skip[l]:
+                sd["block_skip_gating"][l] = torch.tensor([0.3, 0.3])
+        lay = cp.compile_layout(sd, H)
+        x = torch.randn(2, 3, 224, 224, generator=g)
+        with torch.no_grad():
+            want = vo.forward(masked_dense(sd), x, depth, H, skip=list(skip))
+            got = cp.CompactViT(cp.compact_state_dict(sd, lay), backend=TorchOps)(x)
+        assert (got - want).abs().max() <= 3e-5 * want.abs().max().clamp_min(1e-6)
+        m = cp.macs(lay)
+        assert 0.0 < m["budget_ratio"] <= m["ratio"] + 1e-12 <= 1.0 + 1e-12
+    run()
