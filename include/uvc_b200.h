@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 6
+#define UVC_ABI_VERSION 7
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -86,8 +86,9 @@ enum {
                               tensor core truncates its inputs, rounding here keeps the error unbiased) */
   UVC_EPI_COLSUM = 64,     /* colsum[col] += sum_rows v[row,col] (before TF32 rounding): the bias gradient of the Linear whose
                               output gradient this GEMM produces, fused so the tensor is not re-read (fp32 atomics) */
-  UVC_GEMM_F16 = 128,      /* A and B hold fp16 values (K-major, ld in fp16 elements, ld % 8 == 0): tcgen05.mma kind::f16 with fp32
-                              accumulation -- the 10 mantissa bits of TF32 at half the operand bytes.  Unbatched, M >= 1, K-major only. */
+  UVC_GEMM_F16 = 128,      /* A and B hold fp16 values (ld / batch strides in fp16 elements, multiples of 8): tcgen05.mma kind::f16 with fp32
+                              accumulation -- the 10 mantissa bits of TF32 at half the operand bytes.  K-major unbatched operands run on the
+                              CTA-pair kernel; MN-major operands, split-K and batches on the 128 x 128 kernel (fp32 output only there). */
   UVC_EPI_AUX_F16 = 256    /* `aux` points to fp16 values (ldaux in fp16 elements, ldaux % 4 == 0, 8 B-aligned): the gelu' factors are in
                               [-0.13, 1.13] and the product they enter is rounded to TF32 anyway, so 11 significant bits lose nothing and
                               the GELU pair of epilogues moves half the aux bytes.  CTA-pair kernel only (unbatched operands). */
@@ -107,7 +108,8 @@ typedef struct {
   const float* alpha_dev;  /* optional device scalar multiplied into alpha (gate values) */
   const float* beta_dev;   /* optional device scalar multiplied into beta */
   int32_t flags;           /* UVC_EPI_* */
-  int32_t _pad;
+  float colsum_scale;      /* multiplies the UVC_EPI_COLSUM column sums before they are accumulated; 0 means 1 (how the loss scale of the
+                              fp16 gradient tensors is taken back out of a fused bias gradient) */
   float* colsum;           /* [N], accumulated into when UVC_EPI_COLSUM is set */
   void* D16; int64_t ldd16; /* optional fp16 copy of the output [M, ldd16] (round to nearest), for consumers that read it as an fp16 GEMM
                               operand; D may then be NULL.  Needs the unbatched CTA-pair kernel (N % 4 == 0, 16 B-aligned rows). */
@@ -137,6 +139,17 @@ UVC_API int uvc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int
 UVC_API int uvc_layernorm_bwd_cs(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                                  const float* gamma, const float* r1, const float* r2, const float* s2_dev,
                                  float* dx, int64_t lddx, float* dgamma, float* dbeta, float* cs_r1, float* cs_out, int32_t M, int32_t C, void* stream);
+/* 16-bit operand storage variants (the engine's default precision mode, see uvc_vit_dims.operand_f16):
+ *   uvc_layernorm_fwd_f16: y16 is fp16 [M, ldy] -- the A operand of the kind::f16 GEMM that follows the norm.
+ *   uvc_layernorm_bwd_f16: dy16 is fp16 and carries the backward's loss scale (dy = dy_scale * dy16); dx (fp32, unscaled) as above and,
+ *                          when dx16 != NULL, dx16 = fp16(dx16_scale * dx): the operand copy of the stream gradient for the next GEMMs.
+ *   uvc_cvt_f16:           dst16 [rows, cols] = fp16(src) and / or dstT16 [cols, rows] = fp16(src^T) (weights: forward and dgrad operands). */
+UVC_API int uvc_layernorm_fwd_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy,
+                                  float* mean, float* rstd, int32_t M, int32_t C, void* stream);
+UVC_API int uvc_layernorm_bwd_f16(const void* dy16, int64_t lddy, float dy_scale, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                                  const float* gamma, const float* r1, const float* r2, const float* s2_dev, float* dx, void* dx16, float dx16_scale,
+                                  int64_t lddx, float* dgamma, float* dbeta, float* cs_r1, float* cs_out, int32_t M, int32_t C, void* stream);
+UVC_API int uvc_cvt_f16(const float* src, void* dst16, void* dstT16, int32_t rows, int32_t cols, void* stream);
 /* in-place row softmax over the first n (<= 256) columns of S[rows][ld] (models/model_distilled.py:180) */
 UVC_API int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream);
 /* dP <- scale * P .* (dP - rowsum(dP .* P)) */
@@ -178,6 +191,13 @@ UVC_API int uvc_attention_fwd_lse(const float* qkv, float* lse, float* ctx, int3
  * dqkv_bias (optional, [3*H*d]) accumulates the column sums of dqkv, i.e. the gradient of attn.qkv.bias, in the same pass. */
 UVC_API int uvc_attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, const float* dctx, float* D_ws, float* dqkv,
                                     float* dqkv_bias, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+/* The same fused pair with fp16 operand storage (d == 64, N <= 208): qkv16 / ctx16 / dctx16 / dqkv16 hold fp16 values in the fp32 path's
+ * layouts; kind::f16 MMAs, fp32 accumulation and softmax; Q / K / V double-buffered in shared memory; one staged copy of each operand
+ * serves the score (K-major) and the output (MN-major) MMAs.  dctx16 may carry a loss scale (the backward is linear in it): dqkv16
+ * then carries it too and dqkv_bias receives db_scale * column sums (pass 1 / scale). */
+UVC_API int uvc_attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
+UVC_API int uvc_attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* D_ws, void* dqkv16,
+                                  float* dqkv_bias, float db_scale, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
 /* dqkv [B*N, 3*H*d] from dctx [B*N, H*d]; dP is scratch of the same size as P */
 UVC_API int uvc_attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv,
                               int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream);
@@ -225,6 +245,12 @@ typedef struct {
   int32_t B, img, patch, in_chans;
   int32_t C, H, Fh, L, num_classes;
   float ln_eps;
+  int32_t operand_f16;           /* 0: fp32 operand storage, tcgen05 kind::tf32 everywhere (round 1's path).
+                                    1: every tensor that only feeds GEMMs (LayerNorm outputs, qkv, attention context, gelu(fc1), the operand
+                                       copies of the gradients) is stored as fp16 -- the same 10 mantissa bits -- and the block GEMMs / attention run
+                                       kind::f16 with fp32 accumulation; residual stream, statistics, softmax, logits, loss and every parameter
+                                       gradient stay fp32.  Needs head dim 64, <= 208 tokens, C % 8 == 0, Fh % 8 == 0.
+                                    The workspace layout depends on it: use the same value for workspace_bytes / forward / backward. */
 } uvc_vit_dims;
 
 typedef struct {
@@ -255,7 +281,8 @@ typedef struct {
   const float* patch_scale;
   const float* token_mask;
   int32_t enable_jumping;
-  int32_t _pad;
+  float grad_scale;              /* operand_f16 only: the power-of-two loss scale S the fp16 gradient operands carry (g16 = fp16(S g)); it is taken
+                                    back out wherever an fp32 result is produced, so every output of this call is the true gradient.  <= 0 means 1. */
   float* d_blend;                /* [L,2], accumulated; NULL if blend == NULL */
   float* d_patch_scale;          /* [np] accumulated, or NULL */
   float* d_token_mask;           /* [B, np] written, or NULL */

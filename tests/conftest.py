@@ -25,3 +25,10 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(params=["f16", "tf32"])
+def precision(request, monkeypatch):
+    """Run a model-level GPU test in both engine precision modes: fp16 operand storage (the default) and fp32 storage / TF32 MMAs."""
+    monkeypatch.setenv("UVC_PRECISION", request.param)
+    return request.param

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
 
 def test_version_and_struct_sizes():
     lib = _lib.load()
-    assert lib.uvc_version() == 6
+    assert lib.uvc_version() == 7
     for name, st in _lib._ABI_STRUCTS.items():
         assert lib.uvc_abi_sizeof(name.encode()) == ctypes.sizeof(st), name
     assert lib.uvc_abi_sizeof(b"no_such_struct") == -1
@@ -48,6 +48,12 @@ def test_workspace_size_query_runs_on_cpu():
     train = lib.uvc_vit_workspace_bytes(ctypes.byref(d), 1)
     infer = lib.uvc_vit_workspace_bytes(ctypes.byref(d), 0)
     assert 0 < infer < train < 40 * 2 ** 30
+    d.operand_f16 = 1                      # fp16 operand storage: the saved activations shrink by about a third
+    train16 = lib.uvc_vit_workspace_bytes(ctypes.byref(d), 1)
+    infer16 = lib.uvc_vit_workspace_bytes(ctypes.byref(d), 0)
+    assert 0 < infer16 < train16 < 0.8 * train
+    d.H = 4                                # head dim 96: the fp16 mode is refused through the size query's 0
+    assert lib.uvc_vit_workspace_bytes(ctypes.byref(d), 1) == 0 and b"fp16 operand storage" in lib.uvc_last_error()
 
 
 def test_no_cpu_fallback():

@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from oracle import fixtures as fx, vit_oracle as vo
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("precision")]
 
 LOGIT_TOL = 1e-3
 GRAD_TOL = 5e-3

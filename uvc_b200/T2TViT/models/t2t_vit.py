@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ..._lib import VitDims
+from ..._lib import VitDims, operand_f16_for
 from ...models.model_distilled import DistilledVisionTransformer, _VitFunction, _engine_param_list, gumbel_softmax
 from .token_performer import Token_performer
 
@@ -104,6 +104,7 @@ class T2T_ViT(DistilledVisionTransformer):
         d.C, d.H, d.Fh, d.L = self.embed_dim, self.blocks[0].attn.num_heads, self.blocks[0].mlp.fc1.out_features, len(self.blocks)
         d.num_classes = self.num_classes
         d.ln_eps = float(self.norm.eps)
+        d.operand_f16 = 1 if operand_f16_for(self, d.C // d.H, self.num_patches + 1, d.C, d.Fh) else 0
         return d
 
     def _macs_backbone(self, B, executed):

@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ("R", C.c_void_p), ("ldr", C.c_int64), ("r_bs1", C.c_int64), ("r_bs2", C.c_int64),
                 ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_bs1", C.c_int64), ("aux_bs2", C.c_int64),
                 ("alpha", C.c_float), ("beta", C.c_float), ("alpha_dev", C.c_void_p), ("beta_dev", C.c_void_p),
-                ("flags", C.c_int32), ("_pad", C.c_int32), ("colsum", C.c_void_p), ("D16", C.c_void_p), ("ldd16", C.c_int64)]
+                ("flags", C.c_int32), ("colsum_scale", C.c_float), ("colsum", C.c_void_p), ("D16", C.c_void_p), ("ldd16", C.c_int64)]
 
 
 _F = C.c_void_p   # device float*
@@ -47,7 +47,7 @@ class VitTensors(C.Structure):
 class VitDims(C.Structure):
     _fields_ = [("B", C.c_int32), ("img", C.c_int32), ("patch", C.c_int32), ("in_chans", C.c_int32),
                 ("C", C.c_int32), ("H", C.c_int32), ("Fh", C.c_int32), ("L", C.c_int32), ("num_classes", C.c_int32),
-                ("ln_eps", C.c_float)]
+                ("ln_eps", C.c_float), ("operand_f16", C.c_int32)]
 
 
 class VitForwardArgs(C.Structure):
@@ -59,7 +59,7 @@ class VitForwardArgs(C.Structure):
 class VitBackwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("g", VitTensors), ("dlogits", _F), ("blend", _F),
                 ("skip_host", C.c_void_p), ("patch_scale", _F), ("token_mask", _F), ("enable_jumping", C.c_int32),
-                ("_pad", C.c_int32), ("d_blend", _F), ("d_patch_scale", _F), ("d_token_mask", _F),
+                ("grad_scale", C.c_float), ("d_blend", _F), ("d_patch_scale", _F), ("d_token_mask", _F),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("d_pe", _F)]
 
 
@@ -90,12 +90,25 @@ EXPORTS = [
     "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
     "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
+    "uvc_layernorm_fwd_f16", "uvc_layernorm_bwd_f16", "uvc_cvt_f16", "uvc_attention_fwd_f16", "uvc_attention_bwd_f16",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
 EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM, GEMM_F16, EPI_AUX_F16 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 _lib = None
+
+# Precision mode of the engine (uvc_vit_dims.operand_f16).  Default: fp16 operand storage wherever the kernels support it; UVC_PRECISION=tf32 (or
+# model.operand_f16 = False) selects the fp32-storage / TF32 path of round 1.  The fp16 gradient operands carry a power-of-two loss scale
+# (model.grad_scale, default below) that the engine removes again wherever it produces an fp32 gradient.
+DEFAULT_GRAD_SCALE = 8192.0
+
+
+def operand_f16_for(model, d, ntok, C_, Fh):
+    want = getattr(model, "operand_f16", None)
+    if want is None:
+        want = os.environ.get("UVC_PRECISION", "f16").lower() not in ("tf32", "fp32", "0")
+    return bool(want) and d == 64 and ntok <= 208 and C_ % 8 == 0 and Fh % 8 == 0
 
 
 def lib_path():
@@ -132,6 +145,11 @@ def load():
         "uvc_layernorm_fwd": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, i32, vp],
         "uvc_layernorm_bwd": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i32, i32, vp],
         "uvc_layernorm_bwd_cs": [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i32, i32, vp],
+        "uvc_layernorm_fwd_f16": [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, vp],
+        "uvc_layernorm_bwd_f16": [vp, i64, f32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, f32, i64, vp, vp, vp, vp, i32, i32, vp],
+        "uvc_cvt_f16": [vp, vp, vp, i32, i32, vp],
+        "uvc_attention_fwd_f16": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
+        "uvc_attention_bwd_f16": [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, f32, vp],
         "uvc_softmax_fwd": [vp, i64, i64, i32, i32, vp],
         "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, i32, vp],
         "uvc_colsum": [vp, i64, i32, i32, vp, vp, vp],

@@ -32,7 +32,7 @@ struct alignas(64) GemmKParams {
   const float* alpha_dev; const float* beta_dev;
   float* colsum;
   void* D16; long long ldd16;           // optional fp16 copy of the output (v2 kernel), row stride in fp16 elements
-  float alpha, beta;
+  float alpha, beta, colsum_scale;
   int M, N, K, nb1, nb2, splits, flags;
   int a_mn, b_mn;
   int a_use1, a_use2, b_use1, b_use2;   // operand varies with batch index i1 / i2 (else coordinate 0)
@@ -72,7 +72,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
   const int z = zs / p.splits;
   const int i1 = z % p.nb1, i2 = z / p.nb1;
 
-  const int nkb_total = (p.K + BK - 1) / BK;
+  const int bke = p.f16 ? 2 * BK : BK;                 // elements per 128-byte k-block row: 32 fp32 or 64 fp16
+  const int nkb_total = (p.K + bke - 1) / bke;
   const int kb0 = (int)(((long long)nkb_total * split) / p.splits);
   const int kb1 = (int)(((long long)nkb_total * (split + 1)) / p.splits);
   const int nkb = kb1 - kb0;
@@ -105,17 +106,25 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
       mbar_wait(empty_bar(s), ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
-        const int k0 = (kb0 + it) * BK;
+        const int k0 = (kb0 + it) * bke;
         const uint32_t sA = smem_base + s * Cfg::STAGE_BYTES;
         const uint32_t sB = sA + Cfg::A_BYTES;
+        // MN-major staging: fp32 = groups of 32 (mn) x 32 (k) in the 32 B-atom swizzle (4 KB each); fp16 = groups of 64 (mn) x 64 (k) in the
+        // standard 128 B swizzle (8 KB each).  Either way one group is one TMA box and the UMMA descriptor's LBO is the group pitch.
         if (!p.a_mn) {
           tma_load_4d(sA, &p.tmA, full_bar(s), k0, m0, za1, za2);
+        } else if (p.f16) {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_4d(sA + c * 8192, &p.tmA, full_bar(s), m0 + c * 64, k0, za1, za2);
         } else {
 #pragma unroll
           for (int c = 0; c < BM / 32; ++c) tma_load_4d(sA + c * 4096, &p.tmA, full_bar(s), m0 + c * 32, k0, za1, za2);
         }
         if (!p.b_mn) {
           tma_load_4d(sB, &p.tmB, full_bar(s), k0, n0, zb1, zb2);
+        } else if (p.f16) {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_4d(sB + c * 8192, &p.tmB, full_bar(s), n0 + c * 64, k0, zb1, zb2);
         } else {
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) tma_load_4d(sB + c * 4096, &p.tmB, full_bar(s), n0 + c * 32, k0, zb1, zb2);
@@ -128,13 +137,19 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4  (cute/arch/mma_sm100_desc.hpp bit layout).  The smem descriptors are
     // split into a constant high word and a low word advanced by one add per k-slice / stage (see umma_desc_lo).
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+    // fp16 operands (kind::f16, K = 16 per instruction): K-major staging is byte-identical to the fp32 one (128 B rows, 16 B atoms, one K slice =
+    // 32 B); MN-major fp16 uses the standard 128 B swizzle with SBO = 1024 B (8 k-rows), LBO = 8192 B (64 mn) and one K slice = 16 rows = 2048 B.
+    const bool f16 = p.f16 != 0;
+    const uint32_t fmt = f16 ? 0u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint32_t a_hi = p.a_mn ? umma_desc_hi(512, 1) : umma_desc_hi(1024, 2);
-    const uint32_t b_hi = p.b_mn ? umma_desc_hi(512, 1) : umma_desc_hi(1024, 2);
-    const uint32_t a_k = p.a_mn ? 64u : 2u, b_k = p.b_mn ? 64u : 2u;
-    const uint32_t a_lo0 = umma_desc_lo(smem_base, p.a_mn ? 4096u : 16u);
-    const uint32_t b_lo0 = umma_desc_lo(smem_base + Cfg::A_BYTES, p.b_mn ? 4096u : 16u);
+    const uint32_t mn_hi = f16 ? umma_desc_hi(1024, 2) : umma_desc_hi(512, 1);
+    const uint32_t mn_k = f16 ? 128u : 64u, mn_lbo = f16 ? 8192u : 4096u;
+    const uint32_t a_hi = p.a_mn ? mn_hi : umma_desc_hi(1024, 2);
+    const uint32_t b_hi = p.b_mn ? mn_hi : umma_desc_hi(1024, 2);
+    const uint32_t a_k = p.a_mn ? mn_k : 2u, b_k = p.b_mn ? mn_k : 2u;
+    const uint32_t a_lo0 = umma_desc_lo(smem_base, p.a_mn ? mn_lbo : 16u);
+    const uint32_t b_lo0 = umma_desc_lo(smem_base + Cfg::A_BYTES, p.b_mn ? mn_lbo : 16u);
     int s = 0; uint32_t ph = 0, acc = 0;
     for (int it = 0; it < nkb; ++it) {
       mbar_wait(full_bar(s), ph);
@@ -143,7 +158,10 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
         const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
         const uint32_t b_lo = b_lo0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 8; ++k4) umma_tf32_lh(tmem_base, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+        for (int k4 = 0; k4 < BK / 8; ++k4) {
+          if (f16) umma_f16_lh(tmem_base, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+          else umma_tf32_lh(tmem_base, a_lo + k4 * a_k, a_hi, b_lo + k4 * b_k, b_hi, idesc, (k4 > 0) ? 1u : acc);
+        }
         umma_commit(empty_bar(s));     // frees this smem stage once the MMAs above have read it
       }
       __syncwarp();
@@ -191,7 +209,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
           float t = (row < p.M) ? __uint_as_float(r[j]) * alpha : 0.f;
           if ((flags & UVC_EPI_BIAS) && first_split && col0 + j < p.N) t += (row < p.M) ? __ldg(p.bias + col0 + j) : 0.f;
           t = warp_sum(t);
-          if (lane == 0 && col0 + j < p.N) atomicAdd(p.colsum + col0 + j, t);
+          if (lane == 0 && col0 + j < p.N) atomicAdd(p.colsum + col0 + j, t * p.colsum_scale);
         }
       }
       if (row < p.M) {
@@ -557,7 +575,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
             cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x, cs.y, cs.z, cs.w);
+            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x * p.colsum_scale, cs.y * p.colsum_scale, cs.z * p.colsum_scale, cs.w * p.colsum_scale);
           }
           __syncwarp();                                // staging tile is rewritten by the next chunk
         }
@@ -609,6 +627,21 @@ int encode_tmap_4d(CUtensorMap* tm, const float* base, const unsigned long long 
   return UVC_OK;
 }
 
+// generic 4-D fp16 tiled tensor map, 128 B swizzle (16 B atoms: one staged copy serves K-major and MN-major 16-bit UMMA operands alike)
+int encode_tmap_4d_f16(CUtensorMap* tm, const void* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                       const unsigned int box[4], const char* name) {
+  PFN_tmapEncodeTiled enc = get_encode_fn();
+  UVC_REQUIRE(enc != nullptr, UVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UVC_REQUIRE(r == CUDA_SUCCESS, UVC_ERR_CUDA, "cuTensorMapEncodeTiled(%s, fp16) failed with CUresult %d", name, (int)r);
+  return UVC_OK;
+}
+
 // rows_mn: logical M or N extent; box_rows: tile rows for the K-major box
 static int make_tmap(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K, int nb1, int nb2, int box_rows, const char* name) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
@@ -635,17 +668,24 @@ static int make_tmap(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K,
   return UVC_OK;
 }
 
-// K-major fp16 operand [rows][K]: boxes of 64 elements (128 B) x box_rows, 128 B swizzle -- byte-for-byte the staging layout of the fp32 path
-static int make_tmap_f16(CUtensorMap* tm, const uvc_operand& op, int rows, int K, int box_rows, const char* name) {
+// fp16 operand.  K-major [rows][K]: boxes of 64 elements (128 B) x box_rows, 128 B swizzle -- byte-for-byte the staging layout of the fp32
+// path.  MN-major [K rows][MN cols]: boxes of 64 (mn) x 64 (k), 128 B swizzle = one 8 KB group of the canonical MN-major UMMA layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute/atom/mma_traits_sm100.hpp), SBO = 1024 B, LBO = 8192 B.
+static int make_tmap_f16(CUtensorMap* tm, const uvc_operand& op, int rows_mn, int K, int nb1, int nb2, int box_rows, const char* name) {
   PFN_tmapEncodeTiled enc = get_encode_fn();
   UVC_REQUIRE(enc != nullptr, UVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
-  UVC_REQUIRE(op.ptr != nullptr && !op.mn_major, UVC_ERR_BAD_ARG, "gemm (fp16 operands): %s must be a non-NULL K-major operand", name);
-  UVC_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0 && op.ld >= K && (op.ld & 7) == 0, UVC_ERR_BAD_SHAPE,
-              "gemm (fp16 operands): %s needs a 16 B-aligned base and ld=%lld >= K, a multiple of 8", name, (long long)op.ld);
-  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)rows, 1, 1};
+  UVC_REQUIRE(op.ptr != nullptr, UVC_ERR_BAD_ARG, "gemm (fp16 operands): %s is NULL", name);
+  UVC_REQUIRE((reinterpret_cast<uintptr_t>(op.ptr) & 15) == 0 && op.ld > 0 && (op.ld & 7) == 0, UVC_ERR_BAD_SHAPE,
+              "gemm (fp16 operands): %s needs a 16 B-aligned base and ld=%lld a positive multiple of 8", name, (long long)op.ld);
+  UVC_REQUIRE((op.bs1 & 7) == 0 && (op.bs2 & 7) == 0 && op.bs1 >= 0 && op.bs2 >= 0, UVC_ERR_BAD_SHAPE, "gemm (fp16 operands): %s batch strides must be non-negative multiples of 8", name);
+  const cuuint64_t cols = op.mn_major ? (cuuint64_t)rows_mn : (cuuint64_t)K;
+  const cuuint64_t rows = op.mn_major ? (cuuint64_t)K : (cuuint64_t)rows_mn;
+  UVC_REQUIRE((long long)cols <= op.ld, UVC_ERR_BAD_SHAPE, "gemm (fp16 operands): %s ld=%lld smaller than its %llu columns", name, (long long)op.ld, (unsigned long long)cols);
+  const cuuint64_t n1 = (op.bs1 != 0) ? (cuuint64_t)nb1 : 1, n2 = (op.bs2 != 0) ? (cuuint64_t)nb2 : 1;
+  cuuint64_t dims[4] = {cols, rows, n1, n2};
   const cuuint64_t row_bytes = (cuuint64_t)op.ld * 2;
-  cuuint64_t strides[3] = {row_bytes, row_bytes * rows, row_bytes * rows};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint64_t strides[3] = {row_bytes, op.bs1 ? (cuuint64_t)op.bs1 * 2 : row_bytes * rows, op.bs2 ? (cuuint64_t)op.bs2 * 2 : row_bytes * rows};
+  cuuint32_t box[4] = {64, op.mn_major ? 64u : (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<float*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -779,7 +819,8 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   UVC_REQUIRE(!(a.flags & UVC_EPI_RESIDUAL) || a.R, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_RESIDUAL without R");
   UVC_REQUIRE(!(a.flags & UVC_EPI_GELU_BWD) || a.aux, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_GELU_BWD without aux");
   UVC_REQUIRE(!(a.flags & UVC_EPI_COLSUM) || a.colsum, UVC_ERR_BAD_ARG, "gemm: UVC_EPI_COLSUM without colsum");
-  const int nkb = (a.K + BK - 1) / BK;
+  const bool f16 = (a.flags & UVC_GEMM_F16) != 0;
+  const int nkb = f16 ? (a.K + 2 * BK - 1) / (2 * BK) : (a.K + BK - 1) / BK;
   int splits = a.splits;
   const bool colsum_simple = !(a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD | UVC_EPI_RESIDUAL));
   if (splits > nkb) splits = nkb > 0 ? nkb : 1;
@@ -789,16 +830,18 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   const int mode = gemm_v2_mode();
   const int pairs = sm_pairs();
   int bn2 = 0;
-  const bool f16 = (a.flags & UVC_GEMM_F16) != 0;
   const bool aux16 = (a.flags & UVC_EPI_AUX_F16) && (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux;
-  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || f16 || a.D16 || !a.D || aux16;   // features only the CTA-pair kernel has
-  UVC_REQUIRE(!f16 || (!a.A.mn_major && !a.B.mn_major && a.splits == 1), UVC_ERR_BAD_ARG, "gemm: fp16 operands must be K-major, without split-K");
+  // fp16 operands: K-major unbatched problems run on the CTA-pair kernel; MN-major operands (the weight gradients: both operands are read
+  // transposed), split-K and batched problems on the 128 x 128 kernel.
+  const bool f16_v1 = f16 && (a.A.mn_major || a.B.mn_major || a.splits > 1 || a.nb1 != 1 || a.nb2 != 1);
+  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || (f16 && !f16_v1) || a.D16 || !a.D || aux16;   // features only the CTA-pair kernel has
+  UVC_REQUIRE(!(f16_v1 && need_v2), UVC_ERR_BAD_ARG, "gemm: fp16 MN-major / split-K / batched operands cannot be combined with D16, fp16 aux or COLSUM under a GELU / residual epilogue");
   UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: fp16 operands / D16 / UVC_EPI_COLSUM with GELU or residual epilogues need unbatched, 16 B-aligned operands and N % 4 == 0");
   // Split-K weight gradients (few output tiles, K = all tokens) stay on the 128 x 128 kernel: its tiles fit the C-multiple weight shapes without
   // padding and tiles x splits fills one wave of 2 CTAs per SM; measured on the four DeiT-Small shapes it is 0-30 % faster than the CTA-pair
   // kernel there (qkv_w 47 vs 69 us, fc1_w 55 vs 61 us; tests/bringup/wgrad_perf.py).
   const bool splitk_wgrad = a.splits > 1 && (a.flags & UVC_EPI_ATOMIC) && mode != 2 && !need_v2;
-  if ((mode > 0 || need_v2) && v2_legal(a) && !splitk_wgrad && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
+  if ((mode > 0 || need_v2) && v2_legal(a) && !splitk_wgrad && !f16_v1 && (mode == 2 || need_v2 || (a.M >= 512 && a.N >= 128))) {
     // split-K (caller allows it by passing splits > 1 with UVC_EPI_ATOMIC): the persistent kernel wants ~2 units per SM pair
     if (splits > 1 && !getenv("UVC_GEMM_V2_KEEP_SPLITS")) {
       const int bn0 = gemm_v2_force_bn() ? gemm_v2_force_bn() : 128;
@@ -816,8 +859,8 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.aux16 = aux16 ? 1 : 0;
   kp.D16 = a.D16; kp.ldd16 = a.ldd16;
   if (f16) {
-    if ((rc = make_tmap_f16(&kp.tmA, a.A, a.M, a.K, BM, "A"))) return rc;
-    if ((rc = make_tmap_f16(&kp.tmB, a.B, a.N, a.K, bn2 / 2, "B"))) return rc;
+    if ((rc = make_tmap_f16(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A"))) return rc;
+    if ((rc = make_tmap_f16(&kp.tmB, a.B, a.N, a.K, a.nb1, a.nb2, bn2 ? bn2 / 2 : BN, "B"))) return rc;
   } else {
     if (bn2 && a.A.mn_major && make_tmap_grouped(&kp.tmA, a.A, a.M, a.K, 4) == 0) kp.a_grp = 1;
     else if ((rc = make_tmap(&kp.tmA, a.A, a.M, a.K, a.nb1, a.nb2, BM, "A"))) return rc;
@@ -830,7 +873,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.aux = (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) ? a.aux : nullptr; kp.ldaux = a.ldaux; kp.aux_bs1 = a.aux_bs1; kp.aux_bs2 = a.aux_bs2;
   kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev;
   kp.colsum = (a.flags & UVC_EPI_COLSUM) ? a.colsum : nullptr;
-  kp.alpha = a.alpha; kp.beta = a.beta;
+  kp.alpha = a.alpha; kp.beta = a.beta; kp.colsum_scale = (a.colsum_scale != 0.0f) ? a.colsum_scale : 1.0f;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.nb1 = a.nb1; kp.nb2 = a.nb2; kp.splits = splits; kp.flags = a.flags;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("UVC_GEMM_DBG"); dbg = e ? atoi(e) : 0; } kp.flags |= dbg << 29; }   // bring-up experiments only
   kp.a_mn = a.A.mn_major ? 1 : 0; kp.b_mn = a.B.mn_major ? 1 : 0;
@@ -856,7 +899,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   UVC_REQUIRE(gz <= 65535 && gy <= 65535, UVC_ERR_BAD_SHAPE, "gemm: grid too large (m tiles %lld, batch*splits %lld)", gy, gz);
   dim3 grid((a.N + BN - 1) / BN, (unsigned)gy, (unsigned)gz);
   const bool prof = prof_enabled();
-  if (prof) prof_begin(st, 2.0 * a.M * a.N * (double)a.K * a.nb1 * a.nb2);
+  if (prof) prof_begin(st, 2.0 * a.M * a.N * (double)a.K * a.nb1 * a.nb2, f16 ? 4 : 1);
   rc = launch<BN, 3>(kp, grid, st);
   if (prof) prof_end(st);
   return rc;

@@ -10,11 +10,16 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st);
 int encode_tmap_4d(CUtensorMap* tm, const float* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
                    const unsigned int box[4], bool atom32, const char* name);
 
+int encode_tmap_4d_f16(CUtensorMap* tm, const void* base, const unsigned long long dims[4], const unsigned long long strides_bytes[3],
+                       const unsigned int box[4], const char* name);
+
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
-                  float* rstd, int M, int C, cudaStream_t st, int round_out = 0);
+                  float* rstd, int M, int C, cudaStream_t st, int round_out = 0, void* y16 = nullptr);   // y16: write fp16 there instead of fp32 to y
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st, float* cs_r1 = nullptr, float* cs_out = nullptr);   // cs_*: fused column sums of r1 / of dx (bias gradients)
+                  cudaStream_t st, float* cs_r1 = nullptr, float* cs_out = nullptr,    // cs_*: fused column sums of r1 / of dx (bias gradients)
+                  const void* dy16 = nullptr, float dy_scale = 1.0f,                    // dy16: dy as fp16 (row stride lddy), multiplied by dy_scale on load
+                  void* dx16 = nullptr, float out_scale = 1.0f);                        // dx16: also write fp16(out_scale * dx), row stride lddx
 int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int round_out = 0);
 int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int round_out = 0);
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);
@@ -23,11 +28,14 @@ int blend_dots(const float* g, const float* t, const float* x, float* dots, long
 int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st, int round_out = 0);
 constexpr int kMaxRoundSegs = 96;
 int round_tf32_segs(const float* const* src, float* const* dst, const long long* n, int nseg, cudaStream_t st);
+// fp32 -> fp16 copies (dst, [rows, cols]) and optional transposed copies (dstT, [cols, rows]) of up to nseg weight matrices
+int cvt_f16_segs(const float* const* src, void* const* dst, void* const* dstT, const int* rows, const int* cols, int nseg, cudaStream_t st);
 int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
                     cudaStream_t st);
 int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,
                         float* dpos, float* dcls, int B, int np, int C, cudaStream_t st);
 int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st);
+int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st);   // dst16 = fp16(s * src)
 
 int attn_ldp(int N);
 int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P = true, float* lse = nullptr);
@@ -36,6 +44,14 @@ int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, co
                         cudaStream_t st, float* dqkv_bias = nullptr);   // dqkv_bias [3*H*64]: += column sums of dqkv (the qkv bias gradient)
 int attention_bwd(const float* qkv, const float* P, const float* dctx, float* dP, float* dqkv, int B, int H, int N, int d, float scale,
                   cudaStream_t st);
+
+// fp16-operand attention (attention_f16.cu): qkv16 [B*N, 3*H*64] fp16 in, ctx16 [B*N, H*64] fp16 out, lse [B,H,N] fp32 (may be NULL)
+bool attn_f16_ok(int N, int d);
+int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, int N, float scale, cudaStream_t st);
+// dqkv16 [B*N, 3*H*64] fp16 from dctx16 (fp16, may carry a loss scale: everything downstream is linear in it); Dv: [B,H,N] fp32 scratch;
+// dqkv_bias (optional, fp32 [3*H*64]) += db_scale * column sums of dqkv
+int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
+                      float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f);
 
 // ---- helpers to describe GEMM operands tersely
 inline uvc_operand op_k(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 0, 0}; }
@@ -48,10 +64,10 @@ inline uvc_gemm_args gemm_args(int M, int N, int K, uvc_operand A, uvc_operand B
   return a;
 }
 // split-K factor for a weight-gradient GEMM (few output tiles, very long K): fill ~2 waves of 148 SMs
-inline int wgrad_splits(int M, int N, int K) {
+inline int wgrad_splits(int M, int N, int K, int bk = 32) {
   const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
   int s = (2 * 148) / tiles;            // floor: tiles * s CTAs must fit ONE wave of 2 CTAs per SM (a 297th CTA costs a whole second wave)
-  const int nkb = (K + 31) / 32;
+  const int nkb = (K + bk - 1) / bk;
   if (s > nkb / 4) s = nkb / 4;
   if (s < 1) s = 1;
   return s;

@@ -6,6 +6,7 @@
 // Reference spans: models/model_distilled.py:199,204,288,507 (LayerNorm), :179-181 (softmax),
 // :433-471 (patch embed, gates, cls/pos), :477-503 (block gate blend).
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "kernels.h"
 
 namespace uvc {
@@ -25,7 +26,8 @@ constexpr int kMaxVec = 8;   // float4 per lane -> C <= 1024
 
 // ------------------------------------------------------------------------------------------ LayerNorm fwd
 // one warp per row; two-pass moments in registers (mean, then centred variance) like ATen's RowwiseMoments.
-template <int NV>
+// Y16: the output is written as fp16 (the operand storage format of the kind::f16 GEMM that consumes it) instead of fp32
+template <int NV, bool Y16>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float* __restrict__ y, long long ldy,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C, int rnd) {
@@ -63,8 +65,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (rnd) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      yr[c] = o;
+      if (Y16) {
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(y) + (long long)row * ldy)[c] = pack_half4(o.x, o.y, o.z, o.w);
+      } else {
+        if (rnd) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        yr[c] = o;
+      }
     }
   }
   if (lane == 0) {
@@ -78,13 +84,16 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (register partials per lane -> smem -> atomics)
 // Optional fused bias gradients of the neighbouring Linears (they are column sums of tensors this kernel touches anyway):
 //   cs_r1[col] += sum_rows (r1 + s2 * r2)[row, col]      cs_out[col] += sum_rows dx[row, col]
-template <int NV, bool CS>
-__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+// DY16: dy holds fp16 values that carry the loss scale (dy_scale = 1 / scale takes it out on load).  dx16 (optional): an fp16 copy of
+// out_scale * dx for the GEMMs that consume the stream gradient as an operand; the fp32 dx stays unscaled.
+template <int NV, bool CS, bool DY16>
+__global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ r1, const float* __restrict__ r2,
                                                             const float* __restrict__ s2_dev, float* __restrict__ dx, long long lddx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cs_r1,
-                                                            float* __restrict__ cs_out, int M, int C, int rows_per_block) {
+                                                            float* __restrict__ cs_out, int M, int C, int rows_per_block,
+                                                            float dy_scale, __half* __restrict__ dx16, float out_scale) {
   __shared__ float red[4][8][32 * 4 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int nv = C >> 2;
@@ -101,6 +110,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const float* __re
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   for (int row = row0 + warp; row < row1; row += nwarps) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * lddy);
+    const uint2* dyr16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dy) + (long long)row * lddy);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
     const float4* r1r = r1 ? reinterpret_cast<const float4*>(r1 + (long long)row * lddx) : nullptr;
     const float4* r2r = r2 ? reinterpret_cast<const float4*>(r2 + (long long)row * lddx) : nullptr;
@@ -112,7 +122,15 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const float* __re
       const int c = lane + i * 32;
       res[i] = make_float4(0, 0, 0, 0);
       if (c < nv) {
-        const float4 d = dyr[c], xv = xr[c], gm = __ldg(g4 + c);
+        float4 d;
+        if (DY16) {
+          const uint2 u = dyr16[c];
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+          d = make_float4(lo.x * dy_scale, lo.y * dy_scale, hi.x * dy_scale, hi.y * dy_scale);
+        } else {
+          d = dyr[c];
+        }
+        const float4 xv = xr[c], gm = __ldg(g4 + c);
         if (r1r) res[i] = r1r[c];
         if (r2r) { const float4 a = r2r[c]; res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w; }
         if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
@@ -135,6 +153,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const float* __re
         o.z = res[i].z + rs * (gg[i].z - mg - xh[i].z * mgx); o.w = res[i].w + rs * (gg[i].w - mg - xh[i].w * mgx);
         if (CS) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
         dxr[c] = o;
+        if (dx16) reinterpret_cast<uint2*>(dx16 + (long long)row * lddx)[c] = pack_half4(o.x * out_scale, o.y * out_scale, o.z * out_scale, o.w * out_scale);
       }
     }
   }
@@ -398,6 +417,13 @@ __global__ void scale_add_kernel(float4* __restrict__ y, const float4* __restric
   }
 }
 
+__global__ void scale_to_f16_kernel(uint2* __restrict__ dst, const float4* __restrict__ src, float s, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = src[i];
+    dst[i] = pack_half4(a.x * s, a.y * s, a.z * s, a.w * s);
+  }
+}
+
 // dst = rna_tf32(src) over up to kMaxSeg tensors in one launch (all GEMM weights of the model)
 struct RoundSegs { const float* src[kMaxRoundSegs]; float* dst[kMaxRoundSegs]; long long n4[kMaxRoundSegs]; int nseg; };
 __global__ void __launch_bounds__(256) round_segs_kernel(const __grid_constant__ RoundSegs segs) {
@@ -412,6 +438,43 @@ __global__ void __launch_bounds__(256) round_segs_kernel(const __grid_constant__
   }
 }
 
+// fp32 weights -> fp16 operand copies, all GEMM weights of the model in one launch: dst [rows, cols] (K-major B operand of the forward
+// GEMM) and, when dstT != NULL, the transpose [cols, rows] (K-major B operand of the data-gradient GEMM, so no MN-major 16-bit path is
+// needed there).  32 x 32 tiles through shared memory; both stores are coalesced.
+struct CvtSegs { const float* src[kMaxRoundSegs]; __half* dst[kMaxRoundSegs]; __half* dstT[kMaxRoundSegs]; int rows[kMaxRoundSegs]; int cols[kMaxRoundSegs]; int nseg; };
+__global__ void __launch_bounds__(256) cvt_f16_segs_kernel(const __grid_constant__ CvtSegs segs) {
+  __shared__ float tile[32][33];
+  const int seg = blockIdx.y;
+  const float* __restrict__ src = segs.src[seg];
+  __half* __restrict__ dst = segs.dst[seg];
+  __half* __restrict__ dstT = segs.dstT[seg];
+  const int rows = segs.rows[seg], cols = segs.cols[seg];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+  for (int t = blockIdx.x; t < tc * tr; t += gridDim.x) {
+    const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + ty + i * 8, c = c0 + tx;
+      float v = 0.f;
+      if (r < rows && c < cols) {
+        v = src[(long long)r * cols + c];
+        if (dst) dst[(long long)r * cols + c] = __float2half_rn(v);
+      }
+      tile[ty + i * 8][tx] = v;
+    }
+    if (dstT) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8, r = r0 + tx;
+        if (r < rows && c < cols) dstT[(long long)c * rows + r] = __float2half_rn(tile[tx][ty + i * 8]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 static inline int grid_for(long long n, int threads, int max_blocks = 148 * 8) {
   long long b = (n + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
@@ -420,31 +483,39 @@ static inline int grid_for(long long n, int threads, int max_blocks = 148 * 8) {
 }
 
 int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y, long long ldy, float* mean,
-                  float* rstd, int M, int C, cudaStream_t st, int rnd) {
+                  float* rstd, int M, int C, cudaStream_t st, int rnd, void* y16) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kMaxVec * 128);
   UVC_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm: row strides must be multiples of 4");
   if (M <= 0) return UVC_OK;
-  UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd)));
+  if (y16) UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV, true><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<float*>(y16), ldy, mean, rstd, M, C, 0)));
+  else UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV, false><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd)));
   return check_launch("layernorm_fwd");
 }
 
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st, float* cs_r1, float* cs_out) {
+                  cudaStream_t st, float* cs_r1, float* cs_out, const void* dy16, float dy_scale, void* dx16, float out_scale) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
   UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
   UVC_REQUIRE(!cs_r1 || r1 || r2, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without a residual input");
   if (M <= 0) return UVC_OK;
   // one wave of 3 resident blocks per SM (the kernel is compiled for 80 registers): each warp has one row (4 x 1.5 KB) in flight, so the
   // bytes in flight per SM, not the column reductions, set the rate (measured: no gain from dropping the atomics, +8..15 % from 16 -> 24 warps)
-  int blocks = 148 * 3;
+  int blocks = 148 * (C <= 384 ? 3 : 2);           // resident blocks per SM the kernel is compiled for (wider rows need more registers)
   int rpb = (M + blocks - 1) / blocks;
   if (rpb < 8) rpb = 8;
   blocks = (M + rpb - 1) / rpb;
-  if (cs_r1 || cs_out)
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb)));
+  __half* h16 = static_cast<__half*>(dx16);
+  if (dy16) {
+    const float* d16 = static_cast<const float*>(dy16);
+    if (cs_r1 || cs_out)
+      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale)));
+    else
+      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale)));
+  } else if (cs_r1 || cs_out)
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale)));
   else
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb)));
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale)));
   return check_launch("layernorm_bwd");
 }
 
@@ -532,6 +603,29 @@ int round_tf32_segs(const float* const* src, float* const* dst, const long long*
   }
   return UVC_OK;
 }
+int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st) {
+  UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "scale_to_f16: element count must be a multiple of 4");
+  scale_to_f16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(static_cast<uint2*>(dst16), reinterpret_cast<const float4*>(src), s, n / 4);
+  return check_launch("scale_to_f16");
+}
+int cvt_f16_segs(const float* const* src, void* const* dst, void* const* dstT, const int* rows, const int* cols, int nseg, cudaStream_t st) {
+  for (int base = 0; base < nseg; base += kMaxRoundSegs) {
+    CvtSegs segs;
+    segs.nseg = (nseg - base < kMaxRoundSegs) ? nseg - base : kMaxRoundSegs;
+    long long mx = 0;
+    for (int i = 0; i < segs.nseg; ++i) {
+      segs.src[i] = src[base + i]; segs.dst[i] = static_cast<__half*>(dst[base + i]); segs.dstT[i] = dstT ? static_cast<__half*>(dstT[base + i]) : nullptr;
+      segs.rows[i] = rows[base + i]; segs.cols[i] = cols[base + i];
+      const long long tiles = (long long)((rows[base + i] + 31) / 32) * ((cols[base + i] + 31) / 32);
+      if (tiles > mx) mx = tiles;
+    }
+    if (mx == 0) continue;
+    cvt_f16_segs_kernel<<<dim3((unsigned)(mx < 64 ? mx : 64), segs.nseg), 256, 0, st>>>(segs);
+    int rc = check_launch("cvt_f16_segs");
+    if (rc) return rc;
+  }
+  return UVC_OK;
+}
 int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st) {
   UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "scale_add: element count must be a multiple of 4");
   scale_add_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), s_dev, s, n / 4);
@@ -561,6 +655,23 @@ int uvc_layernorm_bwd_cs(const float* dy, int64_t lddy, const float* x, int64_t 
   UVC_REQUIRE(dy && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_cs: NULL pointer");
   UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_cs: dgamma and dbeta must both be given or both NULL");
   return uvc::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST, cs_r1, cs_out);
+}
+int uvc_layernorm_fwd_f16(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y16, int64_t ldy, float* mean,
+                          float* rstd, int32_t M, int32_t C, void* stream) {
+  UVC_REQUIRE(x && gamma && beta && y16, UVC_ERR_BAD_ARG, "uvc_layernorm_fwd_f16: NULL pointer");
+  return uvc::layernorm_fwd(x, ldx, gamma, beta, eps, nullptr, ldy, mean, rstd, M, C, UVC_ST, 0, y16);
+}
+int uvc_layernorm_bwd_f16(const void* dy16, int64_t lddy, float dy_scale, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                          const float* gamma, const float* r1, const float* r2, const float* s2_dev, float* dx, void* dx16, float dx16_scale,
+                          int64_t lddx, float* dgamma, float* dbeta, float* cs_r1, float* cs_out, int32_t M, int32_t C, void* stream) {
+  UVC_REQUIRE(dy16 && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_f16: NULL pointer");
+  UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_f16: dgamma and dbeta must both be given or both NULL");
+  return uvc::layernorm_bwd(nullptr, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST, cs_r1, cs_out, dy16, dy_scale,
+                            dx16, dx16_scale);
+}
+int uvc_cvt_f16(const float* src, void* dst16, void* dstT16, int32_t rows, int32_t cols, void* stream) {
+  UVC_REQUIRE(src && (dst16 || dstT16), UVC_ERR_BAD_ARG, "uvc_cvt_f16: NULL pointer");
+  return uvc::cvt_f16_segs(&src, &dst16, dstT16 ? &dstT16 : nullptr, &rows, &cols, 1, UVC_ST);
 }
 int uvc_softmax_fwd(float* S, int64_t ld, int64_t rows, int32_t n, int32_t round_tf32, void* stream) {
   UVC_REQUIRE(S, UVC_ERR_BAD_ARG, "uvc_softmax_fwd: NULL pointer");

@@ -10,6 +10,7 @@
 // allocator (same carve in forward and backward).  HBM layout: every activation is a row-major
 // [B*ntok, width] fp32 matrix, rows 16-byte aligned; attention probabilities are [B, H, ntok, ldp].
 #include "kernels.h"
+#include <cuda_fp16.h>
 
 namespace uvc {
 
@@ -42,7 +43,7 @@ struct Ws {
   float *cols, *pe, *tok, *mean_f, *rstd_f, *cls_ln, *accum;
   LayerWs layer[UVC_MAX_DEPTH];
   // scratch
-  float *g_a, *g_b, *g_c, *dh, *dqkv, *dP, *Dv, *dcls_ln, *dpe;
+  float *g_a, *g_b, *g_c, *dh, *dqkv, *dP, *Dv, *dcls_ln, *dpe, *dlog_pad;
   size_t bytes;
 };
 
@@ -65,6 +66,9 @@ int check_dims(const uvc_vit_dims& v, Dims* o) {
   o->Kp = v.in_chans * v.patch * v.patch;
   o->M = (long long)v.B * o->ntok;
   UVC_REQUIRE(o->M < (1ll << 31), UVC_ERR_BAD_SHAPE, "vit: too many rows");
+  if (v.operand_f16)
+    UVC_REQUIRE(o->d == 64 && attn_f16_ok(o->ntok, o->d) && (v.C & 7) == 0 && (v.Fh & 7) == 0, UVC_ERR_BAD_SHAPE,
+                "vit: fp16 operand storage needs head dim 64, <= 208 tokens, C and Fh multiples of 8 (got d=%d, tokens=%d, C=%d, Fh=%d)", o->d, o->ntok, v.C, v.Fh);
   return UVC_OK;
 }
 
@@ -96,6 +100,7 @@ void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
     w->g_a = b.f(M * C); w->g_b = b.f(M * C); w->g_c = b.f(M * C);
     w->dh = b.f(M * Fh); w->dqkv = b.f(M * 3 * C); w->dP = psz ? b.f(psz) : nullptr; w->Dv = lsz ? b.f(lsz) : nullptr;
     w->dcls_ln = b.f((size_t)D.B * C); w->dpe = b.f((size_t)D.B * D.np * C);
+    w->dlog_pad = b.f((size_t)D.B * ((D.NC + 3) / 4 * 4));
   } else {
     // inference: every layer reuses one set of buffers; the residual stream ping-pongs between t and xout
     LayerWs L0;
@@ -105,7 +110,7 @@ void carve(const Dims& D, bool save, void* base, size_t cap, Ws* w) {
     L0.t = b.f(M * C); L0.xout = b.f(M * C);
     float* ping = L0.xout; float* pong = b.f(M * C);
     for (int l = 0; l < D.L; ++l) { w->layer[l] = L0; w->layer[l].xout = (l & 1) ? pong : ping; }
-    w->g_a = w->g_b = w->g_c = w->dh = w->dqkv = w->dP = w->Dv = w->dcls_ln = w->dpe = nullptr;
+    w->g_a = w->g_b = w->g_c = w->dh = w->dqkv = w->dP = w->Dv = w->dcls_ln = w->dpe = w->dlog_pad = nullptr;
   }
   w->bytes = b.off;
 }
@@ -160,6 +165,17 @@ int round_weights(const uvc_vit_tensors& p, const Dims& D, const WeightsR& wr, c
   return round_tf32_segs(src, dst, n, k, st);
 }
 
+// TMA operands need 16-byte row pitches: a class count that is not a multiple of 4 (cifar10: 10) gets a zero-padded copy of dlogits
+int pad_dlogits(const float** dlog, long long* ld, float* pad, int B, int NC, cudaStream_t st) {
+  if ((NC & 3) == 0 && (reinterpret_cast<uintptr_t>(*dlog) & 15) == 0) return UVC_OK;
+  const int NCp = (NC + 3) / 4 * 4;
+  cudaError_t e = cudaMemsetAsync(pad, 0, (size_t)B * NCp * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(pad, (size_t)NCp * sizeof(float), *dlog, (size_t)NC * sizeof(float), (size_t)NC * sizeof(float), B, cudaMemcpyDeviceToDevice, st);
+  UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: padding dlogits: %s", cudaGetErrorString(e));
+  *dlog = pad; *ld = NCp;
+  return UVC_OK;
+}
+
 int check_tensors(const uvc_vit_tensors& w, int L, const char* what, bool need_patch) {
   UVC_REQUIRE((!need_patch || (w.patch_w && w.patch_b)) && w.cls_token && w.pos_embed && w.norm_w && w.norm_b && w.head_w && w.head_b && w.blocks, UVC_ERR_BAD_ARG,
               "vit: %s has a NULL tensor", what);
@@ -173,17 +189,24 @@ int check_tensors(const uvc_vit_tensors& w, int L, const char* what, bool need_p
 
 }  // namespace
 
+unsigned long long vit_workspace_bytes_f16(const Dims& D, bool save);
+
 unsigned long long vit_workspace_bytes(const uvc_vit_dims& dims, int save) {
   Dims D;
   if (check_dims(dims, &D)) return 0;
+  if (dims.operand_f16) return vit_workspace_bytes_f16(D, save != 0);
   Ws w;
   carve(D, save != 0, nullptr, 0, &w);
   return w.bytes;
 }
 
+int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t st);
+int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t st);
+
 int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
+  if (a.dims.operand_f16) return vit_forward_f16(a, D, st);
   UVC_TRY(check_tensors(a.w, D.L, "w", a.pe_in == nullptr));
   UVC_REQUIRE((a.x || a.pe_in) && a.logits && a.workspace, UVC_ERR_BAD_ARG, "vit_forward: NULL x / logits / workspace");
   const bool save = a.save_for_backward != 0;
@@ -249,6 +272,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
 int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
+  if (a.dims.operand_f16) return vit_backward_f16(a, D, st);
   UVC_TRY(check_tensors(a.w, D.L, "w", a.d_pe == nullptr));
   UVC_TRY(check_tensors(a.g, D.L, "g", a.d_pe == nullptr));
   UVC_REQUIRE(a.dlogits && a.workspace, UVC_ERR_BAD_ARG, "vit_backward: NULL dlogits / workspace");
@@ -268,8 +292,10 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
   const float* xf = a.enable_jumping ? w.accum : xin[D.L];
 
   // head: dW += dlogits^T cls_ln ; db += colsum ; dcls_ln = dlogits W
-  UVC_TRY(linear_wgrad(a.dlogits, D.NC, w.cls_ln, C, a.g.head_w, a.g.head_b, D.B, D.NC, C, st));
-  UVC_TRY(linear_dgrad(a.dlogits, D.NC, w.wr.head_w, w.dcls_ln, C, D.B, D.NC, C, st));
+  const float* dlog = a.dlogits; long long ldl = D.NC;
+  UVC_TRY(pad_dlogits(&dlog, &ldl, w.dlog_pad, D.B, D.NC, st));
+  UVC_TRY(linear_wgrad(dlog, ldl, w.cls_ln, C, a.g.head_w, a.g.head_b, D.B, D.NC, C, st));
+  UVC_TRY(linear_dgrad(dlog, ldl, w.wr.head_w, w.dcls_ln, C, D.B, D.NC, C, st));
   // final LN backward on the cls rows; every other row of the stream gradient is zero
   float* g = w.g_a;         // gradient wrt the current residual stream
   float* g_jump = nullptr;  // with jumping connections the final-norm gradient reaches every block output
@@ -328,6 +354,285 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
   }
 
   // token assembly + patch embed
+  const int rows = D.B * D.np;
+  float* dpe = a.d_pe ? a.d_pe : w.dpe;
+  UVC_TRY(assemble_tokens_bwd(g, w.pe, a.patch_scale, a.token_mask, dpe, a.patch_scale ? a.d_patch_scale : nullptr,
+                              a.token_mask ? a.d_token_mask : nullptr, a.g.pos_embed, a.g.cls_token, D.B, D.np, C, st));
+  if (!a.d_pe) UVC_TRY(linear_wgrad(w.dpe, C, w.cols, D.Kp, a.g.patch_w, a.g.patch_b, rows, C, D.Kp, st));
+  return UVC_OK;
+}
+
+// ====================================================================================================================
+// 16-bit operand storage (uvc_vit_dims.operand_f16): the same model, but every tensor that only feeds GEMMs lives in HBM as fp16 -- the 10
+// mantissa bits the TF32 path keeps, at half the bytes and twice the tensor-core rate (tcgen05.mma kind::f16, fp32 accumulation).
+//   forward : LayerNorm writes fp16; qkv, gelu(fc1) and the attention context are written ONLY as fp16 by their producers; the residual
+//             stream (tok, x1, block outputs), LayerNorm statistics, softmax, logits and the loss stay fp32.
+//   backward: the fp32 stream gradient g is carried unscaled; its GEMM-operand copy is g16 = fp16(S g) with the loss scale S (a power of two),
+//             so gradients of 1e-6 stay normal fp16 numbers.  Everything downstream of g16 is linear in it: the fp16 intermediates (dh, dln,
+//             dctx, dqkv) carry S, and S is taken back out where fp32 results are produced -- alpha = 1/S in the weight-gradient GEMMs (exact,
+//             a power of two), 1/S on the fused bias-gradient column sums, and on load in the LayerNorm backward.
+//   weights : converted once per forward to fp16 [out, in] (forward B operand) and, for training, fp16 [in, out] (data-gradient B operand, so
+//             only the weight-gradient GEMMs read 16-bit operands MN-major).
+// The patch-embed and head GEMMs (1.5 % of the FLOPs, K = 768 image pixels / B rows) stay on the TF32 path.
+// ====================================================================================================================
+namespace {
+
+typedef __half h16;
+
+struct Layer16 {
+  float *mean1, *rstd1, *mean2, *rstd2, *lse, *x1, *t, *xout;
+  h16 *ln1, *qkv, *ctx, *ln2, *hpre, *h;
+};
+struct Ws16 {
+  float *patch_w, *head_w;
+  h16 *qkv_w[UVC_MAX_DEPTH], *proj_w[UVC_MAX_DEPTH], *fc1_w[UVC_MAX_DEPTH], *fc2_w[UVC_MAX_DEPTH];
+  h16 *qkv_wT[UVC_MAX_DEPTH], *proj_wT[UVC_MAX_DEPTH], *fc1_wT[UVC_MAX_DEPTH], *fc2_wT[UVC_MAX_DEPTH];
+  float *cols, *pe, *tok, *mean_f, *rstd_f, *cls_ln, *accum;
+  Layer16 layer[UVC_MAX_DEPTH];
+  float *g_a, *g_b, *g_c, *Dv, *dcls_ln, *dpe, *dlog_pad;
+  h16 *g16, *dx1_16, *dln16, *dctx16, *dh16, *dqkv16;
+  size_t bytes;
+};
+
+struct Bump16 : Bump {
+  using Bump::Bump;
+  h16* h(size_t n) { return reinterpret_cast<h16*>(f((n + 1) / 2)); }
+};
+
+void carve16(const Dims& D, bool save, void* base, size_t cap, Ws16* w) {
+  Bump16 b(base, cap);
+  const size_t M = (size_t)D.M, C = D.C, Fh = D.Fh;
+  const size_t lsz = (size_t)D.B * D.H * D.ntok;
+  w->patch_w = b.f(C * (size_t)D.Kp); w->head_w = b.f((size_t)D.NC * C);
+  for (int l = 0; l < D.L; ++l) {
+    w->qkv_w[l] = b.h(3 * C * C); w->proj_w[l] = b.h(C * C); w->fc1_w[l] = b.h(Fh * C); w->fc2_w[l] = b.h(C * Fh);
+    if (save) { w->qkv_wT[l] = b.h(3 * C * C); w->proj_wT[l] = b.h(C * C); w->fc1_wT[l] = b.h(Fh * C); w->fc2_wT[l] = b.h(C * Fh); }
+    else w->qkv_wT[l] = w->proj_wT[l] = w->fc1_wT[l] = w->fc2_wT[l] = nullptr;
+  }
+  w->cols = b.f((size_t)D.B * D.np * D.Kp);
+  w->pe = b.f((size_t)D.B * D.np * C);
+  w->tok = b.f(M * C);
+  w->mean_f = b.f(D.B); w->rstd_f = b.f(D.B);
+  w->cls_ln = b.f((size_t)D.B * C);
+  w->accum = b.f(M * C);
+  if (save) {
+    for (int l = 0; l < D.L; ++l) {
+      Layer16& L = w->layer[l];
+      L.mean1 = b.f(M); L.rstd1 = b.f(M); L.mean2 = b.f(M); L.rstd2 = b.f(M); L.lse = b.f(lsz);
+      L.ln1 = b.h(M * C); L.qkv = b.h(M * 3 * C); L.ctx = b.h(M * C); L.x1 = b.f(M * C);
+      L.ln2 = b.h(M * C); L.hpre = b.h(M * Fh); L.h = b.h(M * Fh);
+      L.t = b.f(M * C); L.xout = b.f(M * C);
+    }
+    w->g_a = b.f(M * C); w->g_b = b.f(M * C); w->g_c = b.f(M * C);
+    w->Dv = b.f(lsz); w->dcls_ln = b.f((size_t)D.B * C); w->dpe = b.f((size_t)D.B * D.np * C);
+    w->dlog_pad = b.f((size_t)D.B * ((D.NC + 3) / 4 * 4));
+    w->g16 = b.h(M * C); w->dx1_16 = b.h(M * C); w->dln16 = b.h(M * C); w->dctx16 = b.h(M * C); w->dh16 = b.h(M * Fh); w->dqkv16 = b.h(M * 3 * C);
+  } else {
+    Layer16 L0;
+    L0.mean1 = L0.rstd1 = L0.mean2 = L0.rstd2 = L0.lse = nullptr;
+    L0.ln1 = b.h(M * C); L0.qkv = b.h(M * 3 * C); L0.ctx = b.h(M * C); L0.x1 = b.f(M * C); L0.ln2 = L0.ln1; L0.hpre = nullptr; L0.h = b.h(M * Fh);
+    L0.t = b.f(M * C); L0.xout = b.f(M * C);
+    float* ping = L0.xout; float* pong = b.f(M * C);
+    for (int l = 0; l < D.L; ++l) { w->layer[l] = L0; w->layer[l].xout = (l & 1) ? pong : ping; }
+    w->g_a = w->g_b = w->g_c = w->Dv = w->dcls_ln = w->dpe = w->dlog_pad = nullptr;
+    w->g16 = w->dx1_16 = w->dln16 = w->dctx16 = w->dh16 = w->dqkv16 = nullptr;
+  }
+  w->bytes = b.off;
+}
+
+inline uvc_operand op16_k(const h16* p, long long ld) { return uvc_operand{reinterpret_cast<const float*>(p), ld, 0, 0, 0, 0}; }
+inline uvc_operand op16_mn(const h16* p, long long ld) { return uvc_operand{reinterpret_cast<const float*>(p), ld, 0, 0, 1, 0}; }
+
+// Y = epilogue(X16 W16^T): fp32 output D (with optional fp32 residual R) and / or fp16 output D16
+int linear16(const h16* X, long long ldx, const h16* W, const float* bias, float* Dout, void* D16, long long ldd, int M, int N, int K, cudaStream_t st,
+             int extra_flags = 0, void* aux16 = nullptr, const float* R = nullptr, long long ldr = 0, const float* alpha_dev = nullptr,
+             float* colsum_out = nullptr, float colsum_scale = 1.0f) {
+  uvc_gemm_args a = gemm_args(M, N, K, op16_k(X, ldx), op16_k(W, K), Dout, ldd);
+  a.flags = extra_flags | UVC_GEMM_F16;
+  a.D16 = D16; a.ldd16 = ldd;
+  a.alpha_dev = alpha_dev;
+  if (bias) { a.bias = bias; a.flags |= UVC_EPI_BIAS; }
+  if (aux16) { a.aux = static_cast<float*>(aux16); a.ldaux = ldd; a.flags |= UVC_EPI_AUX_F16; }
+  if (R) { a.R = R; a.ldr = ldr; a.flags |= UVC_EPI_RESIDUAL; }
+  if (colsum_out) { a.colsum = colsum_out; a.colsum_scale = colsum_scale; a.flags |= UVC_EPI_COLSUM; }
+  return gemm_tf32(a, st);
+}
+// dW[N,K] += alpha * dY16[M,N]^T X16[M,K]   (both operands MN-major fp16, split-K with fp32 atomics)
+int linear_wgrad16(const h16* dY, long long lddy, const h16* X, long long ldx, float* dW, int M, int N, int K, float alpha, cudaStream_t st,
+                   const float* scale_dev = nullptr) {
+  uvc_gemm_args a = gemm_args(N, K, M, op16_mn(dY, lddy), op16_mn(X, ldx), dW, K);
+  a.flags = UVC_EPI_ATOMIC | UVC_GEMM_F16;
+  a.alpha = alpha;
+  a.alpha_dev = scale_dev;
+  a.splits = wgrad_splits(N, K, M, 64);
+  return gemm_tf32(a, st);
+}
+
+int convert_weights16(const uvc_vit_tensors& p, const Dims& D, const Ws16& w, bool save, cudaStream_t st) {
+  const float* src[4 * UVC_MAX_DEPTH]; void* dst[4 * UVC_MAX_DEPTH]; void* dstT[4 * UVC_MAX_DEPTH]; int rows[4 * UVC_MAX_DEPTH], cols[4 * UVC_MAX_DEPTH];
+  int k = 0;
+  for (int l = 0; l < D.L; ++l) {
+    const uvc_block_tensors& b = p.blocks[l];
+    src[k] = b.qkv_w; dst[k] = w.qkv_w[l]; dstT[k] = w.qkv_wT[l]; rows[k] = 3 * D.C; cols[k++] = D.C;
+    src[k] = b.proj_w; dst[k] = w.proj_w[l]; dstT[k] = w.proj_wT[l]; rows[k] = D.C; cols[k++] = D.C;
+    src[k] = b.fc1_w; dst[k] = w.fc1_w[l]; dstT[k] = w.fc1_wT[l]; rows[k] = D.Fh; cols[k++] = D.C;
+    src[k] = b.fc2_w; dst[k] = w.fc2_w[l]; dstT[k] = w.fc2_wT[l]; rows[k] = D.C; cols[k++] = D.Fh;
+  }
+  UVC_TRY(cvt_f16_segs(src, dst, save ? dstT : nullptr, rows, cols, k, st));
+  // patch embed / head stay TF32
+  const float* s2[2]; float* d2[2]; long long n2[2]; int m = 0;
+  if (p.patch_w) { s2[m] = p.patch_w; d2[m] = w.patch_w; n2[m++] = (long long)D.C * D.Kp; }
+  s2[m] = p.head_w; d2[m] = w.head_w; n2[m++] = (long long)D.NC * D.C;
+  return round_tf32_segs(s2, d2, n2, m, st);
+}
+
+float grad_scale_of(const uvc_vit_backward_args& a) { return a.grad_scale > 0.f ? a.grad_scale : 1.0f; }
+
+}  // namespace
+
+unsigned long long vit_workspace_bytes_f16(const Dims& D, bool save) {
+  Ws16 w;
+  carve16(D, save, nullptr, 0, &w);
+  return w.bytes;
+}
+
+int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t st) {
+  UVC_TRY(check_tensors(a.w, D.L, "w", a.pe_in == nullptr));
+  UVC_REQUIRE((a.x || a.pe_in) && a.logits && a.workspace, UVC_ERR_BAD_ARG, "vit_forward: NULL x / logits / workspace");
+  const bool save = a.save_for_backward != 0;
+  Ws16 w;
+  carve16(D, save, a.workspace, a.workspace_bytes, &w);
+  UVC_REQUIRE(w.bytes <= a.workspace_bytes, UVC_ERR_WORKSPACE, "vit_forward: workspace %llu bytes < required %llu",
+              (unsigned long long)a.workspace_bytes, (unsigned long long)w.bytes);
+  const int M = (int)D.M, C = D.C, Fh = D.Fh;
+  const float eps = a.dims.ln_eps;
+  const float scale = 1.0f / sqrtf((float)D.d);
+
+  UVC_TRY(convert_weights16(a.w, D, w, save, st));
+  const float* pe = a.pe_in;
+  if (!pe) {
+    UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
+    float* pe_w = a.pe_out ? a.pe_out : w.pe;
+    UVC_TRY(linear_fwd(w.cols, D.Kp, w.patch_w, a.w.patch_b, pe_w, C, D.B * D.np, C, D.Kp, st));
+    pe = pe_w;
+  } else if (a.pe_out && a.pe_out != pe) {
+    cudaError_t e = cudaMemcpyAsync(a.pe_out, pe, (size_t)D.B * D.np * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_forward: memcpy pe_out: %s", cudaGetErrorString(e));
+  }
+  UVC_TRY(assemble_tokens(pe, a.w.cls_token, a.w.pos_embed, a.patch_scale, a.token_mask, w.tok, D.B, D.np, C, st));
+  if (pe != w.pe && save) {
+    cudaError_t e = cudaMemcpyAsync(w.pe, pe, (size_t)D.B * D.np * C * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_forward: memcpy pe: %s", cudaGetErrorString(e));
+  }
+  if (a.enable_jumping) {
+    cudaError_t e = cudaMemsetAsync(w.accum, 0, (size_t)M * C * sizeof(float), st);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_forward: memset accum: %s", cudaGetErrorString(e));
+  }
+
+  const float* x = w.tok;
+  for (int l = 0; l < D.L; ++l) {
+    const bool skipped = a.skip_host && a.skip_host[l];
+    if (!skipped) {
+      const uvc_block_tensors& p = a.w.blocks[l];
+      Layer16& L = w.layer[l];
+      UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, nullptr, C, L.mean1, L.rstd1, M, C, st, 0, L.ln1));
+      UVC_TRY(linear16(L.ln1, C, w.qkv_w[l], p.qkv_b, nullptr, L.qkv, 3 * C, M, 3 * C, C, st));
+      UVC_TRY(attention_fwd_f16(L.qkv, L.ctx, save ? L.lse : nullptr, D.B, D.H, D.ntok, scale, st));
+      UVC_TRY(linear16(L.ctx, C, w.proj_w[l], p.proj_b, L.x1, nullptr, C, M, C, C, st, 0, nullptr, x, C));            // x1 = x + proj(ctx)
+      UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, nullptr, C, L.mean2, L.rstd2, M, C, st, 0, L.ln2));
+      UVC_TRY(linear16(L.ln2, C, w.fc1_w[l], p.fc1_b, nullptr, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU, L.hpre));         // h = gelu(fc1) (fp16); hpre = gelu'(fc1) (fp16)
+      if (a.blend) {
+        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.t, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C));          // t = x1 + fc2(h)
+        UVC_TRY(blend_fwd(L.t, x, a.blend + 2 * l, L.xout, (long long)M * C, st));                                    // x <- d1 t + d0 x
+      } else {
+        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C));
+      }
+      x = L.xout;
+    }
+    if (a.enable_jumping) UVC_TRY(scale_add(w.accum, x, nullptr, 1.0f, (long long)M * C, st));
+  }
+  const float* xf = a.enable_jumping ? w.accum : x;
+  UVC_TRY(layernorm_fwd(xf, (long long)D.ntok * C, a.w.norm_w, a.w.norm_b, eps, w.cls_ln, C, w.mean_f, w.rstd_f, D.B, C, st, 1));
+  UVC_TRY(linear_fwd(w.cls_ln, C, w.head_w, a.w.head_b, a.logits, D.NC, D.B, D.NC, C, st));
+  return UVC_OK;
+}
+
+int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t st) {
+  UVC_TRY(check_tensors(a.w, D.L, "w", a.d_pe == nullptr));
+  UVC_TRY(check_tensors(a.g, D.L, "g", a.d_pe == nullptr));
+  UVC_REQUIRE(a.dlogits && a.workspace, UVC_ERR_BAD_ARG, "vit_backward: NULL dlogits / workspace");
+  UVC_REQUIRE(!a.blend || a.d_blend, UVC_ERR_BAD_ARG, "vit_backward: blend given without d_blend");
+  Ws16 w;
+  carve16(D, true, a.workspace, a.workspace_bytes, &w);
+  UVC_REQUIRE(w.bytes <= a.workspace_bytes, UVC_ERR_WORKSPACE, "vit_backward: workspace %llu bytes < required %llu",
+              (unsigned long long)a.workspace_bytes, (unsigned long long)w.bytes);
+  const int M = (int)D.M, C = D.C, Fh = D.Fh;
+  const float scale = 1.0f / sqrtf((float)D.d);
+  const size_t xbytes = (size_t)M * C * sizeof(float);
+  const float S = grad_scale_of(a), invS = 1.0f / S;
+
+  const float* xin[UVC_MAX_DEPTH + 1];
+  xin[0] = w.tok;
+  for (int l = 0; l < D.L; ++l) xin[l + 1] = (a.skip_host && a.skip_host[l]) ? xin[l] : w.layer[l].xout;
+  const float* xf = a.enable_jumping ? w.accum : xin[D.L];
+
+  // head (TF32, unscaled): dW += dlogits^T cls_ln ; db += colsum ; dcls_ln = dlogits W
+  const float* dlog = a.dlogits; long long ldl = D.NC;
+  UVC_TRY(pad_dlogits(&dlog, &ldl, w.dlog_pad, D.B, D.NC, st));
+  UVC_TRY(linear_wgrad(dlog, ldl, w.cls_ln, C, a.g.head_w, a.g.head_b, D.B, D.NC, C, st));
+  UVC_TRY(linear_dgrad(dlog, ldl, w.head_w, w.dcls_ln, C, D.B, D.NC, C, st));
+  // final LN backward on the cls rows; every other row of the stream gradient (and of its fp16 operand copy) is zero
+  float* g = w.g_a;
+  float* g_jump = nullptr;
+  cudaError_t e = cudaMemsetAsync(g, 0, xbytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(w.g16, 0, xbytes / 2, st);
+  UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: memset: %s", cudaGetErrorString(e));
+  UVC_TRY(layernorm_bwd(w.dcls_ln, C, xf, (long long)D.ntok * C, w.mean_f, w.rstd_f, a.w.norm_w, nullptr, nullptr, nullptr, g,
+                        (long long)D.ntok * C, a.g.norm_w, a.g.norm_b, D.B, C, st, nullptr, nullptr, nullptr, 1.0f, w.g16, S));
+  float* spare1 = w.g_b;
+  float* spare2 = w.g_c;
+  if (a.enable_jumping) {
+    g_jump = w.accum;
+    e = cudaMemcpyAsync(g_jump, g, xbytes, cudaMemcpyDeviceToDevice, st);
+    UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: memcpy: %s", cudaGetErrorString(e));
+  }
+
+  for (int l = D.L - 1; l >= 0; --l) {
+    const bool skipped = a.skip_host && a.skip_host[l];
+    if (!skipped) {
+      const uvc_block_tensors& p = a.w.blocks[l];
+      const uvc_block_tensors& gp = a.g.blocks[l];
+      const Layer16& L = w.layer[l];
+      const float* x = xin[l];
+      const float* d = a.blend ? a.blend + 2 * l : nullptr;
+      const float* d1 = d ? d + 1 : nullptr;
+      if (d) UVC_TRY(blend_dots(g, L.t, x, a.d_blend + 2 * l, (long long)M * C, st));
+      // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2))); dt = d1 g is never materialised (d1 rides as a device-scalar alpha)
+      UVC_TRY(linear_wgrad16(w.g16, C, L.h, Fh, gp.fc2_w, M, C, Fh, invS, st, d1));
+      UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, Fh, M, Fh, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, gp.fc1_b, invS));   // dhpre (x S)
+      UVC_TRY(linear_wgrad16(w.dh16, Fh, L.ln2, C, gp.fc1_w, M, Fh, C, invS, st));
+      UVC_TRY(linear16(w.dh16, Fh, w.fc1_wT[l], nullptr, nullptr, w.dln16, C, M, C, Fh, st));                                                          // dln2 (x S)
+      // dx1 = dt + LN2'(dln2); fc2.bias / proj.bias gradients ride along as column sums
+      UVC_TRY(layernorm_bwd(nullptr, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, d ? nullptr : g, d ? g : nullptr, d1, spare2, C, gp.norm2_w, gp.norm2_b,
+                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, invS, w.dx1_16, S));
+      float* dx1 = spare2;
+      // ---- attention:  x1 = x + proj(ctx)
+      UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, C, gp.proj_w, M, C, C, invS, st));
+      UVC_TRY(linear16(w.dx1_16, C, w.proj_wT[l], nullptr, nullptr, w.dctx16, C, M, C, C, st));                                                        // dctx (x S)
+      UVC_TRY(attention_bwd_f16(L.qkv, L.lse, L.ctx, w.dctx16, w.Dv, w.dqkv16, D.B, D.H, D.ntok, scale, st, gp.qkv_b, invS));
+      UVC_TRY(linear_wgrad16(w.dqkv16, 3 * C, L.ln1, C, gp.qkv_w, M, 3 * C, C, invS, st));
+      UVC_TRY(linear16(w.dqkv16, 3 * C, w.qkv_wT[l], nullptr, nullptr, w.dln16, C, M, C, 3 * C, st));                                                  // dln1 (x S)
+      // dx = dx1 + LN1'(dln1) + d0 g   (written over spare1); its fp16 operand copy replaces g16 (last read by the fc2 GEMMs above)
+      UVC_TRY(layernorm_bwd(nullptr, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st,
+                            nullptr, nullptr, w.dln16, invS, w.g16, S));
+      float* old = g; g = spare1; spare1 = old;
+    }
+    if (g_jump && l > 0) {
+      UVC_TRY(scale_add(g, g_jump, nullptr, 1.0f, (long long)M * C, st));
+      UVC_TRY(scale_to_f16(w.g16, g, S, (long long)M * C, st));
+    }
+  }
+
   const int rows = D.B * D.np;
   float* dpe = a.d_pe ? a.d_pe : w.dpe;
   UVC_TRY(assemble_tokens_bwd(g, w.pe, a.patch_scale, a.token_mask, dpe, a.patch_scale ? a.d_patch_scale : nullptr,

@@ -276,6 +276,7 @@ class DistilledVisionTransformer(VisionTransformer):
         d.C, d.H, d.Fh, d.L = self.embed_dim, self.blocks[0].attn.num_heads, self.blocks[0].mlp.fc1.out_features, len(self.blocks)
         d.num_classes = self.num_classes
         d.ln_eps = float(self.norm.eps)
+        d.operand_f16 = 1 if _lib.operand_f16_for(self, d.C // d.H, pe.num_patches + self.num_tokens, d.C, d.Fh) else 0
         return d
 
     def _tables(self):
@@ -305,7 +306,7 @@ class DistilledVisionTransformer(VisionTransformer):
 
     def _workspace(self, B, save):
         es = self._es
-        key = (int(B), bool(save))
+        key = (int(B), bool(save), self._dims(B).operand_f16)
         ws = es.ws.get(key)
         if ws is None:
             lib = _lib.load()
@@ -382,6 +383,7 @@ class DistilledVisionTransformer(VisionTransformer):
             d_tm = torch.empty_like(token_mask)
             a.d_token_mask = d_tm.data_ptr()
         a.enable_jumping = 1 if self.enable_jumping else 0
+        a.grad_scale = float(getattr(self, "grad_scale", _lib.DEFAULT_GRAD_SCALE))
         ws = self._workspace(B, True)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.uvc_vit_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_backward")

@@ -31,7 +31,8 @@ def operand(t, ld=None, bs1=0, bs2=0, mn_major=False):
 
 
 def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=None, ldr=None, r_bs=(0, 0),
-         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None, D16=None):
+         aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None, D16=None,
+         colsum_scale=0.0):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T) with A:[M,K], B:[N,K] (see include/uvc_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
@@ -63,6 +64,7 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
         flags |= GEMM_F16
     if colsum is not None:
         a.colsum = colsum.data_ptr(); flags |= EPI_COLSUM
+        a.colsum_scale = float(colsum_scale)
     a.flags = int(flags)
     _lib.check(lib.uvc_gemm_tf32(C.byref(a), _stream()), "uvc_gemm_tf32")
     return D
@@ -119,6 +121,46 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=No
         _call("uvc_layernorm_bwd", _p(dy), C_, _p(x), ldx, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), lddx,
               _p(dgamma), _p(dbeta), M, C_)
     return dx
+
+
+def _p16(t):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float16):
+        raise _lib.UvcError("expected a CUDA fp16 tensor")
+    return t.data_ptr()
+
+
+def layernorm_fwd_f16(x, gamma, beta, eps, save_stats=True):
+    """x:[M,C] fp32 -> y16:[M,C] fp16 (operand of the next kind::f16 GEMM), (mean, rstd)."""
+    C_ = gamma.numel()
+    M = x.numel() // C_
+    y = torch.empty(M, C_, device=x.device, dtype=torch.float16)
+    mean = torch.empty(M, device=x.device) if save_stats else None
+    rstd = torch.empty(M, device=x.device) if save_stats else None
+    _call("uvc_layernorm_fwd_f16", _p(x), C_, _p(gamma), _p(beta), float(eps), _p16(y), C_, _p(mean), _p(rstd), M, C_)
+    return y, mean, rstd
+
+
+def layernorm_bwd_f16(dy16, dy_scale, x, mean, rstd, gamma, r1=None, r2=None, s2=None, dgamma=None, dbeta=None, cs_r1=None, cs_out=None,
+                      want_dx16=True, dx16_scale=1.0):
+    """dy16 fp16 (scaled by 1/dy_scale) -> (dx fp32, dx16 = fp16(dx16_scale * dx) or None)"""
+    C_ = gamma.numel()
+    M = mean.numel()
+    dx = torch.empty(M, C_, device=x.device)
+    dx16 = torch.empty(M, C_, device=x.device, dtype=torch.float16) if want_dx16 else None
+    _call("uvc_layernorm_bwd_f16", _p16(dy16), C_, float(dy_scale), _p(x), C_, _p(mean), _p(rstd), _p(gamma), _p(r1), _p(r2), _p(s2), _p(dx), _p16(dx16),
+          float(dx16_scale), C_, _p(dgamma), _p(dbeta), _p(cs_r1), _p(cs_out), M, C_)
+    return dx, dx16
+
+
+def cvt_f16(src, transposed=True):
+    """fp32 [rows, cols] -> (fp16 copy, fp16 transposed copy [cols, rows] or None)"""
+    rows, cols = src.shape
+    dst = torch.empty(rows, cols, device=src.device, dtype=torch.float16)
+    dstT = torch.empty(cols, rows, device=src.device, dtype=torch.float16) if transposed else None
+    _call("uvc_cvt_f16", _p(src), _p16(dst), _p16(dstT), rows, cols)
+    return dst, dstT
 
 
 def softmax_fwd_(S, n, round_tf32=False):
@@ -217,6 +259,23 @@ def attention_bwd_fused(qkv, lse, ctx, dctx, B, H, N, d, scale=None, dbias=None)
     dqkv = torch.empty_like(qkv)
     ws = torch.empty(B, H, N, device=qkv.device)
     _call("uvc_attention_bwd_fused", _p(qkv), _p(lse), _p(ctx), _p(dctx), _p(ws), _p(dqkv), _p(dbias), B, H, N, d, float(scale))
+    return dqkv
+
+
+def attention_fwd_f16(qkv16, B, H, N, d=64, scale=None, want_lse=True):
+    """fp16 operand storage: qkv16 [B*N, 3*H*64] fp16 -> (ctx16 [B*N, H*64] fp16, lse [B,H,N] fp32 or None)"""
+    scale = d ** -0.5 if scale is None else scale
+    lse = torch.empty(B, H, N, device=qkv16.device) if want_lse else None
+    ctx = torch.empty(B * N, H * d, device=qkv16.device, dtype=torch.float16)
+    _call("uvc_attention_fwd_f16", _p16(qkv16), _p16(ctx), _p(lse), B, H, N, d, float(scale))
+    return ctx, lse
+
+
+def attention_bwd_f16(qkv16, lse, ctx16, dctx16, B, H, N, d=64, scale=None, dbias=None, db_scale=1.0):
+    scale = d ** -0.5 if scale is None else scale
+    dqkv = torch.empty_like(qkv16)
+    ws = torch.empty(B, H, N, device=qkv16.device)
+    _call("uvc_attention_bwd_f16", _p16(qkv16), _p(lse), _p16(ctx16), _p16(dctx16), _p(ws), _p16(dqkv), _p(dbias), float(db_scale), B, H, N, d, float(scale))
     return dqkv
 
 
