@@ -263,7 +263,8 @@ def run_gpu(a):
     torch.cuda.synchronize()
     import ctypes
     t_ms, t_fl, n_l = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-    lib.uvc_gemm_profile_read_kind(2, ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(n_l))       # the dominant kernel: persistent CTA-pair GEMM
+    f16_mode = bool(model._dims(B).operand_f16)
+    lib.uvc_gemm_profile_read_kind(3 if f16_mode else 2, ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(n_l))   # the dominant kernel: persistent CTA-pair GEMM (kind 3: fp16 operands)
     a_ms, a_fl, a_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
     lib.uvc_gemm_profile_read_kind(0, ctypes.byref(a_ms), ctypes.byref(a_fl), ctypes.byref(a_n))       # every GEMM launch (both kernels)
     lib.uvc_gemm_profile(0)
@@ -285,10 +286,13 @@ def run_gpu(a):
     step_flops = 4 * DENSE_FWD_FLOPS[MODEL] * B          # student fwd + bwd (2x) + dense teacher fwd, reference MAC accounting
     gemm_tflops = (t_fl.value / max(t_ms.value, 1e-9)) / 1e9
     tf32_peak = peaks["bf16_sustained"] / 2.0
+    mma_peak = peaks["bf16_sustained"] if f16_mode else tf32_peak       # the peak of the operand format the kernel actually uses
+    kind_txt = "kind::f16 (fp16 operand storage, fp32 accumulate)" if f16_mode else "kind::tf32"
     out = {
         "metric": "images/sec DeiT-Small UVC@50%FLOPs (Stage-1 joint_train step)", "value": round(value, 1), "unit": "images/sec",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": ("f16 operands / f32 accumulate (GEMM + attention operands stored as fp16 = TF32's 10 mantissa bits; residual stream, LayerNorm, softmax, loss, "
+                  "optimizer, ADMM in f32)" if f16_mode else "tf32 (fp32 storage, fp32 accumulate)"), "data": "synthetic",
         "config": {"workload": "BASELINE.json configs[2] at per-GPU size: DeiT-Small patch16 224 UVC joint_train (ADMM active), budget 0.5, "
                                "soft-distill alpha=0.1, 128 images/GPU, DDP over N GPUs", "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush"},
@@ -299,19 +303,20 @@ def run_gpu(a):
                             "last step's read-back is inside the timed region", "last_loss": round(losses[-1], 4) if losses else None},
         "gpu_launches": launches,
         "step_tflops_per_gpu": round(step_flops / (ms / a.steps / 1e3) / 1e12, 1),
-        "roofline": {"bound": "tensor", "kernel": "uvc::gemm2_tf32_kernel (persistent CTA pairs, tcgen05.mma cta_group::2 kind::tf32)",
-                     "achieved": round(gemm_tflops, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_tflops / tf32_peak, 3),
+        "roofline": {"bound": "tensor", "kernel": f"uvc::gemm2_tf32_kernel (persistent CTA pairs, tcgen05.mma cta_group::2 {kind_txt})",
+                     "achieved": round(gemm_tflops, 1), "peak": round(mma_peak, 1), "unit": "TFLOP/s", "frac": round(gemm_tflops / mma_peak, 3),
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                      "traffic_source": traffic["source"] if traffic else None,
                      "algorithmic_flops_per_launch": round(t_fl.value / max(1, n_l.value)),
                      "avg_launch_us": round(t_ms.value * 1e3 / max(1, n_l.value), 2),
-                     "peak_source": f"TF32 dense = 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}); bf16 sustained {peaks['bf16_sustained']}",
+                     "peak_source": (f"bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}): 16-bit dense, the format the kernel's MMAs run in" if f16_mode else
+                                     f"TF32 dense = 1/2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['src']}); bf16 sustained {peaks['bf16_sustained']}"),
                      "launches_per_step": int(n_l.value // 2), "kernel_ms_per_step": round(t_ms.value / 2, 3),
                      "all_gemm_launches_per_step": int(a_n.value // 2), "all_gemm_ms_per_step": round(a_ms.value / 2, 3),
                      "all_gemm_tflops": round((a_fl.value / max(a_ms.value, 1e-9)) / 1e9, 1),
                      "how": "CUDA-event pair on the launching stream around every GEMM launch of 2 instrumented steps run right after the timed region; "
                             "achieved = sum of 2*M*N*K over the CTA-pair kernel's launches / sum of their durations",
-                     "step_frac_of_tf32_peak": round(step_flops / (ms / a.steps / 1e3) / 1e12 / tf32_peak, 3)},
+                     "step_frac_of_peak": round(step_flops / (ms / a.steps / 1e3) / 1e12 / mma_peak, 3)},
     }
     out["cpu_baseline"] = run_cpu_sample(steps=2, warmup=1) if world == 1 and not a.no_cpu_baseline else None
     print(json.dumps(out), flush=True)

@@ -111,6 +111,8 @@ typedef struct {
   float colsum_scale;      /* multiplies the UVC_EPI_COLSUM column sums before they are accumulated; 0 means 1 (how the loss scale of the
                               fp16 gradient tensors is taken back out of a fused bias gradient) */
   float* colsum;           /* [N], accumulated into when UVC_EPI_COLSUM is set */
+  const float* alpha_dev2; /* a second optional device scalar multiplied into alpha (gate value x inverse loss scale) */
+  const float* colsum_scale_dev;  /* optional device scalar multiplied into colsum_scale */
   void* D16; int64_t ldd16; /* optional fp16 copy of the output [M, ldd16] (round to nearest), for consumers that read it as an fp16 GEMM
                               operand; D may then be NULL.  Needs the unbatched CTA-pair kernel (N % 4 == 0, 16 B-aligned rows). */
 } uvc_gemm_args;
@@ -282,7 +284,9 @@ typedef struct {
   const float* token_mask;
   int32_t enable_jumping;
   float grad_scale;              /* operand_f16 only: the power-of-two loss scale S the fp16 gradient operands carry (g16 = fp16(S g)); it is taken
-                                    back out wherever an fp32 result is produced, so every output of this call is the true gradient.  <= 0 means 1. */
+                                    back out wherever an fp32 result is produced, so every output of this call is the true gradient.
+                                    <= 0 (default): chosen on the device per call, the largest power of two with S * max|dlogits| <= 128 --
+                                    every gradient is linear in dlogits, so the fp16 range use does not depend on how the loss was scaled. */
   float* d_blend;                /* [L,2], accumulated; NULL if blend == NULL */
   float* d_patch_scale;          /* [np] accumulated, or NULL */
   float* d_token_mask;           /* [B, np] written, or NULL */

@@ -28,7 +28,8 @@ class GemmArgs(C.Structure):
                 ("R", C.c_void_p), ("ldr", C.c_int64), ("r_bs1", C.c_int64), ("r_bs2", C.c_int64),
                 ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_bs1", C.c_int64), ("aux_bs2", C.c_int64),
                 ("alpha", C.c_float), ("beta", C.c_float), ("alpha_dev", C.c_void_p), ("beta_dev", C.c_void_p),
-                ("flags", C.c_int32), ("colsum_scale", C.c_float), ("colsum", C.c_void_p), ("D16", C.c_void_p), ("ldd16", C.c_int64)]
+                ("flags", C.c_int32), ("colsum_scale", C.c_float), ("colsum", C.c_void_p), ("alpha_dev2", C.c_void_p), ("colsum_scale_dev", C.c_void_p),
+                ("D16", C.c_void_p), ("ldd16", C.c_int64)]
 
 
 _F = C.c_void_p   # device float*
@@ -99,9 +100,8 @@ EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_
 _lib = None
 
 # Precision mode of the engine (uvc_vit_dims.operand_f16).  Default: fp16 operand storage wherever the kernels support it; UVC_PRECISION=tf32 (or
-# model.operand_f16 = False) selects the fp32-storage / TF32 path of round 1.  The fp16 gradient operands carry a power-of-two loss scale
-# (model.grad_scale, default below) that the engine removes again wherever it produces an fp32 gradient.
-DEFAULT_GRAD_SCALE = 8192.0
+# model.operand_f16 = False) selects the fp32-storage / TF32 path of round 1.  The fp16 gradient operands carry a power-of-two loss scale that
+# the engine picks on the device from max|dlogits| (or model.grad_scale if set > 0) and removes again wherever it produces an fp32 gradient.
 
 
 def operand_f16_for(model, d, ntok, C_, Fh):

@@ -319,6 +319,7 @@ struct alignas(64) Attn16BwdParams {
   long long ldo;
   int B, H, N, ntiles;
   float scale, scale_log2e, db_scale;
+  const float* db_scale_dev;   // optional device scalar multiplied into db_scale (the inverse loss scale chosen on the device)
 };
 
 __device__ __forceinline__ void warp_colsum32f(float (&v)[32], int lane) {
@@ -445,6 +446,7 @@ __global__ void __launch_bounds__(kThreadsA, 1) attn16_bwd_kernel(const __grid_c
     const int hh = ew >> 2;                          // column range: hh = 0 -> [0, 112), hh = 1 -> [112, 208)
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const int N = p.N;
+    const float db_scale = p.db_scale * ((p.db0 && p.db_scale_dev) ? __ldg(p.db_scale_dev) : 1.0f);
     const int tid2 = threadIdx.x - 64;
     uint32_t ia = 0;
     // The per-row statistics are fetched one step AHEAD (phase 1: next tile's row values into registers; phase 2: the next head's 208 column
@@ -544,12 +546,12 @@ __global__ void __launch_bounds__(kThreadsA, 1) attn16_bwd_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = row < N ? __uint_as_float(o0[j]) : 0.f;
           warp_colsum32f(v, lane);
-          atomicAdd(p.db0 + h * 64 + hh * 32 + lane, v[0] * p.db_scale);
+          atomicAdd(p.db0 + h * 64 + hh * 32 + lane, v[0] * db_scale);
           if (PHASE == 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = row < N ? __uint_as_float(o1[j]) : 0.f;
             warp_colsum32f(v, lane);
-            atomicAdd(p.db1 + h * 64 + hh * 32 + lane, v[0] * p.db_scale);
+            atomicAdd(p.db1 + h * 64 + hh * 32 + lane, v[0] * db_scale);
           }
         }
         if (row < N) {
@@ -642,7 +644,7 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
 }
 
 int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
-                      float scale, cudaStream_t st, float* dqkv_bias, float db_scale) {
+                      float scale, cudaStream_t st, float* dqkv_bias, float db_scale, const float* db_scale_dev) {
   UVC_REQUIRE(B > 0 && H > 0 && attn_f16_ok(N, 64), UVC_ERR_BAD_SHAPE, "attention_bwd_f16: bad dims B=%d H=%d N=%d (N <= %d)", B, H, N, kNK);
   const long long C = (long long)H * 64, ld3 = 3 * C;
   const __half* q = static_cast<const __half*>(qkv16);
@@ -658,7 +660,7 @@ int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, co
   UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn16_bwd): %s", cudaGetErrorString(e));
   Attn16BwdParams kp;
   kp.lse = lse; kp.Dv = Dv; kp.ldo = ld3; kp.B = B; kp.H = H; kp.N = N; kp.ntiles = (N + 127) / 128;
-  kp.scale = scale; kp.scale_log2e = scale * 1.4426950408889634f; kp.db_scale = db_scale;
+  kp.scale = scale; kp.scale_log2e = scale * 1.4426950408889634f; kp.db_scale = db_scale; kp.db_scale_dev = db_scale_dev;
   // phase 1: dQ
   if ((rc = attn16_tmap(&kp.tmA0, q, ld3, B, H, N, 128, "attn16 bwd Q tile"))) return rc;
   if ((rc = attn16_tmap(&kp.tmA1, dctx16, C, B, H, N, 128, "attn16 bwd dO tile"))) return rc;
@@ -690,5 +692,5 @@ extern "C" int uvc_attention_bwd_f16(const void* qkv16, const float* lse, const 
                                      float* dqkv_bias, float db_scale, int32_t B, int32_t H, int32_t N, int32_t d, float scale, void* stream) {
   UVC_REQUIRE(qkv16 && lse && ctx16 && dctx16 && D_ws && dqkv16, UVC_ERR_BAD_ARG, "uvc_attention_bwd_f16: NULL pointer");
   UVC_REQUIRE(uvc::attn_f16_ok(N, d), UVC_ERR_BAD_SHAPE, "uvc_attention_bwd_f16: needs d == 64 and N <= 208 (got d=%d, N=%d)", d, N);
-  return uvc::attention_bwd_f16(qkv16, lse, ctx16, dctx16, D_ws, dqkv16, B, H, N, scale, static_cast<cudaStream_t>(stream), dqkv_bias, db_scale);
+  return uvc::attention_bwd_f16(qkv16, lse, ctx16, dctx16, D_ws, dqkv16, B, H, N, scale, static_cast<cudaStream_t>(stream), dqkv_bias, db_scale, nullptr);
 }

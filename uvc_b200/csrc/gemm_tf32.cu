@@ -29,7 +29,7 @@ struct alignas(64) GemmKParams {
   const float* bias;
   const float* R; long long ldr, r_bs1, r_bs2;
   float* aux; long long ldaux, aux_bs1, aux_bs2;
-  const float* alpha_dev; const float* beta_dev;
+  const float* alpha_dev; const float* beta_dev; const float* alpha_dev2; const float* colsum_scale_dev;
   float* colsum;
   void* D16; long long ldd16;           // optional fp16 copy of the output (v2 kernel), row stride in fp16 elements
   float alpha, beta, colsum_scale;
@@ -177,7 +177,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
     const int flags = p.flags;
     float alpha = p.alpha, beta = p.beta;
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    if (p.alpha_dev2) alpha *= __ldg(p.alpha_dev2);
     if (p.beta_dev) beta *= __ldg(p.beta_dev);
+    const float cs_scale = p.colsum_scale * (p.colsum_scale_dev ? __ldg(p.colsum_scale_dev) : 1.0f);
     const bool first_split = (split == 0);
 
     mbar_wait(tmem_full_bar, 0);
@@ -209,7 +211,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
           float t = (row < p.M) ? __uint_as_float(r[j]) * alpha : 0.f;
           if ((flags & UVC_EPI_BIAS) && first_split && col0 + j < p.N) t += (row < p.M) ? __ldg(p.bias + col0 + j) : 0.f;
           t = warp_sum(t);
-          if (lane == 0 && col0 + j < p.N) atomicAdd(p.colsum + col0 + j, t * p.colsum_scale);
+          if (lane == 0 && col0 + j < p.N) atomicAdd(p.colsum + col0 + j, t * cs_scale);
         }
       }
       if (row < p.M) {
@@ -476,7 +478,9 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     const int flags = p.flags;
     float alpha = p.alpha, beta = p.beta;
     if (p.alpha_dev) alpha *= __ldg(p.alpha_dev);
+    if (p.alpha_dev2) alpha *= __ldg(p.alpha_dev2);
     if (p.beta_dev) beta *= __ldg(p.beta_dev);
+    const float cs_scale = p.colsum_scale * (p.colsum_scale_dev ? __ldg(p.colsum_scale_dev) : 1.0f);
     const int rl = lane >> 3, cc = lane & 7;
     const uint32_t st_row = stg + lane * 128;                                        // staging: this lane's TMEM row
     const uint32_t ld_even = stg + rl * 128 + (((uint32_t)cc ^ (uint32_t)rl) << 4);  // rows i*4 + rl, i even: (row & 7) = rl
@@ -575,7 +579,7 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
             cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x * p.colsum_scale, cs.y * p.colsum_scale, cs.z * p.colsum_scale, cs.w * p.colsum_scale);
+            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x * cs_scale, cs.y * cs_scale, cs.z * cs_scale, cs.w * cs_scale);
           }
           __syncwarp();                                // staging tile is rewritten by the next chunk
         }
@@ -871,7 +875,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.bias = a.bias;
   kp.R = (a.flags & UVC_EPI_RESIDUAL) ? a.R : nullptr; kp.ldr = a.ldr; kp.r_bs1 = a.r_bs1; kp.r_bs2 = a.r_bs2;
   kp.aux = (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) ? a.aux : nullptr; kp.ldaux = a.ldaux; kp.aux_bs1 = a.aux_bs1; kp.aux_bs2 = a.aux_bs2;
-  kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev;
+  kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev; kp.alpha_dev2 = a.alpha_dev2; kp.colsum_scale_dev = a.colsum_scale_dev;
   kp.colsum = (a.flags & UVC_EPI_COLSUM) ? a.colsum : nullptr;
   kp.alpha = a.alpha; kp.beta = a.beta; kp.colsum_scale = (a.colsum_scale != 0.0f) ? a.colsum_scale : 1.0f;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.nb1 = a.nb1; kp.nb2 = a.nb2; kp.splits = splits; kp.flags = a.flags;

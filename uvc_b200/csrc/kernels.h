@@ -19,7 +19,8 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
                   cudaStream_t st, float* cs_r1 = nullptr, float* cs_out = nullptr,    // cs_*: fused column sums of r1 / of dx (bias gradients)
                   const void* dy16 = nullptr, float dy_scale = 1.0f,                    // dy16: dy as fp16 (row stride lddy), multiplied by dy_scale on load
-                  void* dx16 = nullptr, float out_scale = 1.0f);                        // dx16: also write fp16(out_scale * dx), row stride lddx
+                  void* dx16 = nullptr, float out_scale = 1.0f,                         // dx16: also write fp16(out_scale * dx), row stride lddx
+                  const float* scales_dev = nullptr);                                   // device {S, 1/S}: out_scale *= S, dy_scale *= 1/S
 int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int round_out = 0);
 int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int round_out = 0);
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);
@@ -35,7 +36,8 @@ int assemble_tokens(const float* pe, const float* cls, const float* pos, const f
 int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe, float* dscale, float* dtmask,
                         float* dpos, float* dcls, int B, int np, int C, cudaStream_t st);
 int scale_add(float* y, const float* x, const float* s_dev, float s, long long n, cudaStream_t st);
-int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st);   // dst16 = fp16(s * src)
+int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st, const float* s_dev = nullptr);   // dst16 = fp16(s * (*s_dev) * src)
+int grad_scale(const float* dlogits, long long n, float target, float fixed, float* scales, cudaStream_t st);   // scales = {S, 1/S} (see rowwise.cu)
 
 int attn_ldp(int N);
 int attention_fwd(const float* qkv, float* P, float* ctx, int B, int H, int N, int d, float scale, cudaStream_t st, bool need_P = true, float* lse = nullptr);
@@ -51,7 +53,7 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
 // dqkv16 [B*N, 3*H*64] fp16 from dctx16 (fp16, may carry a loss scale: everything downstream is linear in it); Dv: [B,H,N] fp32 scratch;
 // dqkv_bias (optional, fp32 [3*H*64]) += db_scale * column sums of dqkv
 int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
-                      float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f);
+                      float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f, const float* db_scale_dev = nullptr);
 
 // ---- helpers to describe GEMM operands tersely
 inline uvc_operand op_k(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 0, 0}; }

@@ -93,8 +93,10 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(c
                                                             const float* __restrict__ s2_dev, float* __restrict__ dx, long long lddx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cs_r1,
                                                             float* __restrict__ cs_out, int M, int C, int rows_per_block,
-                                                            float dy_scale, __half* __restrict__ dx16, float out_scale) {
+                                                            float dy_scale, __half* __restrict__ dx16, float out_scale,
+                                                            const float* __restrict__ scales_dev) {
   __shared__ float red[4][8][32 * 4 + 4];
+  if (scales_dev) { out_scale *= __ldg(scales_dev); dy_scale *= __ldg(scales_dev + 1); }     // {S, 1/S} chosen on the device (see grad_scale_kernel)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int nv = C >> 2;
   const float s2 = (r2 && s2_dev) ? __ldg(s2_dev) : 1.0f;
@@ -417,11 +419,35 @@ __global__ void scale_add_kernel(float4* __restrict__ y, const float4* __restric
   }
 }
 
-__global__ void scale_to_f16_kernel(uint2* __restrict__ dst, const float4* __restrict__ src, float s, long long n4) {
+__global__ void scale_to_f16_kernel(uint2* __restrict__ dst, const float4* __restrict__ src, float s, const float* __restrict__ s_dev, long long n4) {
+  if (s_dev) s *= __ldg(s_dev);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = src[i];
     dst[i] = pack_half4(a.x * s, a.y * s, a.z * s, a.w * s);
   }
+}
+
+// Loss scale of the fp16 gradient operands, chosen ON THE DEVICE from the gradient that enters the backward: the largest power of two S with
+// S * max|dlogits| <= target.  Every gradient is linear in dlogits, so this makes the fp16 range use independent of how the caller scaled the loss
+// (mean over 128 images, sum over a batch, an arbitrary autograd head, ...).  scales = {S, 1/S}; a fixed S (> 0) bypasses the reduction.
+__global__ void __launch_bounds__(1024) grad_scale_kernel(const float* __restrict__ dlogits, long long n, float target, float fixed, float* __restrict__ scales) {
+  __shared__ float red[32];
+  float S = fixed;
+  if (!(fixed > 0.f)) {
+    float mx = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(dlogits[i]));     // NaN / inf entries: fmaxf drops NaN, inf gives S = 0 -> clamped below
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      mx = warp_max(threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f);
+      int e = 0;
+      if (mx > 0.f && mx < INFINITY) { frexpf(target / mx, &e); e -= 1; }       // 2^e <= target / mx < 2^(e+1)
+      e = max(-24, min(24, e));
+      S = ldexpf(1.0f, e);
+    }
+  }
+  if (threadIdx.x == 0) { scales[0] = S; scales[1] = 1.0f / S; }
 }
 
 // dst = rna_tf32(src) over up to kMaxSeg tensors in one launch (all GEMM weights of the model)
@@ -494,7 +520,7 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st, float* cs_r1, float* cs_out, const void* dy16, float dy_scale, void* dx16, float out_scale) {
+                  cudaStream_t st, float* cs_r1, float* cs_out, const void* dy16, float dy_scale, void* dx16, float out_scale, const float* scales_dev) {
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
   UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
   UVC_REQUIRE(!cs_r1 || r1 || r2, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without a residual input");
@@ -509,13 +535,13 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
   if (dy16) {
     const float* d16 = static_cast<const float*>(dy16);
     if (cs_r1 || cs_out)
-      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale)));
+      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale, scales_dev)));
     else
-      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale)));
+      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale, scales_dev)));
   } else if (cs_r1 || cs_out)
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale)));
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale, scales_dev)));
   else
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale)));
+    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale, scales_dev)));
   return check_launch("layernorm_bwd");
 }
 
@@ -603,10 +629,14 @@ int round_tf32_segs(const float* const* src, float* const* dst, const long long*
   }
   return UVC_OK;
 }
-int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st) {
+int scale_to_f16(void* dst16, const float* src, float s, long long n, cudaStream_t st, const float* s_dev) {
   UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "scale_to_f16: element count must be a multiple of 4");
-  scale_to_f16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(static_cast<uint2*>(dst16), reinterpret_cast<const float4*>(src), s, n / 4);
+  scale_to_f16_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(static_cast<uint2*>(dst16), reinterpret_cast<const float4*>(src), s, s_dev, n / 4);
   return check_launch("scale_to_f16");
+}
+int grad_scale(const float* dlogits, long long n, float target, float fixed, float* scales, cudaStream_t st) {
+  grad_scale_kernel<<<1, 1024, 0, st>>>(dlogits, n, target, fixed, scales);
+  return check_launch("grad_scale");
 }
 int cvt_f16_segs(const float* const* src, void* const* dst, void* const* dstT, const int* rows, const int* cols, int nseg, cudaStream_t st) {
   for (int base = 0; base < nseg; base += kMaxRoundSegs) {
@@ -667,7 +697,7 @@ int uvc_layernorm_bwd_f16(const void* dy16, int64_t lddy, float dy_scale, const 
   UVC_REQUIRE(dy16 && x && mean && rstd && gamma && dx, UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_f16: NULL pointer");
   UVC_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), UVC_ERR_BAD_ARG, "uvc_layernorm_bwd_f16: dgamma and dbeta must both be given or both NULL");
   return uvc::layernorm_bwd(nullptr, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, M, C, UVC_ST, cs_r1, cs_out, dy16, dy_scale,
-                            dx16, dx16_scale);
+                            dx16, dx16_scale, nullptr);
 }
 int uvc_cvt_f16(const float* src, void* dst16, void* dstT16, int32_t rows, int32_t cols, void* stream) {
   UVC_REQUIRE(src && (dst16 || dstT16), UVC_ERR_BAD_ARG, "uvc_cvt_f16: NULL pointer");

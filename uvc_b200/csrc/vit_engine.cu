@@ -389,7 +389,7 @@ struct Ws16 {
   h16 *qkv_wT[UVC_MAX_DEPTH], *proj_wT[UVC_MAX_DEPTH], *fc1_wT[UVC_MAX_DEPTH], *fc2_wT[UVC_MAX_DEPTH];
   float *cols, *pe, *tok, *mean_f, *rstd_f, *cls_ln, *accum;
   Layer16 layer[UVC_MAX_DEPTH];
-  float *g_a, *g_b, *g_c, *Dv, *dcls_ln, *dpe, *dlog_pad;
+  float *g_a, *g_b, *g_c, *Dv, *dcls_ln, *dpe, *dlog_pad, *scales;
   h16 *g16, *dx1_16, *dln16, *dctx16, *dh16, *dqkv16;
   size_t bytes;
 };
@@ -426,6 +426,7 @@ void carve16(const Dims& D, bool save, void* base, size_t cap, Ws16* w) {
     w->g_a = b.f(M * C); w->g_b = b.f(M * C); w->g_c = b.f(M * C);
     w->Dv = b.f(lsz); w->dcls_ln = b.f((size_t)D.B * C); w->dpe = b.f((size_t)D.B * D.np * C);
     w->dlog_pad = b.f((size_t)D.B * ((D.NC + 3) / 4 * 4));
+    w->scales = b.f(4);
     w->g16 = b.h(M * C); w->dx1_16 = b.h(M * C); w->dln16 = b.h(M * C); w->dctx16 = b.h(M * C); w->dh16 = b.h(M * Fh); w->dqkv16 = b.h(M * 3 * C);
   } else {
     Layer16 L0;
@@ -434,7 +435,7 @@ void carve16(const Dims& D, bool save, void* base, size_t cap, Ws16* w) {
     L0.t = b.f(M * C); L0.xout = b.f(M * C);
     float* ping = L0.xout; float* pong = b.f(M * C);
     for (int l = 0; l < D.L; ++l) { w->layer[l] = L0; w->layer[l].xout = (l & 1) ? pong : ping; }
-    w->g_a = w->g_b = w->g_c = w->Dv = w->dcls_ln = w->dpe = w->dlog_pad = nullptr;
+    w->g_a = w->g_b = w->g_c = w->Dv = w->dcls_ln = w->dpe = w->dlog_pad = w->scales = nullptr;
     w->g16 = w->dx1_16 = w->dln16 = w->dctx16 = w->dh16 = w->dqkv16 = nullptr;
   }
   w->bytes = b.off;
@@ -446,7 +447,7 @@ inline uvc_operand op16_mn(const h16* p, long long ld) { return uvc_operand{rein
 // Y = epilogue(X16 W16^T): fp32 output D (with optional fp32 residual R) and / or fp16 output D16
 int linear16(const h16* X, long long ldx, const h16* W, const float* bias, float* Dout, void* D16, long long ldd, int M, int N, int K, cudaStream_t st,
              int extra_flags = 0, void* aux16 = nullptr, const float* R = nullptr, long long ldr = 0, const float* alpha_dev = nullptr,
-             float* colsum_out = nullptr, float colsum_scale = 1.0f) {
+             float* colsum_out = nullptr, const float* colsum_scale_dev = nullptr) {
   uvc_gemm_args a = gemm_args(M, N, K, op16_k(X, ldx), op16_k(W, K), Dout, ldd);
   a.flags = extra_flags | UVC_GEMM_F16;
   a.D16 = D16; a.ldd16 = ldd;
@@ -454,16 +455,16 @@ int linear16(const h16* X, long long ldx, const h16* W, const float* bias, float
   if (bias) { a.bias = bias; a.flags |= UVC_EPI_BIAS; }
   if (aux16) { a.aux = static_cast<float*>(aux16); a.ldaux = ldd; a.flags |= UVC_EPI_AUX_F16; }
   if (R) { a.R = R; a.ldr = ldr; a.flags |= UVC_EPI_RESIDUAL; }
-  if (colsum_out) { a.colsum = colsum_out; a.colsum_scale = colsum_scale; a.flags |= UVC_EPI_COLSUM; }
+  if (colsum_out) { a.colsum = colsum_out; a.colsum_scale_dev = colsum_scale_dev; a.flags |= UVC_EPI_COLSUM; }
   return gemm_tf32(a, st);
 }
-// dW[N,K] += alpha * dY16[M,N]^T X16[M,K]   (both operands MN-major fp16, split-K with fp32 atomics)
-int linear_wgrad16(const h16* dY, long long lddy, const h16* X, long long ldx, float* dW, int M, int N, int K, float alpha, cudaStream_t st,
+// dW[N,K] += (*inv_scale_dev) * dY16[M,N]^T X16[M,K]   (both operands MN-major fp16, split-K with fp32 atomics)
+int linear_wgrad16(const h16* dY, long long lddy, const h16* X, long long ldx, float* dW, int M, int N, int K, const float* inv_scale_dev, cudaStream_t st,
                    const float* scale_dev = nullptr) {
   uvc_gemm_args a = gemm_args(N, K, M, op16_mn(dY, lddy), op16_mn(X, ldx), dW, K);
   a.flags = UVC_EPI_ATOMIC | UVC_GEMM_F16;
-  a.alpha = alpha;
   a.alpha_dev = scale_dev;
+  a.alpha_dev2 = inv_scale_dev;
   a.splits = wgrad_splits(N, K, M, 64);
   return gemm_tf32(a, st);
 }
@@ -485,8 +486,6 @@ int convert_weights16(const uvc_vit_tensors& p, const Dims& D, const Ws16& w, bo
   s2[m] = p.head_w; d2[m] = w.head_w; n2[m++] = (long long)D.NC * D.C;
   return round_tf32_segs(s2, d2, n2, m, st);
 }
-
-float grad_scale_of(const uvc_vit_backward_args& a) { return a.grad_scale > 0.f ? a.grad_scale : 1.0f; }
 
 }  // namespace
 
@@ -569,7 +568,9 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
   const int M = (int)D.M, C = D.C, Fh = D.Fh;
   const float scale = 1.0f / sqrtf((float)D.d);
   const size_t xbytes = (size_t)M * C * sizeof(float);
-  const float S = grad_scale_of(a), invS = 1.0f / S;
+  // loss scale of the fp16 gradient operands: device scalars {S, 1/S} (fixed by the caller, or the largest power of two with S max|dlogits| <= 128)
+  const float* Sd = w.scales; const float* invSd = w.scales + 1;
+  UVC_TRY(grad_scale(a.dlogits, (long long)D.B * D.NC, 128.0f, a.grad_scale, w.scales, st));
 
   const float* xin[UVC_MAX_DEPTH + 1];
   xin[0] = w.tok;
@@ -588,7 +589,7 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
   if (e == cudaSuccess) e = cudaMemsetAsync(w.g16, 0, xbytes / 2, st);
   UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: memset: %s", cudaGetErrorString(e));
   UVC_TRY(layernorm_bwd(w.dcls_ln, C, xf, (long long)D.ntok * C, w.mean_f, w.rstd_f, a.w.norm_w, nullptr, nullptr, nullptr, g,
-                        (long long)D.ntok * C, a.g.norm_w, a.g.norm_b, D.B, C, st, nullptr, nullptr, nullptr, 1.0f, w.g16, S));
+                        (long long)D.ntok * C, a.g.norm_w, a.g.norm_b, D.B, C, st, nullptr, nullptr, nullptr, 1.0f, w.g16, 1.0f, w.scales));
   float* spare1 = w.g_b;
   float* spare2 = w.g_c;
   if (a.enable_jumping) {
@@ -608,28 +609,28 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
       const float* d1 = d ? d + 1 : nullptr;
       if (d) UVC_TRY(blend_dots(g, L.t, x, a.d_blend + 2 * l, (long long)M * C, st));
       // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2))); dt = d1 g is never materialised (d1 rides as a device-scalar alpha)
-      UVC_TRY(linear_wgrad16(w.g16, C, L.h, Fh, gp.fc2_w, M, C, Fh, invS, st, d1));
-      UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, Fh, M, Fh, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, gp.fc1_b, invS));   // dhpre (x S)
-      UVC_TRY(linear_wgrad16(w.dh16, Fh, L.ln2, C, gp.fc1_w, M, Fh, C, invS, st));
+      UVC_TRY(linear_wgrad16(w.g16, C, L.h, Fh, gp.fc2_w, M, C, Fh, invSd, st, d1));
+      UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, Fh, M, Fh, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, gp.fc1_b, invSd));   // dhpre (x S)
+      UVC_TRY(linear_wgrad16(w.dh16, Fh, L.ln2, C, gp.fc1_w, M, Fh, C, invSd, st));
       UVC_TRY(linear16(w.dh16, Fh, w.fc1_wT[l], nullptr, nullptr, w.dln16, C, M, C, Fh, st));                                                          // dln2 (x S)
       // dx1 = dt + LN2'(dln2); fc2.bias / proj.bias gradients ride along as column sums
       UVC_TRY(layernorm_bwd(nullptr, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, d ? nullptr : g, d ? g : nullptr, d1, spare2, C, gp.norm2_w, gp.norm2_b,
-                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, invS, w.dx1_16, S));
+                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, 1.0f, w.dx1_16, 1.0f, w.scales));
       float* dx1 = spare2;
       // ---- attention:  x1 = x + proj(ctx)
-      UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, C, gp.proj_w, M, C, C, invS, st));
+      UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, C, gp.proj_w, M, C, C, invSd, st));
       UVC_TRY(linear16(w.dx1_16, C, w.proj_wT[l], nullptr, nullptr, w.dctx16, C, M, C, C, st));                                                        // dctx (x S)
-      UVC_TRY(attention_bwd_f16(L.qkv, L.lse, L.ctx, w.dctx16, w.Dv, w.dqkv16, D.B, D.H, D.ntok, scale, st, gp.qkv_b, invS));
-      UVC_TRY(linear_wgrad16(w.dqkv16, 3 * C, L.ln1, C, gp.qkv_w, M, 3 * C, C, invS, st));
+      UVC_TRY(attention_bwd_f16(L.qkv, L.lse, L.ctx, w.dctx16, w.Dv, w.dqkv16, D.B, D.H, D.ntok, scale, st, gp.qkv_b, 1.0f, invSd));
+      UVC_TRY(linear_wgrad16(w.dqkv16, 3 * C, L.ln1, C, gp.qkv_w, M, 3 * C, C, invSd, st));
       UVC_TRY(linear16(w.dqkv16, 3 * C, w.qkv_wT[l], nullptr, nullptr, w.dln16, C, M, C, 3 * C, st));                                                  // dln1 (x S)
       // dx = dx1 + LN1'(dln1) + d0 g   (written over spare1); its fp16 operand copy replaces g16 (last read by the fc2 GEMMs above)
       UVC_TRY(layernorm_bwd(nullptr, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st,
-                            nullptr, nullptr, w.dln16, invS, w.g16, S));
+                            nullptr, nullptr, w.dln16, 1.0f, w.g16, 1.0f, w.scales));
       float* old = g; g = spare1; spare1 = old;
     }
     if (g_jump && l > 0) {
       UVC_TRY(scale_add(g, g_jump, nullptr, 1.0f, (long long)M * C, st));
-      UVC_TRY(scale_to_f16(w.g16, g, S, (long long)M * C, st));
+      UVC_TRY(scale_to_f16(w.g16, g, 1.0f, (long long)M * C, st, Sd));
     }
   }
 

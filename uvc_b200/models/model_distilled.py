@@ -383,7 +383,7 @@ class DistilledVisionTransformer(VisionTransformer):
             d_tm = torch.empty_like(token_mask)
             a.d_token_mask = d_tm.data_ptr()
         a.enable_jumping = 1 if self.enable_jumping else 0
-        a.grad_scale = float(getattr(self, "grad_scale", _lib.DEFAULT_GRAD_SCALE))
+        a.grad_scale = float(getattr(self, "grad_scale", 0.0))      # 0: the engine picks the fp16 loss scale from max|dlogits| on the device
         ws = self._workspace(B, True)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.uvc_vit_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_backward")
