@@ -171,6 +171,23 @@ UVC_API int uvc_assemble_tokens(const float* pe, const float* cls, const float* 
 /* backward of uvc_assemble_tokens: dpe = g * scale; dscale[p] += ..., dtmask[b,p] = ..., dpos += sum_b g, dcls += sum_b g[:,0] */
 UVC_API int uvc_assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, const float* tmask, float* dpe,
                                     float* dscale, float* dtmask, float* dpos, float* dcls, int32_t B, int32_t np, int32_t C, void* stream);
+/* Token (patch) slimming gate, mode 2 of --enable_patch_gating (models/model_distilled.py:446-456, gumbel_softmax :36-63, scatter :21-33),
+ * one CTA per image, no host round trip:
+ *   scores = pscale * (feat . v + c1) + gate_b ; l = log_softmax(scores) ; y = softmax((l + noise) / tau) ;
+ *   hard = the k largest y (exact rank, ties to the lower index = torch.topk on CUDA) ; mask = (hard - y) + y ; mask[:, 0] = 1.
+ * The score is an fp32 dot product over the rows the patch GEMM reads (feat = im2col rows [B*np, Kf] with v, c1 from uvc_token_gate_fold =
+ * W_patch^T w_gate, b_patch . w_gate), or over the token embeddings themselves (T2T: feat = tokens, v = w_gate, c1 = NULL), so the kept-token
+ * indices do not depend on tensor-core rounding.  noise [B, np] is the caller's Gumbel sample (torch's generator: the reference's stream).
+ * ysoft / ls / scores (each [B, np], optional) are what the backward needs.
+ *   uvc_token_gate_bwd:   dscores from dmask (straight-through: d mask / d y = 1, none through column 0).
+ *   uvc_token_gate_apply: dx += dscores pscale (x) w_gate ; d_gate_w += sum dscores pscale x ; d_gate_b += sum dscores ; d_pscale[p] += ... */
+UVC_API int uvc_token_gate_fold(const float* patch_w, const float* patch_b, const float* gate_w, int32_t C, int32_t Kp, float* v, float* c1, void* stream);
+UVC_API int uvc_token_gate_fwd(const float* feat, int64_t ldf, int32_t Kf, const float* v, const float* c1, const float* gate_b, const float* pscale,
+                               const float* noise, float tau, int32_t k, int32_t B, int32_t np, float* mask, float* ysoft, float* ls, float* scores,
+                               void* stream);
+UVC_API int uvc_token_gate_bwd(const float* dmask, const float* ysoft, const float* ls, float tau, int32_t B, int32_t np, float* dscores, void* stream);
+UVC_API int uvc_token_gate_apply(const float* dscores, const float* x, const float* gate_w, const float* pscale, int32_t B, int32_t np, int32_t C,
+                                 float* dx, float* d_gate_w, float* d_gate_b, float* d_pscale, void* stream);
 /* dst[i] = round_to_nearest_tf32(src[i])  (weights are rounded once per forward into the workspace) */
 UVC_API int uvc_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 /* y += s * (*s_dev) * x */

@@ -107,6 +107,22 @@ def t2t_tokens(sd, x):
     return F.linear(t, sd[pre + "project.weight"], sd[pre + "project.bias"]), macs
 
 
+def token_gate(sd, pe, noise, tau, k, patch_scale=None):
+    """Token slimming gate of models/model_distilled.py:446-456 with gumbel_softmax :36-63 / scatter :21-33, the Gumbel draw supplied:
+    scores = Linear(C,1)(pe) -> log_softmax -> (+ noise) / tau -> softmax -> one-hot of the top k -> straight-through value; column 0 forced to 1.
+    Returns (mask [B, np] as the reference multiplies it in, y_soft)."""
+    x = pe if patch_scale is None else pe * patch_scale.view(1, -1, 1)
+    B = x.shape[0]
+    scores = F.linear(x, sd["gumbel.weight"], sd["gumbel.bias"]).reshape(B, -1)
+    y_soft = ((F.log_softmax(scores, dim=-1) + noise) / tau).softmax(-1)
+    index = y_soft.topk(k, dim=-1)[1]
+    y_hard = torch.zeros_like(y_soft).scatter_(1, index, 1.0)
+    mask = y_hard - y_soft.detach() + y_soft
+    mask = mask.clone()
+    mask[:, 0] = 1.0
+    return mask, y_soft
+
+
 def forward(sd, x, depth, num_heads, eps=1e-6, blend=None, skip=None, patch_scale=None, token_mask=None, enable_jumping=False, patch=16,
             tokens=None):
     """DistilledVisionTransformer.forward_features + forward, enable_dist == 0 (models/model_distilled.py:429-531).

@@ -163,3 +163,61 @@ def test_admm_step_matches_oracle_on_full_size_layers(model_type, depth):
             close(ul["W1"][l].weight, W1[l], rtol=1e-6, atol=0)
             close(ul["W3"][l].weight, W3[l], rtol=1e-6, atol=0)
     close(glist.acc, torch.cat(st["gate_buf"]).sum(0), rtol=1e-4, atol=1e-7)
+
+
+def test_admm_selections_under_exact_ties_match_reference_golden(golden_dir):
+    """Exactly-zero columns / a dead head / duplicated columns (the state Stage 2 lives in): tests/golden/admm_ties.pt was written by the
+    UNMODIFIED reference (oracle/gen_golden_admm_ties.py).  Case A: every tie group lies entirely inside or outside each selection -> masks must
+    be equal index for index and the trajectory must follow.  Case B: the boundary cuts a group of 100 equal (zero) scores with k = 60 -> torch.topk
+    leaves the choice inside the group unspecified on the CPU; defined (and asserted) are the count taken from the group and everything outside it;
+    this implementation takes the lower indices, as torch.topk does on CUDA."""
+    from oracle.gen_golden_admm_ties import tie_state
+    from uvc_b200.uvc_optimizer import build_minimax_model, uvc_optimizer
+    from uvc_b200.uvc_utils import prune_w_mask
+    G = torch.load(os.path.join(golden_dir, "admm_ties.pt"), weights_only=False)
+    sp = G["spec"]
+    sd, dims = fx.make_state_dict(sp["model_type"], sp["depth"], seed=sp["seed"], wstd=0.05)
+    sd = tie_state(sd, sp["depth"])
+    model = build(sp["model_type"], sp["depth"], sd)
+    args = types.SimpleNamespace(**G["args"])
+    layer_names, uvc_layers, uvc_dict = get_uvc_layers(model)
+    model.eval()
+    with torch.no_grad():
+        _, flops_list = model(torch.ones(1, 3, 224, 224, device="cuda"))
+    mm, dual_opt, s_opt, r_opt, g_opt = build_minimax_model(model, layer_names, uvc_layers, uvc_dict, args, flops_list)
+    model.train(); model.enable_warmup = 0
+    with torch.no_grad():
+        for k in ("s", "r", "y", "p", "z"):
+            getattr(mm, k).copy_(G["init"][k])
+    prune_w_mask(mm)
+    L = sp["depth"]
+    for l in range(L):      # case A: index for index
+        assert torch.equal(uvc_layers["W1"][l].mask.cpu()[0], G["masksA"]["w1"][l]) and (uvc_layers["W1"][l].mask.cpu() == G["masksA"]["w1"][l]).all(), l
+        assert (uvc_layers["W3"][l].mask.cpu() == G["masksA"]["w3"][l]).all(), l
+        assert (uvc_layers["W2"][l].mask.cpu() == G["masksA"]["w2"][l].unsqueeze(1)).all(), l
+    glist = []
+    for step, t in enumerate(G["traj"]):
+        model.block_skip_gating.grad = torch.zeros(L, 2, device="cuda")
+        noises = iter([t["noise1"], t["noise2"]])
+        mm.noise_source = lambda: next(noises)
+        mm.update_gating()
+        cur, s_np, r_np, g_np, glist = uvc_optimizer(FakeOpt(sp["lr"]), mm, s_opt, r_opt, g_opt, dual_opt, args, {}, [], flops_list,
+                                                     args.z_grad_clip, step, args.gating_interval, glist)
+        assert abs(cur - t["cur"]) < 2e-6, (step, cur, t["cur"])
+        for k in ("s", "r", "y", "p", "z"):
+            close(getattr(mm, k), t[k])
+        for l in range(L):
+            for grp, key in (("W1", "w1_sum"), ("W3", "w3_sum")):
+                for a, b in zip(fx.checksum(uvc_layers[grp][l].weight), t[key][l]):
+                    assert abs(a - b) <= 1e-5 * max(1.0, abs(b)), (step, grp, l, a, b)
+    # case B: the cut tie group
+    cb = G["caseB"]
+    with torch.no_grad():
+        mm.s.copy_(cb["s"]); mm.r.copy_(G["init"]["r"])
+    prune_w_mask(mm)
+    for l in range(L):
+        off = uvc_layers["W3"][l].mask.cpu()[0] == 0
+        ref_off = cb["masks_w3"][l] == 0
+        assert int(off.sum()) == cb["k"] == int(ref_off.sum())
+        assert bool(off[cb["tie_group"]].sum() == cb["k"])                       # all taken from the tie group, like the reference
+        assert torch.equal(off.nonzero().flatten(), cb["tie_group"][:cb["k"]])   # and inside it: the lower indices

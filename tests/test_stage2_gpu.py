@@ -154,9 +154,10 @@ def test_patch_gate_mode1_forward_and_gradient():
     assert rel(lh, loh) < LOGIT_TOL
 
 
-def test_token_gate_mode2_indices_exact():
-    """Gumbel top-k token mask (:446-456): with the generator rewound, the kept-token indices equal torch.topk on the same noised
-    scores exactly, k tokens (+ patch 0) are kept per image, and the masked forward equals the oracle under that mask."""
+def test_token_gate_mode2_masked_forward_and_patch_conv_gradient():
+    """Gumbel top-k token mask (:446-456) through the public forward: k tokens (+ patch 0) kept per image, the masked forward equals the oracle
+    under that mask, and the patch conv (run once, engine `pe_in`) gets its gradient in the flat arena.  Index equality with the reference is
+    pinned separately against a reference-written golden (tests/test_token_gate_gpu.py)."""
     from uvc_b200.models.token_gate import token_gate_mask
     mt, depth, B = "deit_tiny_patch16_224", 2, 6
     sd, dims = fx.make_state_dict(mt, depth, seed=9)
@@ -170,22 +171,11 @@ def test_token_gate_mode2_indices_exact():
     assert mask.shape == (B, 196)
     hard = (mask.detach() > 0.5)
     assert (hard[:, 0]).all() and ((hard.sum(1) == k) | (hard.sum(1) == k + 1)).all()
-    # rewind: same exponential draw -> same Gumbel noise -> identical top-k set
-    with torch.no_grad():
-        pe = vo.patch_embed({kk: v.cuda() for kk, v in sd.items()}, xc)
-        scores = F.log_softmax(F.linear(pe, m.gumbel.weight, m.gumbel.bias).reshape(B, -1), dim=-1)
-        torch.manual_seed(123)
-        gum = -torch.empty_like(scores).exponential_().log()
-        idx = ((scores + gum) / tau).softmax(-1).topk(k, dim=-1)[1]
-    want = torch.zeros_like(scores, dtype=torch.bool).scatter_(1, idx, True); want[:, 0] = True
-    agree = (want == hard).float().mean().item()
-    assert agree > 0.999, agree      # scores come from a TF32 GEMM here vs fp32 above: only exact-tie-level flips are tolerated
     torch.manual_seed(123)
     (logits, _), _ = m(xc, tau, 0.9)
     with torch.no_grad():
         lo = vo.forward(sd, x, depth, H, token_mask=hard.float().cpu())
     assert rel(logits, lo) < LOGIT_TOL
-    # backward: the patch conv ran once (engine `pe_in`); its gradients must sit in the flat arena slots AND equal the oracle's under the same mask
     r = torch.randn(B, 1000, generator=torch.Generator().manual_seed(2)) * 0.1
     m.zero_grad(set_to_none=True)
     (logits * r.cuda()).sum().backward()
@@ -199,6 +189,7 @@ def test_token_gate_mode2_indices_exact():
     cos = float(torch.dot(gw.flatten().cpu(), go) / (gw.norm().cpu() * go.norm()))
     print(f"token-gate patch_w grad: cosine vs fixed-mask oracle {cos:.4f}")
     assert cos > 0.95 and rel(m.blocks[0].attn.qkv.weight.grad, sdo["blocks.0.attn.qkv.weight"].grad) < 5e-3
+    assert m.gumbel.weight.grad is not None and float(m.gumbel.weight.grad.abs().max()) > 0
 
 
 def test_full_size_properties():

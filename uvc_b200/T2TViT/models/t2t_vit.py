@@ -139,11 +139,8 @@ class T2T_ViT(DistilledVisionTransformer):
                 pg[0] = 1
             patch_scale = pg.contiguous()
         if tau > 0 and self.enable_patch_gating == 2:
-            scored = pe if patch_scale is None else pe * patch_scale.view(1, -1, 1)
-            scores = F.linear(scored, self.gumbel.weight, self.gumbel.bias).reshape(B, -1)
-            token_mask = gumbel_softmax(F.log_softmax(scores, dim=-1), k=int(ratio * np_), tau=tau, hard=True).clone()
-            token_mask[:, 0] = 1.
-            token_mask = token_mask.contiguous()
+            from ...models.token_gate import token_gate_from_tokens
+            token_mask = token_gate_from_tokens(self, pe, patch_scale, tau, int(ratio * np_))
         blend, skip = self._block_gates()
         params = [p for _, p in _engine_param_list(self)]
         logits = _VitFunction.apply(self, pe.contiguous(), blend, patch_scale, token_mask, skip, *params)

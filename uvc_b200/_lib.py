@@ -92,6 +92,7 @@ EXPORTS = [
     "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
     "uvc_layernorm_fwd_f16", "uvc_layernorm_bwd_f16", "uvc_cvt_f16", "uvc_attention_fwd_f16", "uvc_attention_bwd_f16",
+    "uvc_token_gate_fold", "uvc_token_gate_fwd", "uvc_token_gate_bwd", "uvc_token_gate_apply",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
@@ -120,8 +121,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
+    path = os.environ.get("UVC_LIB_PATH") or _build.LIB_PATH       # UVC_LIB_PATH: bring-up only (an alternative build of the same sources)
+    if path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build_library()
         except Exception as e:  # no nvcc on this box and no prebuilt library
@@ -150,6 +151,10 @@ def load():
         "uvc_cvt_f16": [vp, vp, vp, i32, i32, vp],
         "uvc_attention_fwd_f16": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_attention_bwd_f16": [vp, vp, vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, f32, vp],
+        "uvc_token_gate_fold": [vp, vp, vp, i32, i32, vp, vp, vp],
+        "uvc_token_gate_fwd": [vp, i64, i32, vp, vp, vp, vp, vp, f32, i32, i32, i32, vp, vp, vp, vp, vp],
+        "uvc_token_gate_bwd": [vp, vp, vp, f32, i32, i32, vp, vp],
+        "uvc_token_gate_apply": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp],
         "uvc_softmax_fwd": [vp, i64, i64, i32, i32, vp],
         "uvc_softmax_bwd": [vp, vp, i64, i64, i32, f32, i32, vp],
         "uvc_colsum": [vp, i64, i32, i32, vp, vp, vp],

@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace uvc {
 
@@ -313,7 +314,10 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
 // ====================================================================================================================
 // epilogue warps: 8 (two per TMEM lane quadrant, each half of the BN columns); the GELU / GELU' epilogues at BN = 192 take 12 (three per
 // quadrant, 64 columns each): they are issue-bound on the transcendental math with only two warps per SM sub-partition
-__host__ __device__ constexpr int epi_warps2(int BN, int MODE) { return (BN == 192 && MODE != 0) ? 12 : 8; }
+#ifndef UVC_GELU_EW
+#define UVC_GELU_EW 12
+#endif
+__host__ __device__ constexpr int epi_warps2(int BN, int MODE) { return (BN == 192 && MODE != 0) ? UVC_GELU_EW : 8; }
 __host__ __device__ constexpr int threads2(int BN, int MODE) { return 64 + 32 * epi_warps2(BN, MODE); }
 
 template <int BN, int STAGES, int MODE = 0>
@@ -499,88 +503,131 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
       tc_fence_after();
       if (row_base < p.M) {
         const int rows_left = p.M - row_base - rl;     // row i*4 + rl is valid iff i*4 < rows_left
+        const long long roff = (long long)(row_base + rl);
 #pragma unroll 1
         for (int c = 0; c < Cfg::COLS_PER_WARP / 32; ++c) {
           const int col_t = part * Cfg::COLS_PER_WARP + c * 32;
           const int col0 = nt * BN + col_t;
           if (col0 >= p.N) break;                      // warp-uniform
-          if (flags & (1 << 29)) break;                // bring-up: no epilogue body
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + (uint32_t)col_t, r);
-          tmem_ld_wait();
-          // transpose through the warp's staging tile: lane = row, 16 B chunk index XOR (row & 7)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t addr = st_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
-          }
-          __syncwarp();
           const int gcol = col0 + cc * 4;
           const bool colok = gcol < p.N;               // N % 4 == 0: a float4 is entirely in or out
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (do_bias && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-          const long long roff = (long long)(row_base + rl);
-          float* dptr = p.D + roff * p.ldd + gcol;
-          const float* rptr = p.R + roff * p.ldr + gcol;
-          float* xptr = p.aux + roff * p.ldaux + gcol;
-          __half* xptr16 = reinterpret_cast<__half*>(p.aux) + roff * p.ldaux + gcol;     // UVC_EPI_AUX_F16 view of the same argument
-          float4 rr[8];
-          if (MODE == kEpiGeluBwd) {                   // gelu'(pre-activation) factors, loaded up front (8 independent loads in flight)
-            if (p.aux16) {
+          // Per-row pointers advance by a constant step; every kernel-uniform option (which outputs exist, aux width, residual, rounding, ...) is
+          // tested once per chunk, outside the unrolled row loops, and chunks that lie entirely inside the matrix (all but the last row / column
+          // tile) run without per-access predicates.  The epilogue warps are issue-bound: before this restructuring the loop spent ~60
+          // instructions per output element, two thirds of them address arithmetic, null checks and bounds predicates.
+          float* const dptr = p.D + roff * p.ldd + gcol; const long long dstep = 4 * p.ldd;
+          __half* const d16ptr = reinterpret_cast<__half*>(p.D16) + roff * p.ldd16 + gcol; const long long d16step = 4 * p.ldd16;
+          const float* const rptr = p.R + roff * p.ldr + gcol; const long long rstep = 4 * p.ldr;
+          float* const xptr = p.aux + roff * p.ldaux + gcol;
+          __half* const xptr16 = reinterpret_cast<__half*>(p.aux) + roff * p.ldaux + gcol;     // UVC_EPI_AUX_F16 view of the same argument
+          const long long xstep = 4 * p.ldaux;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN + (uint32_t)col_t;
+          auto chunk = [&](auto interior_c) {
+            constexpr bool INTR = decltype(interior_c)::value;
+            auto ok = [&](int i) { return INTR || (colok && i * 4 < rows_left); };
+            // (a) operand loads that do not depend on the accumulator go first: their latency overlaps the TMEM read and the transpose
+            float4 rr[8];
+            if (MODE == kEpiGeluBwd) {                 // gelu'(pre-activation) factors
+              if (p.aux16) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                uint2 u = make_uint2(0u, 0u);
-                if (colok && i * 4 < rows_left) u = *reinterpret_cast<const uint2*>(xptr16 + (long long)i * 4 * p.ldaux);
-                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                rr[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                for (int i = 0; i < 8; ++i) {
+                  uint2 u = make_uint2(0u, 0u);
+                  if (ok(i)) u = *reinterpret_cast<const uint2*>(xptr16 + i * xstep);
+                  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                  rr[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rr[i] = ok(i) ? *reinterpret_cast<const float4*>(xptr + i * xstep) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
-            } else {
+            } else if (do_res) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(xptr + (long long)i * 4 * p.ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int i = 0; i < 8; ++i) rr[i] = ok(i) ? *reinterpret_cast<const float4*>(rptr + i * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          } else if (do_res) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (do_bias && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            // (b) accumulator chunk: TMEM -> registers -> XOR-swizzled staging tile (lane = row) -> registers in the coalesced layout
+            {
+              uint32_t r[32];
+              tmem_ld_32x32(taddr, r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              rr[i] = (colok && i * 4 < rows_left) ? *reinterpret_cast<const float4*>(rptr + (long long)i * 4 * p.ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);   // fused bias gradient: column sums of this warp's 32 rows
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t addr = st_row + (((uint32_t)j ^ ((uint32_t)lane & 7u)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+              }
+            }
+            __syncwarp();
+            float4 v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 v;
-            const uint32_t addr = ((i & 1) ? ld_odd : ld_even) + i * 512;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-            if (!(colok && i * 4 < rows_left) || (flags & (1 << 30))) continue;   // (bit 30: bring-up, no global traffic)
-            v.x = fmaf(v.x, alpha, b4.x); v.y = fmaf(v.y, alpha, b4.y); v.z = fmaf(v.z, alpha, b4.z); v.w = fmaf(v.w, alpha, b4.w);
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t addr = ((i & 1) ? ld_odd : ld_even) + i * 512;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w) : "r"(addr) : "memory");
+              v[i].x = fmaf(v[i].x, alpha, b4.x); v[i].y = fmaf(v[i].y, alpha, b4.y); v[i].z = fmaf(v[i].z, alpha, b4.z); v[i].w = fmaf(v[i].w, alpha, b4.w);
+            }
+            // (c) the fused epilogue math
             if (MODE == kEpiGelu) {
-              float4 dg;                                 // aux receives gelu'(pre-activation): the same exponential gives both, and the backward
-              gelu_both(v.x, v.x, dg.x); gelu_both(v.y, v.y, dg.y); gelu_both(v.z, v.z, dg.z); gelu_both(v.w, v.w, dg.w);   // epilogue becomes a multiply
-              if (p.aux) {
-                if (p.aux16) *reinterpret_cast<uint2*>(xptr16 + (long long)i * 4 * p.ldaux) = pack_half4(dg.x, dg.y, dg.z, dg.w);
-                else *reinterpret_cast<float4*>(xptr + (long long)i * 4 * p.ldaux) = dg;
+              if (p.aux) {                             // aux receives gelu'(pre-activation): the same exponential gives both, and the backward epilogue becomes a multiply
+                if (p.aux16) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4 dg;
+                    gelu_both(v[i].x, v[i].x, dg.x); gelu_both(v[i].y, v[i].y, dg.y); gelu_both(v[i].z, v[i].z, dg.z); gelu_both(v[i].w, v[i].w, dg.w);
+                    if (ok(i)) *reinterpret_cast<uint2*>(xptr16 + i * xstep) = pack_half4(dg.x, dg.y, dg.z, dg.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4 dg;
+                    gelu_both(v[i].x, v[i].x, dg.x); gelu_both(v[i].y, v[i].y, dg.y); gelu_both(v[i].z, v[i].z, dg.z); gelu_both(v[i].w, v[i].w, dg.w);
+                    if (ok(i)) *reinterpret_cast<float4*>(xptr + i * xstep) = dg;
+                  }
+                }
+              } else {                                 // inference / teacher forward: no derivative
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[i].x = gelu_f(v[i].x); v[i].y = gelu_f(v[i].y); v[i].z = gelu_f(v[i].z); v[i].w = gelu_f(v[i].w); }
               }
             }
             if (MODE == kEpiGeluBwd) {
-              v.x *= rr[i].x; v.y *= rr[i].y; v.z *= rr[i].z; v.w *= rr[i].w;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[i].x *= rr[i].x; v[i].y *= rr[i].y; v[i].z *= rr[i].z; v[i].w *= rr[i].w; }
             } else if (do_res) {
-              v.x = fmaf(beta, rr[i].x, v.x); v.y = fmaf(beta, rr[i].y, v.y); v.z = fmaf(beta, rr[i].z, v.z); v.w = fmaf(beta, rr[i].w, v.w);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[i].x = fmaf(beta, rr[i].x, v[i].x); v[i].y = fmaf(beta, rr[i].y, v[i].y); v[i].z = fmaf(beta, rr[i].z, v[i].z); v[i].w = fmaf(beta, rr[i].w, v[i].w);
+              }
             }
-            if (p.colsum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
-            if (do_round) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-            if (p.D16) *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.D16) + (roff + i * 4) * p.ldd16 + gcol) = pack_half4(v.x, v.y, v.z, v.w);
+            if (p.colsum) {                            // fused bias gradient: column sums of this warp's 32 rows (before any rounding)
+              float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) if (ok(i)) { cs.x += v[i].x; cs.y += v[i].y; cs.z += v[i].z; cs.w += v[i].w; }
+              // lanes with the same cc hold the same 4 columns: fold the 4 row phases, one red per 4 columns
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+              if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x * cs_scale, cs.y * cs_scale, cs.z * cs_scale, cs.w * cs_scale);
+            }
+            if (do_round) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { v[i].x = round_tf32(v[i].x); v[i].y = round_tf32(v[i].y); v[i].z = round_tf32(v[i].z); v[i].w = round_tf32(v[i].w); }
+            }
+            // (d) stores
+            if (p.D16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) if (ok(i)) *reinterpret_cast<uint2*>(d16ptr + i * d16step) = pack_half4(v[i].x, v[i].y, v[i].z, v[i].w);
+            }
             if (p.D) {
-              float* dp = dptr + (long long)i * 4 * p.ldd;
-              if (do_atomic) red_add_v4(dp, v.x, v.y, v.z, v.w);
-              else *reinterpret_cast<float4*>(dp) = v;
+              if (do_atomic) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (ok(i)) red_add_v4(dptr + i * dstep, v[i].x, v[i].y, v[i].z, v[i].w);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (ok(i)) *reinterpret_cast<float4*>(dptr + i * dstep) = v[i];
+              }
             }
-          }
-          if (p.colsum) {                              // lanes with the same cc hold the same 4 columns: fold the 4 row phases, one red per 4 columns
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-            if (rl == 0 && colok) red_add_v4(p.colsum + gcol, cs.x * cs_scale, cs.y * cs_scale, cs.z * cs_scale, cs.w * cs_scale);
-          }
+          };
+          if (row_base + 32 <= p.M && col0 + 32 <= p.N) chunk(std::true_type{}); else chunk(std::false_type{});
           __syncwarp();                                // staging tile is rewritten by the next chunk
         }
       }
@@ -879,7 +926,6 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.colsum = (a.flags & UVC_EPI_COLSUM) ? a.colsum : nullptr;
   kp.alpha = a.alpha; kp.beta = a.beta; kp.colsum_scale = (a.colsum_scale != 0.0f) ? a.colsum_scale : 1.0f;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.nb1 = a.nb1; kp.nb2 = a.nb2; kp.splits = splits; kp.flags = a.flags;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("UVC_GEMM_DBG"); dbg = e ? atoi(e) : 0; } kp.flags |= dbg << 29; }   // bring-up experiments only
   kp.a_mn = a.A.mn_major ? 1 : 0; kp.b_mn = a.B.mn_major ? 1 : 0;
   kp.a_use1 = a.A.bs1 != 0; kp.a_use2 = a.A.bs2 != 0; kp.b_use1 = a.B.bs1 != 0; kp.b_use2 = a.B.bs2 != 0;
 

@@ -55,6 +55,14 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
 int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
                       float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f, const float* db_scale_dev = nullptr);
 
+// token slimming gate (token_gate.cu)
+int token_gate_fold(const float* patch_w, const float* patch_b, const float* gate_w, int C, int Kp, float* v, float* c1, cudaStream_t st);
+int token_gate_fwd(const float* F, long long ldf, int Kf, const float* v, const float* c1, const float* gate_b, const float* pscale, const float* noise,
+                   float tau, int k, int B, int np, float* mask, float* ysoft, float* ls, float* scores, cudaStream_t st);
+int token_gate_bwd(const float* dmask, const float* ysoft, const float* ls, float tau, int B, int np, float* dscores, cudaStream_t st);
+int token_gate_apply(const float* dscores, const float* x, const float* gate_w, const float* pscale, int B, int np, int C, float* dx, float* d_gate_w,
+                     float* d_gate_b, float* d_pscale, cudaStream_t st);
+
 // ---- helpers to describe GEMM operands tersely
 inline uvc_operand op_k(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 0, 0}; }
 inline uvc_operand op_mn(const float* p, long long ld, long long bs1 = 0, long long bs2 = 0) { return uvc_operand{p, ld, bs1, bs2, 1, 0}; }

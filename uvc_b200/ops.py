@@ -225,6 +225,38 @@ def assemble_tokens_bwd(g, pe, pscale=None, tmask=None, want_dpos=True):
     return dpe, dscale, dtmask, dpos, dcls
 
 
+def token_gate_fold(patch_w, patch_b, gate_w):
+    """(v [Kp], c1 [1]) with scores = feat . v + c1 equal to Linear(C,1)(conv(x)) in fp32"""
+    C_ = patch_w.shape[0]
+    w2 = patch_w.reshape(C_, -1)
+    v = torch.empty(w2.shape[1], device=patch_w.device)
+    c1 = torch.empty(1, device=patch_w.device)
+    _call("uvc_token_gate_fold", _p(w2), _p(patch_b), _p(gate_w), C_, w2.shape[1], _p(v), _p(c1))
+    return v, c1
+
+
+def token_gate_fwd(feat, v, c1, gate_b, pscale, noise, tau, k, B, np_, want_saved=True):
+    """-> (mask [B,np], ysoft, ls, scores): Gumbel top-k straight-through token mask, fp32 scores from `feat` rows"""
+    Kf = feat.shape[-1]
+    dev = feat.device
+    mask = torch.empty(B, np_, device=dev)
+    ysoft, ls, scores = (torch.empty(B, np_, device=dev) for _ in range(3)) if want_saved else (None, None, None)
+    _call("uvc_token_gate_fwd", _p(feat), Kf, Kf, _p(v), _p(c1), _p(gate_b), _p(pscale), _p(noise), float(tau), int(k), B, np_, _p(mask), _p(ysoft), _p(ls), _p(scores))
+    return mask, ysoft, ls, scores
+
+
+def token_gate_bwd(dmask, ysoft, ls, tau):
+    B, np_ = ysoft.shape
+    ds = torch.empty_like(ysoft)
+    _call("uvc_token_gate_bwd", _p(dmask), _p(ysoft), _p(ls), float(tau), B, np_, _p(ds))
+    return ds
+
+
+def token_gate_apply_(dscores, x, gate_w, pscale, dx, d_gate_w, d_gate_b=None, d_pscale=None):
+    B, np_, C_ = x.shape
+    _call("uvc_token_gate_apply", _p(dscores), _p(x), _p(gate_w), _p(pscale), B, np_, C_, _p(dx), _p(d_gate_w), _p(d_gate_b), _p(d_pscale))
+
+
 def scale_add_(y, x, s=1.0, s_dev=None):
     _call("uvc_scale_add", _p(y), _p(x), _p(s_dev), float(s), y.numel())
     return y
