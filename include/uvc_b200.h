@@ -240,6 +240,14 @@ UVC_API int uvc_distill_loss(const float* logits, const float* teacher_logits, c
  * multiplies the update so masked weights stay exactly 0 (Stage 2, post_train.py:357-360).
  */
 UVC_API int uvc_sqnorm_accum(const float* g, int64_t n, float* acc, void* stream);
+/* Flat-arena variants with one option byte per element (arenas 16 B aligned, n % 4 == 0), so the WHOLE model stays one launch each also in
+ * Stage 2 (post_train.py:357-379: re-masked weights, timm's decay / no-decay parameter groups) and with tenants that have no gradient:
+ *   bit 0 keep   (0: pruned weight -- updated like the reference's AdamW does, then forced back to exactly 0 = the next step's `weight *= mask`),
+ *   bit 1 decay  (decoupled weight decay applies), bit 2 active (0: no gradient this step -- frozen parameter or hard-skipped block: untouched
+ *   and excluded from the clip norm, as a `.grad is None` parameter is in torch). */
+UVC_API int uvc_sqnorm_accum_flags(const float* g, const uint8_t* flags, int64_t n, float* acc, void* stream);
+UVC_API int uvc_clip_adamw_flags(float* p, float* g, float* m, float* v, const uint8_t* flags, int64_t n, const float* sqnorm_acc, float max_norm,
+                                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 UVC_API int uvc_clip_adamw(float* p, float* g, float* m, float* v, const float* mask, int64_t n, const float* sqnorm_acc, float max_norm,
                            float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
 

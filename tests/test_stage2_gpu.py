@@ -53,9 +53,11 @@ def synthetic_layout(sd, depth, H, d=64, heads_pruned=1, dims_pruned=16, neurons
     return masks
 
 
-def test_stage2_step_masked_update_and_hard_skip():
+@pytest.mark.parametrize("flat", [False, True])
+def test_stage2_step_masked_update_and_hard_skip(flat):
     """one post_train step on a fixed layout: block 1 hard-skipped, masked weights stay EXACTLY zero, the live weights follow
-    clip_grad_norm_ + AdamW on the reference's semantics (weight *= mask before the step, full-gradient clip norm)."""
+    clip_grad_norm_ + AdamW on the reference's semantics (weight *= mask before the step, full-gradient clip norm).
+    flat: parameters in the model's flat arena -> the whole update must be ONE sweep (option byte per element: mask / decay group / inactive)."""
     from uvc_b200 import ops
     from uvc_b200.post_train import apply_masks, param_groups_weight_decay
     from uvc_b200.utils.optim import FusedClipAdamW
@@ -64,6 +66,8 @@ def test_stage2_step_masked_update_and_hard_skip():
     sd["block_skip_gating"][1] = torch.tensor([1.0, -1.0])                    # gate prefers "skip" for block 1 (:496-500)
     H = dims["num_heads"]
     m = build(mt, depth, sd, gumbel_hard=True).train()
+    if flat:
+        m.flatten_parameters()
     for _, mod in m.named_modules():
         if hasattr(mod, "weight"):
             mod.register_buffer("mask", torch.ones_like(mod.weight))
@@ -95,8 +99,15 @@ def test_stage2_step_masked_update_and_hard_skip():
     assert rel(logits, lo) < LOGIT_TOL
     parts, dl = ops.distill_loss(logits.detach(), t_logits.cuda(), tgt.cuda(), 0.1, 1.0)
     logits.backward(dl)
-    assert m.blocks[1].mlp.fc1.weight.grad is None or float(m.blocks[1].mlp.fc1.weight.grad.abs().max()) == 0.0
+    assert m.blocks[1].mlp.fc1.weight.grad is None          # a skipped block is outside the graph (reference :496-500): no gradient, no decay
+    w_skipped = m.blocks[1].mlp.fc1.weight.detach().clone()
+    from uvc_b200 import _lib
+    n0 = _lib.load().uvc_launch_count()
     opt.step()
+    launches = _lib.load().uvc_launch_count() - n0
+    assert torch.equal(m.blocks[1].mlp.fc1.weight.detach(), w_skipped)
+    if flat:
+        assert opt._flat is not None and launches <= 2 + 2 * 2, launches     # norm + update over the arena (+ the two gumbel.* tensors outside it)
     names = [k for k, p in m.named_parameters() if p.requires_grad and sdr[k].grad is not None]
     ps = [sdr[k].detach().clone() for k in names]
     gs = [sdr[k].grad for k in names]

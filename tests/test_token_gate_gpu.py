@@ -34,7 +34,7 @@ def test_kept_token_indices_equal_reference_golden(golden, name, monkeypatch):
     g = golden[name]; sp = g["spec"]
     m, sd, dims = build(sp, g)
     x, _ = fx.make_batch(sp["B"], seed=sp["batch_seed"])
-    assert fx.checksum(x) == g["x_sum"]
+    assert all(abs(a - b) <= 1e-9 * max(1.0, abs(b)) for a, b in zip(fx.checksum(x), g["x_sum"]))     # fp64 sums: summation order differs between CPUs
     k = int(sp["ratio"] * 196)
     monkeypatch.setattr(tg, "gumbel_noise_like", lambda B, np_, device: g["noise"].to(device))
     pe, mask = tg.token_gate_mask(m, x.cuda(), None, sp["tau"], k)
@@ -83,4 +83,6 @@ def test_gate_gradients_match_autograd_of_the_oracle_restatement(golden):
     mask = _TokenGateFn.apply(pe.detach(), w.detach().reshape(-1).contiguous(), None, pe, None, w, b, g["noise"].cuda(), sp["tau"], k)
     assert torch.equal(mask.detach().cpu() > 0.5, mask_r.detach() > 0.5)
     (mask * up.cuda()).sum().backward()
-    assert rel(pe.grad, pe_r.grad) < 1e-4 and rel(w.grad, w_r.grad) < 1e-4 and rel(b.grad, b_r.grad) < 1e-4
+    assert rel(pe.grad, pe_r.grad) < 1e-4 and rel(w.grad, w_r.grad) < 1e-4
+    # log_softmax is shift invariant: the bias gradient is analytically zero, both sides hold rounding noise only
+    assert float(b.grad.abs().max()) < 1e-5 * float(w.grad.abs().max()) and float(b_r.grad.abs().max()) < 1e-5 * float(w_r.grad.abs().max())

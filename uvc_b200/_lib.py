@@ -89,7 +89,7 @@ EXPORTS = [
     "uvc_version", "uvc_last_error", "uvc_abi_sizeof", "uvc_launch_count", "uvc_gemm_profile", "uvc_gemm_profile_read", "uvc_gemm_profile_read_kind", "uvc_gemm_tf32",
     "uvc_layernorm_fwd", "uvc_layernorm_bwd", "uvc_layernorm_bwd_cs", "uvc_softmax_fwd", "uvc_softmax_bwd", "uvc_colsum", "uvc_blend_fwd",
     "uvc_blend_dots", "uvc_im2col16", "uvc_assemble_tokens", "uvc_assemble_tokens_bwd", "uvc_round_tf32", "uvc_scale_add",
-    "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw",
+    "uvc_attn_ldp", "uvc_attention_fwd", "uvc_attention_bwd", "uvc_attention_fwd_lse", "uvc_attention_bwd_fused", "uvc_distill_loss", "uvc_sqnorm_accum", "uvc_clip_adamw", "uvc_sqnorm_accum_flags", "uvc_clip_adamw_flags",
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
     "uvc_layernorm_fwd_f16", "uvc_layernorm_bwd_f16", "uvc_cvt_f16", "uvc_attention_fwd_f16", "uvc_attention_bwd_f16",
     "uvc_token_gate_fold", "uvc_token_gate_fwd", "uvc_token_gate_bwd", "uvc_token_gate_apply",
@@ -171,6 +171,8 @@ def load():
         "uvc_attention_bwd_fused": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_distill_loss": [vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp],
         "uvc_sqnorm_accum": [vp, i64, vp, vp],
+        "uvc_sqnorm_accum_flags": [vp, vp, i64, vp, vp],
+        "uvc_clip_adamw_flags": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],
         "uvc_clip_adamw": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],
         "uvc_vit_forward": [C.POINTER(VitForwardArgs), vp],
         "uvc_vit_backward": [C.POINTER(VitBackwardArgs), vp],

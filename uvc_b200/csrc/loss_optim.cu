@@ -152,6 +152,60 @@ __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, 
   }
 }
 
+// Per-element option bytes for the flat-arena sweep (one launch for the whole model also in Stage 2 and with frozen tenants):
+//   bit 0  keep   : 0 = the weight is pruned (mask 0): it is updated like any other (moments included) and then forced back to exactly 0
+//   bit 1  decay  : decoupled weight decay applies (timm's param groups: matrices yes, biases / norms / tokens no)
+//   bit 2  active : 0 = no gradient this step (frozen parameter, hard-skipped block): p, m, v untouched, excluded from the clip norm
+__global__ void __launch_bounds__(256) sqnorm_flags_kernel(const float* __restrict__ g, const uint8_t* __restrict__ flags, long long n, float* __restrict__ acc) {
+  float s = 0.f;
+  const long long n4 = n >> 2;        // arenas are 16-byte aligned and padded to 4 elements
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    const uchar4 f = reinterpret_cast<const uchar4*>(flags)[i];
+    s += ((f.x & 4) ? v.x * v.x : 0.f) + ((f.y & 4) ? v.y * v.y : 0.f) + ((f.z & 4) ? v.z * v.z : 0.f) + ((f.w & 4) ? v.w * v.w : 0.f);
+  }
+  __shared__ float sh[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    atomicAdd(acc, t);
+  }
+}
+
+__device__ __forceinline__ void adam_one_f(float& p, float& g, float& m, float& v, unsigned f, float coef, const AdamHyper& h) {
+  if (!(f & 4u)) return;
+  g *= coef;
+  if (f & 2u) p *= 1.0f - h.lr * h.wd;
+  m = m + (g - m) * (1.0f - h.beta1);
+  v = v * h.beta2 + (1.0f - h.beta2) * g * g;
+  const float denom = sqrtf(v) / h.bc2_sqrt + h.eps;
+  p -= (h.lr / h.bc1) * (m / denom);
+  if (!(f & 1u)) p = 0.0f;
+}
+
+__global__ void __launch_bounds__(256) clip_adamw_flags_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                               const uint8_t* __restrict__ flags, long long n, const float* __restrict__ acc, AdamHyper h) {
+  float coef = 1.0f;
+  if (h.max_norm > 0.f && acc) {
+    const float nrm = sqrtf(__ldg(acc));
+    coef = fminf(h.max_norm / (nrm + 1e-6f), 1.0f);
+  }
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uchar4 f = reinterpret_cast<const uchar4*>(flags)[i];
+    if (!((f.x | f.y | f.z | f.w) & 4)) continue;          // whole vector inactive (a skipped block's weights): no traffic beyond the flag bytes
+    float4 pv = reinterpret_cast<float4*>(p)[i], gv = reinterpret_cast<float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    adam_one_f(pv.x, gv.x, mv.x, vv.x, f.x, coef, h); adam_one_f(pv.y, gv.y, mv.y, vv.y, f.y, coef, h);
+    adam_one_f(pv.z, gv.z, mv.z, vv.z, f.z, coef, h); adam_one_f(pv.w, gv.w, mv.w, vv.w, f.w, coef, h);
+    reinterpret_cast<float4*>(p)[i] = pv; reinterpret_cast<float4*>(g)[i] = gv;
+    reinterpret_cast<float4*>(m)[i] = mv; reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
 static inline int blocks_for(long long n, int per_thread_elems) {
   long long b = (n / per_thread_elems + 255) / 256;
   const long long cap = 148 * 8;
@@ -178,8 +232,39 @@ int clip_adamw(float* p, float* g, float* m, float* v, const float* mask, long l
   return check_launch("clip_adamw");
 }
 
+int sqnorm_accum_flags(const float* g, const uint8_t* flags, long long n, float* acc, cudaStream_t st) {
+  UVC_REQUIRE((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(flags)) & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+              UVC_ERR_BAD_SHAPE, "sqnorm_accum_flags: arenas must be 16 B aligned with a length that is a multiple of 4");
+  if (n <= 0) return UVC_OK;
+  sqnorm_flags_kernel<<<blocks_for(n, 4), 256, 0, st>>>(g, flags, n, acc);
+  return check_launch("sqnorm_accum_flags");
+}
+
+int clip_adamw_flags(float* p, float* g, float* m, float* v, const uint8_t* flags, long long n, const float* acc, float max_norm, float lr, float beta1,
+                     float beta2, float eps, float wd, int step, cudaStream_t st) {
+  UVC_REQUIRE(step >= 1, UVC_ERR_BAD_ARG, "clip_adamw_flags: step must be >= 1 (got %d)", step);
+  UVC_REQUIRE((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(flags) & 3) == 0, UVC_ERR_BAD_SHAPE, "clip_adamw_flags: arenas must be 16 B aligned with a length that is a multiple of 4");
+  if (n <= 0) return UVC_OK;
+  AdamHyper h;
+  h.max_norm = max_norm; h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.wd = wd;
+  h.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  h.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  clip_adamw_flags_kernel<<<blocks_for(n, 4), 256, 0, st>>>(p, g, m, v, flags, n, acc, h);
+  return check_launch("clip_adamw_flags");
+}
+
 }  // namespace uvc
 
+extern "C" int uvc_sqnorm_accum_flags(const float* g, const uint8_t* flags, int64_t n, float* acc, void* stream) {
+  UVC_REQUIRE(g && flags && acc, UVC_ERR_BAD_ARG, "uvc_sqnorm_accum_flags: NULL pointer");
+  return uvc::sqnorm_accum_flags(g, flags, n, acc, static_cast<cudaStream_t>(stream));
+}
+extern "C" int uvc_clip_adamw_flags(float* p, float* g, float* m, float* v, const uint8_t* flags, int64_t n, const float* sqnorm_acc, float max_norm, float lr,
+                                    float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+  UVC_REQUIRE(p && g && m && v && flags, UVC_ERR_BAD_ARG, "uvc_clip_adamw_flags: NULL pointer");
+  return uvc::clip_adamw_flags(p, g, m, v, flags, n, sqnorm_acc, max_norm, lr, beta1, beta2, eps, weight_decay, step, static_cast<cudaStream_t>(stream));
+}
 extern "C" int uvc_distill_loss(const float* logits, const float* teacher_logits, const float* targets, int32_t B, int32_t NC, float alpha, float T,
                                 float grad_scale, float* loss_out, float* dlogits, void* stream) {
   UVC_REQUIRE(logits && targets && loss_out, UVC_ERR_BAD_ARG, "uvc_distill_loss: NULL pointer");

@@ -234,6 +234,10 @@ class _VitFunction(torch.autograd.Function):
         grads, d_blend, d_ps, d_tm, d_pe = ctx.model._engine_backward(ctx.B, dlogits.contiguous(), blend, patch_scale, token_mask, ctx.skip,
                                                                       ctx.pe_mode)
         out = [g if (g is not None and req) else None for g, req in zip(grads, ctx.param_requires)]
+        if ctx.skip is not None:        # a hard-skipped block is outside the graph: its parameters get no gradient (reference :496-500), so the
+            for i, sk in enumerate(ctx.skip):     # optimiser neither decays nor moves them
+                if sk:
+                    out[8 + 12 * i: 8 + 12 * (i + 1)] = [None] * 12
         if ctx.pe_mode:
             out[0] = out[1] = None      # patch conv ran outside the engine: whoever produced the embeddings owns those two gradients
         return (None, d_pe, d_blend, d_ps, d_tm, None, *out)

@@ -337,3 +337,15 @@ def sqnorm_accum_(g, acc):
 def clip_adamw_(p, g, m, v, sqnorm_acc, max_norm, lr, beta1, beta2, eps, weight_decay, step, mask=None):
     _call("uvc_clip_adamw", _p(p), _p(g), _p(m), _p(v), _p(mask), p.numel(), _p(sqnorm_acc), float(max_norm), float(lr),
           float(beta1), float(beta2), float(eps), float(weight_decay), int(step))
+
+
+def sqnorm_accum_flags_(g, flags, acc):
+    _call("uvc_sqnorm_accum_flags", _p(g), flags.data_ptr(), g.numel(), _p(acc))
+    return acc
+
+
+def clip_adamw_flags_(p, g, m, v, flags, sqnorm_acc, max_norm, lr, beta1, beta2, eps, weight_decay, step):
+    """flat-arena sweep with one option byte per element: bit 0 keep (mask), bit 1 decay, bit 2 active"""
+    assert flags.dtype == torch.uint8 and flags.numel() == p.numel()
+    _call("uvc_clip_adamw_flags", _p(p), _p(g), _p(m), _p(v), flags.data_ptr(), p.numel(), _p(sqnorm_acc), float(max_norm), float(lr),
+          float(beta1), float(beta2), float(eps), float(weight_decay), int(step))

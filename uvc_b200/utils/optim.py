@@ -27,30 +27,61 @@ class FusedClipAdamW(Optimizer):
         self.last_sqnorm = None       # device scalar: squared global gradient norm of the last step (before clipping)
 
     # ---- flat fast path ------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._flat = None            # the flat moment arenas are rebuilt from the freshly loaded per-parameter state
+
     def _flat_ready(self):
+        """One launch for the norm and one for the update over the model's flat arenas -- also with Stage 2's masks and decay / no-decay
+        parameter groups (post_train.py:299, timm create_optimizer) and with tenants that have no gradient (frozen T2T pos_embed, the weights
+        of hard-skipped blocks): those differences are one option byte per element (uvc_clip_adamw_flags)."""
         m = self.model
-        if m is None or m.flat_param is None or len(self.param_groups) != 1 or self.masks:
+        if m is None or m.flat_param is None:
             return None
         eng = m.engine_parameters()
         fg = m.flat_grad
-        ids = {id(p) for p in self.param_groups[0]['params']}
-        if any(id(p) not in ids for p in eng):
+        gid = {id(p): g for g in self.param_groups for p in g['params']}
+        g0 = self.param_groups[0]
+        if any((g['lr'], tuple(g['betas']), g['eps']) != (g0['lr'], tuple(g0['betas']), g0['eps']) for g in self.param_groups):
+            return None
+        wds = {float(g['weight_decay']) for g in self.param_groups if g['weight_decay']}
+        if len(wds) > 1:
             return None
         lo, hi = fg.data_ptr(), fg.data_ptr() + fg.numel() * 4
-        if any(p.grad is None or not (lo <= p.grad.data_ptr() < hi) for p in eng):
+        active = []
+        for p in eng:
+            a = id(p) in gid and p.grad is not None
+            if a and not (lo <= p.grad.data_ptr() < hi):
+                return None          # a gradient that does not live in the arena (set by hand): per-tensor path
+            active.append(a)
+        if not any(active):
             return None
-        if self._flat is None or self._flat["p"].data_ptr() != m.flat_param.data_ptr():
-            fm, fv = torch.zeros_like(m.flat_param), torch.zeros_like(m.flat_param)
+        sig = (m.flat_param.data_ptr(), tuple(active), tuple(id(self.masks.get(p)) for p in eng), tuple(bool(gid[id(p)]['weight_decay']) if id(p) in gid else False for p in eng))
+        if self._flat is None or self._flat["sig"] != sig:
+            old = self._flat
+            if old is not None and old["p"].data_ptr() == m.flat_param.data_ptr():
+                fm, fv = old["m"], old["v"]
+            else:
+                fm, fv = torch.zeros_like(m.flat_param), torch.zeros_like(m.flat_param)
+            flags = torch.zeros(m.flat_param.numel(), dtype=torch.uint8, device=m.flat_param.device)
             off = 0
-            for p in eng:       # expose per-parameter views so state_dict() has the usual exp_avg / exp_avg_sq entries
+            for p, a in zip(eng, active):     # expose per-parameter views so state_dict() has the usual exp_avg / exp_avg_sq entries
                 n = p.numel()
                 st = self.state[p]
-                if "exp_avg" in st:
+                if "exp_avg" in st and st["exp_avg"].data_ptr() != fm[off:off + n].data_ptr():
                     fm[off:off + n].copy_(st["exp_avg"].reshape(-1)); fv[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
                 st["exp_avg"], st["exp_avg_sq"] = fm[off:off + n].view(p.shape), fv[off:off + n].view(p.shape)
                 st.setdefault("step", 0)
+                if a:
+                    bits = 4 | (2 if gid[id(p)]['weight_decay'] else 0)
+                    mask = self.masks.get(p)
+                    if mask is None:
+                        flags[off:off + n] = bits | 1
+                    else:
+                        flags[off:off + n] = (mask.reshape(-1) != 0).to(torch.uint8) | bits
                 off += (n + 3) // 4 * 4
-            self._flat = {"p": m.flat_param, "m": fm, "v": fv, "ids": {id(p) for p in eng}}
+            self._flat = {"p": m.flat_param, "m": fm, "v": fv, "ids": {id(p) for p in eng}, "flags": flags, "sig": sig,
+                          "wd": (wds.pop() if wds else 0.0), "active": [p for p, a in zip(eng, active) if a]}
         return self._flat
 
     @torch.no_grad()
@@ -74,7 +105,7 @@ class FusedClipAdamW(Optimizer):
         acc = self._acc
         acc.zero_()
         if flat is not None:
-            ops.sqnorm_accum_(self.model.flat_grad, acc)
+            ops.sqnorm_accum_flags_(self.model.flat_grad, flat["flags"], acc)
         for p, _ in todo:
             if not p.grad.is_contiguous():
                 p.grad = p.grad.contiguous()
@@ -82,12 +113,11 @@ class FusedClipAdamW(Optimizer):
         self.last_sqnorm = acc
         if flat is not None:
             g = self.param_groups[0]
-            st0 = self.state[self.model.engine_parameters()[0]]
-            step = int(st0["step"]) + 1
-            for p in self.model.engine_parameters():
+            step = int(self.state[flat["active"][0]]["step"]) + 1
+            for p in flat["active"]:
                 self.state[p]["step"] = step
-            ops.clip_adamw_(flat["p"], self.model.flat_grad, flat["m"], flat["v"], acc, self.max_grad_norm, g['lr'], g['betas'][0], g['betas'][1],
-                            g['eps'], g['weight_decay'], step)
+            ops.clip_adamw_flags_(flat["p"], self.model.flat_grad, flat["m"], flat["v"], flat["flags"], acc, self.max_grad_norm, g['lr'], g['betas'][0],
+                                  g['betas'][1], g['eps'], flat["wd"], step)
         for p, g in todo:
             st = self.state[p]
             if "exp_avg" not in st:
