@@ -69,10 +69,12 @@ __global__ void __launch_bounds__(kThreadsA, 1) attn16_fwd_kernel(const __grid_c
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                                          // on-chip setup above overlaps the previous kernel's tail
   const int nheads = p.B * p.H;
   const int ntiles = p.ntiles;
   constexpr uint32_t kO = 2 * kNK;               // O accumulator columns [416, 480)
@@ -361,10 +363,12 @@ __global__ void __launch_bounds__(kThreadsA, 1) attn16_bwd_kernel(const __grid_c
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), 512);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                                          // on-chip setup above overlaps the previous kernel's tail
   const int nheads = p.B * p.H, ntiles = p.ntiles;
   constexpr uint32_t kX = 0, kY = kNK, kAcc = 2 * kNK, kAcc2 = 64;     // TMEM columns (kAcc2: inside X, free once the elementwise pass has read it)
 
@@ -581,6 +585,8 @@ __global__ void __launch_bounds__(kThreadsA, 1) attn16_bwd_kernel(const __grid_c
 
 // D[b,h,row] = sum_j dO[row, h*64 + j] * O[row, h*64 + j]   (one warp per token row; 8 lanes x 8 halves cover one head)
 __global__ void __launch_bounds__(256) attn16_rowdot_kernel(const __half* __restrict__ dO, const __half* __restrict__ O, float* __restrict__ Dv, int B, int H, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= (long long)B * N) return;
@@ -639,7 +645,7 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
   UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn16_fwd smem=%d): %s", kFSmem, cudaGetErrorString(e));
   const int sms = sm_count();
   const int grid = B * H < sms ? B * H : sms;
-  attn16_fwd_kernel<<<grid, kThreadsA, kFSmem, st>>>(kp);
+  launch_pdl(attn16_fwd_kernel, dim3(grid), dim3(kThreadsA), kFSmem, st, kp);
   return check_launch("attn16_fwd_kernel");
 }
 
@@ -650,7 +656,7 @@ int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, co
   const __half* q = static_cast<const __half*>(qkv16);
   const __half* k = q + C; const __half* v = q + 2 * C;
   __half* dq = static_cast<__half*>(dqkv16);
-  attn16_rowdot_kernel<<<(unsigned)(((long long)B * N + 7) / 8), 256, 0, st>>>(static_cast<const __half*>(dctx16), static_cast<const __half*>(ctx16), Dv, B, H, N);
+  launch_pdl(attn16_rowdot_kernel, dim3((unsigned)(((long long)B * N + 7) / 8)), dim3(256), 0, st, static_cast<const __half*>(dctx16), static_cast<const __half*>(ctx16), Dv, B, H, N);
   int rc = check_launch("attn16_rowdot_kernel");
   if (rc) return rc;
   const int sms = sm_count();
@@ -668,7 +674,7 @@ int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, co
   if ((rc = attn16_tmap(&kp.tmB1, v, ld3, B, H, N, kNK, "attn16 bwd V"))) return rc;
   kp.out0 = dq; kp.out1 = nullptr;
   kp.db0 = dqkv_bias; kp.db1 = nullptr;
-  attn16_bwd_kernel<1><<<grid, kThreadsA, kBSmem, st>>>(kp);
+  launch_pdl(attn16_bwd_kernel<1>, dim3(grid), dim3(kThreadsA), kBSmem, st, kp);
   if ((rc = check_launch("attn16_bwd_kernel<1>"))) return rc;
   // phase 2: dK, dV
   if ((rc = attn16_tmap(&kp.tmA0, k, ld3, B, H, N, 128, "attn16 bwd K tile"))) return rc;
@@ -677,7 +683,7 @@ int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, co
   if ((rc = attn16_tmap(&kp.tmB1, dctx16, C, B, H, N, kNK, "attn16 bwd dO"))) return rc;
   kp.out0 = dq + 2 * C; kp.out1 = dq + C;
   kp.db0 = dqkv_bias ? dqkv_bias + 2 * C : nullptr; kp.db1 = dqkv_bias ? dqkv_bias + C : nullptr;
-  attn16_bwd_kernel<2><<<grid, kThreadsA, kBSmem, st>>>(kp);
+  launch_pdl(attn16_bwd_kernel<2>, dim3(grid), dim3(kThreadsA), kBSmem, st, kp);
   return check_launch("attn16_bwd_kernel<2>");
 }
 

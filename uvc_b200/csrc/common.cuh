@@ -21,6 +21,26 @@ void prof_end(cudaStream_t st);
 #define UVC_REQUIRE(cond, code, ...)                                   \
   do { if (!(cond)) { ::uvc::set_error(__VA_ARGS__); return (code); } } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The engine enqueues ~35 dependent kernels per transformer block; with plain stream order each one pays the launch latency and its own
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) after its predecessor has fully drained.  Kernels launched through
+// launch_pdl() may become resident while the predecessor's last CTAs are still running: everything before pdl_wait() must not touch global
+// memory that another kernel writes; pdl_wait() returns once the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();      // UVC_PDL=0 switches the launch attribute off (bring-up A/B)
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through check_launch() (cudaGetLastError)
+}
+
 // ---------------------------------------------------------------- small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -1,6 +1,7 @@
 // Error plumbing + ABI introspection for libuvc_sm100.so.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <vector>
@@ -14,6 +15,12 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("UVC_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on != 0;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -92,10 +92,12 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), BN);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                                          // everything above is on-chip setup; operands / outputs belong to the stream order
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -366,10 +368,12 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     fence_proxy_async();
   }
   if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), Cfg::TMEM_COLS);
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();                                          // everything above is on-chip setup; operands / outputs belong to the stream order
 
   const int tiles = p.m_tiles * p.n_tiles;
   const int bke = p.f16 ? 2 * BK : BK;                 // elements per 128-byte k-block row: 32 fp32 or 64 fp16
@@ -768,7 +772,7 @@ static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm_tf32_kernel<BN, STAGES><<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(kp);
+  launch_pdl(gemm_tf32_kernel<BN, STAGES>, grid, dim3(kThreads), Cfg::SMEM_BYTES, st, kp);
   return check_launch("gemm_tf32_kernel");
 }
 
@@ -782,7 +786,7 @@ static int launch2k(const GemmKParams& kp, int pairs, cudaStream_t st) {
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE><<<dim3(2 * pairs), threads2(BN, MODE), Cfg::SMEM_BYTES, st>>>(kp);
+  launch_pdl(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE>, dim3(2 * pairs), dim3(threads2(BN, MODE)), Cfg::SMEM_BYTES, st, kp);
   return check_launch("gemm2_tf32_kernel");
 }
 template <int BN, int STAGES, bool A_MN, bool B_MN>

@@ -31,6 +31,8 @@ template <int NV, bool Y16>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, float* __restrict__ y, long long ldy,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out, int M, int C, int rnd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(c
                                                             float dy_scale, __half* __restrict__ dx16, float out_scale,
                                                             const float* __restrict__ scales_dev) {
   __shared__ float red[4][8][32 * 4 + 4];
+  pdl_launch_dependents();
+  pdl_wait();
   if (scales_dev) { out_scale *= __ldg(scales_dev); dy_scale *= __ldg(scales_dev + 1); }     // {S, 1/S} chosen on the device (see grad_scale_kernel)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int nv = C >> 2;
@@ -293,6 +297,8 @@ __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X
 // out = d[1] * t + d[0] * x           (models/model_distilled.py:493)
 __global__ void __launch_bounds__(256) blend_fwd_kernel(const float4* __restrict__ t, const float4* __restrict__ x, const float* __restrict__ d,
                                                         float4* __restrict__ out, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float d0 = __ldg(d), d1 = __ldg(d + 1);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 a = t[i], b = x[i];
@@ -302,6 +308,8 @@ __global__ void __launch_bounds__(256) blend_fwd_kernel(const float4* __restrict
 // dots[0] += <g, x>, dots[1] += <g, t>   (gradients of the loss wrt the blend weights d0, d1)
 __global__ void __launch_bounds__(256) blend_dots_kernel(const float4* __restrict__ g, const float4* __restrict__ t, const float4* __restrict__ x,
                                                          float* __restrict__ dots, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   float sx = 0.f, st = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 gg = g[i], a = t[i], b = x[i];
@@ -513,8 +521,8 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm: C=%d must be a multiple of 4 and <= %d", C, kMaxVec * 128);
   UVC_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm: row strides must be multiples of 4");
   if (M <= 0) return UVC_OK;
-  if (y16) UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV, true><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, static_cast<float*>(y16), ldy, mean, rstd, M, C, 0)));
-  else UVC_LN_DISPATCH(C, (layernorm_fwd_kernel<NV, false><<<(M + 7) / 8, 256, 0, st>>>(x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd)));
+  if (y16) UVC_LN_DISPATCH(C, launch_pdl(layernorm_fwd_kernel<NV, true>, dim3((M + 7) / 8), dim3(256), 0, st, x, ldx, gamma, beta, eps, static_cast<float*>(y16), ldy, mean, rstd, M, C, 0));
+  else UVC_LN_DISPATCH(C, launch_pdl(layernorm_fwd_kernel<NV, false>, dim3((M + 7) / 8), dim3(256), 0, st, x, ldx, gamma, beta, eps, y, ldy, mean, rstd, M, C, rnd));
   return check_launch("layernorm_fwd");
 }
 
@@ -535,13 +543,13 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
   if (dy16) {
     const float* d16 = static_cast<const float*>(dy16);
     if (cs_r1 || cs_out)
-      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale, scales_dev)));
+      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale, scales_dev));
     else
-      UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, true><<<blocks, 256, 0, st>>>(d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale, scales_dev)));
+      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale, scales_dev));
   } else if (cs_r1 || cs_out)
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, true, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale, scales_dev)));
+    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale, scales_dev));
   else
-    UVC_LN_DISPATCH(C, (layernorm_bwd_kernel<NV, false, false><<<blocks, 256, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale, scales_dev)));
+    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale, scales_dev));
   return check_launch("layernorm_bwd");
 }
 
@@ -579,12 +587,12 @@ int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, f
 }
 int blend_fwd(const float* t, const float* x, const float* d, float* out, long long n, cudaStream_t st) {
   UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "blend: element count must be a multiple of 4");
-  blend_fwd_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), d, reinterpret_cast<float4*>(out), n / 4);
+  launch_pdl(blend_fwd_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), d, reinterpret_cast<float4*>(out), n / 4);
   return check_launch("blend_fwd");
 }
 int blend_dots(const float* g, const float* t, const float* x, float* dots, long long n, cudaStream_t st) {
   UVC_REQUIRE((n & 3) == 0, UVC_ERR_BAD_SHAPE, "blend_dots: element count must be a multiple of 4");
-  blend_dots_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, st>>>(reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), dots, n / 4);
+  launch_pdl(blend_dots_kernel, dim3(grid_for(n / 4, 256, 148 * 4)), dim3(256), 0, st, reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(x), dots, n / 4);
   return check_launch("blend_dots");
 }
 int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st, int rnd) {
