@@ -232,6 +232,16 @@ UVC_API int uvc_distill_loss(const float* logits, const float* teacher_logits, c
                              float alpha, float T, float grad_scale, float* loss_out, float* dlogits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input pipeline on the device: timm batch-mode Mixup / CutMix + smoothed mixed one-hot targets in ONE launch
+ * (joint_train.py:409,930-933; post_train.py:362,618-621).  lam and the CutMix box come from the host RNG as in timm.
+ *   mixup : x[i] <- lam x[i] + (1-lam) x[B-1-i] in place;  cutmix: the box [yl,yh) x [xl,xh) of x[i] <- that of x[B-1-i] in place;
+ *   targets[i,c] = lam * sm(y[i])[c] + (1-lam) * sm(y[B-1-i])[c],  sm = smoothing/NC + (1-smoothing) [c == y].   lam == 1: images untouched.
+ * x: [B, C, H, W] fp32 (B even), y: [B] int64, targets: [B, num_classes] fp32 (may be NULL).  Parity unpinned by the reference (timm is not in
+ * its tree): pinned against the plain-torch formula in tests/. */
+UVC_API int uvc_mixup(float* x, const int64_t* y, float* targets, int32_t B, int32_t C, int32_t H, int32_t W, int32_t num_classes, float lam,
+                      float smoothing, int32_t use_cutmix, int32_t yl, int32_t yh, int32_t xl, int32_t xh, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimiser: global-norm clip + AdamW   (joint_train.py:428-429, torch.optim.AdamW semantics)
  *   uvc_sqnorm_accum : acc[0] += sum g^2                       (call once per gradient buffer)
  *   uvc_clip_adamw   : coef = min(1, max_norm / (sqrt(acc[0]) + 1e-6)) (1 if max_norm <= 0); g *= coef;

@@ -93,6 +93,7 @@ EXPORTS = [
     "uvc_vit_workspace_bytes", "uvc_vit_forward", "uvc_vit_backward",
     "uvc_layernorm_fwd_f16", "uvc_layernorm_bwd_f16", "uvc_cvt_f16", "uvc_attention_fwd_f16", "uvc_attention_bwd_f16",
     "uvc_token_gate_fold", "uvc_token_gate_fwd", "uvc_token_gate_bwd", "uvc_token_gate_apply",
+    "uvc_mixup",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
@@ -170,6 +171,7 @@ def load():
         "uvc_attention_fwd_lse": [vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_attention_bwd_fused": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
         "uvc_distill_loss": [vp, vp, vp, i32, i32, f32, f32, f32, vp, vp, vp],
+        "uvc_mixup": [vp, vp, vp, i32, i32, i32, i32, i32, f32, f32, i32, i32, i32, i32, i32, vp],
         "uvc_sqnorm_accum": [vp, i64, vp, vp],
         "uvc_sqnorm_accum_flags": [vp, vp, i64, vp, vp],
         "uvc_clip_adamw_flags": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],

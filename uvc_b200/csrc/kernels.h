@@ -55,6 +55,9 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
 int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
                       float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f, const float* db_scale_dev = nullptr);
 
+// timm batch-mode mixup / cutmix + mixed smoothed targets (input_pipeline.cu)
+int mixup_batch(float* x, const long long* y, float* targets, int B, int C, int H, int W, int NC, float lam, float smoothing, int use_cutmix, int yl, int yh,
+                int xl, int xh, cudaStream_t st);
 // token slimming gate (token_gate.cu)
 int token_gate_fold(const float* patch_w, const float* patch_b, const float* gate_w, int C, int Kp, float* v, float* c1, cudaStream_t st);
 int token_gate_fwd(const float* F, long long ldf, int Kf, const float* v, const float* c1, const float* gate_b, const float* pscale, const float* noise,

@@ -349,3 +349,14 @@ def clip_adamw_flags_(p, g, m, v, flags, sqnorm_acc, max_norm, lr, beta1, beta2,
     assert flags.dtype == torch.uint8 and flags.numel() == p.numel()
     _call("uvc_clip_adamw_flags", _p(p), _p(g), _p(m), _p(v), flags.data_ptr(), p.numel(), _p(sqnorm_acc), float(max_norm), float(lr),
           float(beta1), float(beta2), float(eps), float(weight_decay), int(step))
+
+
+def mixup_(x, y, num_classes, lam, smoothing, box=None):
+    """in-place batch mixup (box None) or cutmix (box = (yl, yh, xl, xh)) of x [B,C,H,W] with x.flip(0); returns the mixed smoothed targets [B, NC]"""
+    B, C_, H, W = x.shape
+    assert x.is_contiguous() and y.dtype == torch.int64 and y.is_cuda
+    tgt = torch.empty(B, num_classes, device=x.device)
+    yl, yh, xl, xh = box if box is not None else (0, 0, 0, 0)
+    _call("uvc_mixup", _p(x), y.data_ptr(), _p(tgt), B, C_, H, W, int(num_classes), float(lam), float(smoothing), 1 if box is not None else 0,
+          int(yl), int(yh), int(xl), int(xh))
+    return tgt

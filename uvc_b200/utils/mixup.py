@@ -1,7 +1,11 @@
 """Batch mixup / cutmix and the soft-target criteria the UVC loops take from timm (un-vendored, unpinned dependency of the
 reference: joint_train.py:924-944, post_train.py:618-632).  Re-stated from timm's public semantics (timm.data.Mixup in
 'batch' mode, timm.loss.SoftTargetCrossEntropy / LabelSmoothingCrossEntropy); numpy's global RNG drives the draws exactly
-as timm does, so `np.random.seed(args.seed)` reproduces the same lambda / box sequence."""
+as timm does, so `np.random.seed(args.seed)` reproduces the same lambda / box sequence.
+
+On CUDA batches the mixing of the images AND the smoothed mixed targets are ONE kernel launch (`uvc_mixup`, input_pipeline.cu) instead of ~10
+elementwise torch launches; lambda and the CutMix box are still drawn here on the host, from numpy's RNG, as timm does.  The plain-torch
+arithmetic below is what runs for host (CPU) tensors -- a loader that mixes before the copy, and the CPU tests of these semantics."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -80,6 +84,13 @@ class Mixup:
 
     def __call__(self, x, target):
         assert len(x) % 2 == 0, 'Batch size should be even when using this'
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and (x[0].numel() % 4 == 0):
+            from .. import ops
+            lam, use_cutmix = self._params_per_batch()       # same draws, in the same order, as the host path below
+            box = None
+            if lam != 1. and use_cutmix:
+                box, lam = cutmix_bbox_and_lam(x.shape, lam, correct_lam=self.correct_lam)
+            return x, ops.mixup_(x, target.long().contiguous(), self.num_classes, lam, self.label_smoothing, box)
         lam = self._mix_batch(x)
         return x, mixup_target(target, self.num_classes, lam, self.label_smoothing)
 
