@@ -111,6 +111,31 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": label}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and therefore its first-touch pinned staging buffers) to the NUMA node its GPU hangs off: with 8 ranks
+    feeding 77 MB per step each, cross-socket staging is what the end-to-end scaling loses first.  Best effort; returns a note for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"node {node}: no allowed cpus"
+        os.sched_setaffinity(0, cpus)
+        return f"node {node} ({len(cpus)} cpus)"
+    except Exception as e:
+        return f"unavailable ({type(e).__name__})"
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -161,7 +186,9 @@ def build_gpu_step(cfg, device, world):
     model.eval()
     with torch.no_grad():
         _, flops_list = model(torch.ones(1, 3, 224, 224, device=device))
-    uvc = list(build_minimax_model(model, layer_names, uvc_layers, uvc_dict, args, flops_list))
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # the reference's "** Initial FLOP size" print: stdout carries the ONE JSON line only
+        uvc = list(build_minimax_model(model, layer_names, uvc_layers, uvc_dict, args, flops_list))
     mm = uvc[0]
     Fh = model.blocks[0].mlp.fc1.out_features
     mixup = Mixup(mixup_alpha=args.mixup, cutmix_alpha=args.cutmix, prob=args.mixup_prob, switch_prob=args.mixup_switch_prob,
@@ -218,6 +245,7 @@ def run_gpu(a):
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
@@ -362,7 +390,7 @@ def run_gpu(a):
         "dtype": ("f16 operands / f32 accumulate (GEMM + attention operands stored as fp16 = TF32's 10 mantissa bits; residual stream, LayerNorm, softmax, loss, "
                   "optimizer, ADMM in f32)" if f16_mode else "tf32 (fp32 storage, fp32 accumulate)"), "data": "synthetic",
         "config": {"workload": cfg["workload"], "name": a.config, "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world}", "host_numa_binding": numa, "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush",
                    "parity_unpinned": "Mixup / soft-target CE / AdamW grouping follow timm's public semantics (timm is absent from the reference tree)", **info},
         "clocks": clk,
         "e2e": {"value": round(imgs / (ms_e2e / 1e3), 1), "unit": "images/sec", "ms_per_step": round(ms_e2e / a.steps, 3),

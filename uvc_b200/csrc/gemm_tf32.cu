@@ -576,20 +576,23 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     float4 dg;
-                    gelu_both(v[i].x, v[i].x, dg.x); gelu_both(v[i].y, v[i].y, dg.y); gelu_both(v[i].z, v[i].z, dg.z); gelu_both(v[i].w, v[i].w, dg.w);
+                    gelu_pair<true>(v[i].x, v[i].y, v[i].x, v[i].y, dg.x, dg.y); gelu_pair<true>(v[i].z, v[i].w, v[i].z, v[i].w, dg.z, dg.w);
                     if (ok(i)) *reinterpret_cast<uint2*>(xptr16 + i * xstep) = pack_half4(dg.x, dg.y, dg.z, dg.w);
                   }
                 } else {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) {
                     float4 dg;
-                    gelu_both(v[i].x, v[i].x, dg.x); gelu_both(v[i].y, v[i].y, dg.y); gelu_both(v[i].z, v[i].z, dg.z); gelu_both(v[i].w, v[i].w, dg.w);
+                    gelu_pair<true>(v[i].x, v[i].y, v[i].x, v[i].y, dg.x, dg.y); gelu_pair<true>(v[i].z, v[i].w, v[i].z, v[i].w, dg.z, dg.w);
                     if (ok(i)) *reinterpret_cast<float4*>(xptr + i * xstep) = dg;
                   }
                 }
               } else {                                 // inference / teacher forward: no derivative
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { v[i].x = gelu_f(v[i].x); v[i].y = gelu_f(v[i].y); v[i].z = gelu_f(v[i].z); v[i].w = gelu_f(v[i].w); }
+                for (int i = 0; i < 8; ++i) {
+                  float u0, u1;
+                  gelu_pair<false>(v[i].x, v[i].y, v[i].x, v[i].y, u0, u1); gelu_pair<false>(v[i].z, v[i].w, v[i].z, v[i].w, u0, u1);
+                }
               }
             }
             if (MODE == kEpiGeluBwd) {
