@@ -89,6 +89,8 @@ enum {
   UVC_GEMM_F16 = 128,      /* A and B hold fp16 values (ld / batch strides in fp16 elements, multiples of 8): tcgen05.mma kind::f16 with fp32
                               accumulation -- the 10 mantissa bits of TF32 at half the operand bytes.  K-major unbatched operands run on the
                               CTA-pair kernel; MN-major operands, split-K and batches on the 128 x 128 kernel (fp32 output only there). */
+  UVC_EPI_BLEND = 512,     /* block gate blend fused behind the residual (models/model_distilled.py:493): with t = the value formed so far
+                              (alpha acc + bias + beta R), D2 = t (optional) and v = blend_dev[1] * t + blend_dev[0] * R2.  CTA-pair kernel, plain epilogue. */
   UVC_EPI_AUX_F16 = 256    /* `aux` points to fp16 values (ldaux in fp16 elements, ldaux % 4 == 0, 8 B-aligned): the gelu' factors are in
                               [-0.13, 1.13] and the product they enter is rounded to TF32 anyway, so 11 significant bits lose nothing and
                               the GELU pair of epilogues moves half the aux bytes.  CTA-pair kernel only (unbatched operands). */
@@ -111,6 +113,9 @@ typedef struct {
   float colsum_scale;      /* multiplies the UVC_EPI_COLSUM column sums before they are accumulated; 0 means 1 (how the loss scale of the
                               fp16 gradient tensors is taken back out of a fused bias gradient) */
   float* colsum;           /* [N], accumulated into when UVC_EPI_COLSUM is set */
+  const float* R2; int64_t ldr2;   /* UVC_EPI_BLEND: the block input x */
+  float* D2; int64_t ldd2;         /* UVC_EPI_BLEND: where the un-blended t goes (the backward's gate gradient needs it), or NULL */
+  const float* blend_dev;          /* UVC_EPI_BLEND: device (d0, d1) */
   const float* alpha_dev2; /* a second optional device scalar multiplied into alpha (gate value x inverse loss scale) */
   const float* colsum_scale_dev;  /* optional device scalar multiplied into colsum_scale */
   void* D16; int64_t ldd16; /* optional fp16 copy of the output [M, ldd16] (round to nearest), for consumers that read it as an fp16 GEMM

@@ -76,7 +76,7 @@ def test_epilogue_flag_values_match_the_header():
     vals = {k: int(v) for k, v in re.findall(r"\b(UVC_(?:EPI|GEMM)_\w+)\s*=\s*(\d+)", text)}
     want = {"UVC_EPI_BIAS": _lib.EPI_BIAS, "UVC_EPI_GELU": _lib.EPI_GELU, "UVC_EPI_GELU_BWD": _lib.EPI_GELU_BWD, "UVC_EPI_RESIDUAL": _lib.EPI_RESIDUAL,
             "UVC_EPI_ATOMIC": _lib.EPI_ATOMIC, "UVC_EPI_ROUND_TF32": _lib.EPI_ROUND_TF32, "UVC_EPI_COLSUM": _lib.EPI_COLSUM,
-            "UVC_GEMM_F16": _lib.GEMM_F16, "UVC_EPI_AUX_F16": _lib.EPI_AUX_F16}
+            "UVC_GEMM_F16": _lib.GEMM_F16, "UVC_EPI_AUX_F16": _lib.EPI_AUX_F16, "UVC_EPI_BLEND": _lib.EPI_BLEND}
     assert vals == want
     assert len(set(want.values())) == len(want) and all(v & (v - 1) == 0 for v in want.values())      # distinct single bits
 

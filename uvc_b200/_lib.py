@@ -28,7 +28,8 @@ class GemmArgs(C.Structure):
                 ("R", C.c_void_p), ("ldr", C.c_int64), ("r_bs1", C.c_int64), ("r_bs2", C.c_int64),
                 ("aux", C.c_void_p), ("ldaux", C.c_int64), ("aux_bs1", C.c_int64), ("aux_bs2", C.c_int64),
                 ("alpha", C.c_float), ("beta", C.c_float), ("alpha_dev", C.c_void_p), ("beta_dev", C.c_void_p),
-                ("flags", C.c_int32), ("colsum_scale", C.c_float), ("colsum", C.c_void_p), ("alpha_dev2", C.c_void_p), ("colsum_scale_dev", C.c_void_p),
+                ("flags", C.c_int32), ("colsum_scale", C.c_float), ("colsum", C.c_void_p), ("R2", C.c_void_p), ("ldr2", C.c_int64), ("D2", C.c_void_p), ("ldd2", C.c_int64), ("blend_dev", C.c_void_p),
+                ("alpha_dev2", C.c_void_p), ("colsum_scale_dev", C.c_void_p),
                 ("D16", C.c_void_p), ("ldd16", C.c_int64)]
 
 
@@ -97,7 +98,7 @@ EXPORTS = [
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
-EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM, GEMM_F16, EPI_AUX_F16 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+EPI_BIAS, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ATOMIC, EPI_ROUND_TF32, EPI_COLSUM, GEMM_F16, EPI_AUX_F16, EPI_BLEND = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 _lib = None
 

@@ -29,6 +29,9 @@ struct alignas(64) GemmKParams {
   float* D; long long ldd, d_bs1, d_bs2;
   const float* bias;
   const float* R; long long ldr, r_bs1, r_bs2;
+  const float* R2; long long ldr2;      // v2, UVC_EPI_BLEND: second residual (the block input x)
+  float* D2; long long ldd2;            // v2, UVC_EPI_BLEND: optional copy of the un-blended value t
+  const float* blend_dev;               // v2, UVC_EPI_BLEND: device (d0, d1)
   float* aux; long long ldaux, aux_bs1, aux_bs2;
   const float* alpha_dev; const float* beta_dev; const float* alpha_dev2; const float* colsum_scale_dev;
   float* colsum;
@@ -319,7 +322,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmKParams p) {
 #ifndef UVC_GELU_EW
 #define UVC_GELU_EW 12
 #endif
-__host__ __device__ constexpr int epi_warps2(int BN, int MODE) { return (BN == 192 && MODE != 0) ? UVC_GELU_EW : 8; }
+__host__ __device__ constexpr int epi_warps2(int BN, int MODE) { return (BN == 192 && (MODE == 1 || MODE == 2)) ? UVC_GELU_EW : 8; }
 __host__ __device__ constexpr int threads2(int BN, int MODE) { return 64 + 32 * epi_warps2(BN, MODE); }
 
 template <int BN, int STAGES, int MODE = 0>
@@ -336,7 +339,7 @@ struct Gemm2Cfg {
   static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 };
 
-enum { kEpiPlain = 0, kEpiGelu = 1, kEpiGeluBwd = 2 };
+enum { kEpiPlain = 0, kEpiGelu = 1, kEpiGeluBwd = 2, kEpiBlend = 3 };   // kEpiBlend: plain + residual + the fused block-gate blend (its own instantiation: 32 more live registers)
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(threads2(BN, MODE), 1)
@@ -495,6 +498,8 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
     const uint32_t ld_odd = stg + rl * 128 + (((uint32_t)cc ^ (uint32_t)(rl + 4)) << 4);
     const uint32_t tempty_leader = mapa_cluster(tempty_bar(0), 0);
     const bool do_round = (flags & UVC_EPI_ROUND_TF32) != 0, do_atomic = (flags & UVC_EPI_ATOMIC) != 0;
+    const bool do_blend = (flags & UVC_EPI_BLEND) != 0;
+    const float bl_d0 = do_blend ? __ldg(p.blend_dev) : 0.f, bl_d1 = do_blend ? __ldg(p.blend_dev + 1) : 1.f;
     uint32_t ac = 0;
     for (int u = pair; u < p.units; u += npairs, ++ac) {
       const int tile = u % tiles, split = u / tiles;
@@ -522,6 +527,8 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
           float* const dptr = p.D + roff * p.ldd + gcol; const long long dstep = 4 * p.ldd;
           __half* const d16ptr = reinterpret_cast<__half*>(p.D16) + roff * p.ldd16 + gcol; const long long d16step = 4 * p.ldd16;
           const float* const rptr = p.R + roff * p.ldr + gcol; const long long rstep = 4 * p.ldr;
+          const float* const r2ptr = p.R2 + roff * p.ldr2 + gcol; const long long r2step = 4 * p.ldr2;
+          float* const d2ptr = p.D2 + roff * p.ldd2 + gcol; const long long d2step = 4 * p.ldd2;
           float* const xptr = p.aux + roff * p.ldaux + gcol;
           __half* const xptr16 = reinterpret_cast<__half*>(p.aux) + roff * p.ldaux + gcol;     // UVC_EPI_AUX_F16 view of the same argument
           const long long xstep = 4 * p.ldaux;
@@ -547,6 +554,11 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
             } else if (do_res) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) rr[i] = ok(i) ? *reinterpret_cast<const float4*>(rptr + i * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 rr2[MODE == kEpiBlend ? 8 : 1];
+            if (MODE == kEpiBlend) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rr2[i] = ok(i) ? *reinterpret_cast<const float4*>(r2ptr + i * r2step) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (do_bias && colok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
@@ -602,6 +614,17 @@ gemm2_tf32_kernel(const __grid_constant__ GemmKParams p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 v[i].x = fmaf(beta, rr[i].x, v[i].x); v[i].y = fmaf(beta, rr[i].y, v[i].y); v[i].z = fmaf(beta, rr[i].z, v[i].z); v[i].w = fmaf(beta, rr[i].w, v[i].w);
+              }
+            }
+            if (MODE == kEpiBlend) {                   // block gate (models/model_distilled.py:493): x_out = d1 t + d0 x, t = the value formed so far
+              if (p.D2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (ok(i)) *reinterpret_cast<float4*>(d2ptr + i * d2step) = v[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[i].x = fmaf(bl_d0, rr2[i].x, bl_d1 * v[i].x); v[i].y = fmaf(bl_d0, rr2[i].y, bl_d1 * v[i].y);
+                v[i].z = fmaf(bl_d0, rr2[i].z, bl_d1 * v[i].z); v[i].w = fmaf(bl_d0, rr2[i].w, bl_d1 * v[i].w);
               }
             }
             if (p.colsum) {                            // fused bias gradient: column sums of this warp's 32 rows (before any rounding)
@@ -796,6 +819,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch2m(const GemmKParams& kp, int pairs, cudaStream_t st) {
   if (kp.flags & UVC_EPI_GELU) return launch2k<BN, STAGES, A_MN, B_MN, kEpiGelu>(kp, pairs, st);
   if (kp.flags & UVC_EPI_GELU_BWD) return launch2k<BN, STAGES, A_MN, B_MN, kEpiGeluBwd>(kp, pairs, st);
+  if constexpr (!A_MN && !B_MN) { if (kp.flags & UVC_EPI_BLEND) return launch2k<BN, STAGES, A_MN, B_MN, kEpiBlend>(kp, pairs, st); }
   return launch2k<BN, STAGES, A_MN, B_MN, kEpiPlain>(kp, pairs, st);
 }
 template <int BN, int STAGES>
@@ -845,6 +869,10 @@ static bool v2_legal(const uvc_gemm_args& a) {
   if ((a.flags & UVC_EPI_BIAS) && !al16(a.bias)) return false;
   if ((a.flags & UVC_EPI_COLSUM) && !al16(a.colsum)) return false;
   if ((a.flags & UVC_EPI_RESIDUAL) && ((a.ldr & 3) || !al16(a.R))) return false;
+  if (a.flags & UVC_EPI_BLEND) {
+    if (a.A.mn_major || a.B.mn_major || !a.R2 || !a.blend_dev || (a.ldr2 & 3) || !al16(a.R2) || (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD | UVC_EPI_ATOMIC)) || a.splits != 1) return false;
+    if (a.D2 && ((a.ldd2 & 3) || !al16(a.D2))) return false;
+  }
   if ((a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) && a.aux) {
     if (a.flags & UVC_EPI_AUX_F16) { if ((a.ldaux & 3) || (reinterpret_cast<uintptr_t>(a.aux) & 7)) return false; }
     else if ((a.ldaux & 3) || !al16(a.aux)) return false;
@@ -892,7 +920,7 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   // fp16 operands: K-major unbatched problems run on the CTA-pair kernel; MN-major operands (the weight gradients: both operands are read
   // transposed), split-K and batched problems on the 128 x 128 kernel.
   const bool f16_v1 = f16 && (a.A.mn_major || a.B.mn_major || a.splits > 1 || a.nb1 != 1 || a.nb2 != 1);
-  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || (f16 && !f16_v1) || a.D16 || !a.D || aux16;   // features only the CTA-pair kernel has
+  const bool need_v2 = ((a.flags & UVC_EPI_COLSUM) && !colsum_simple) || (f16 && !f16_v1) || a.D16 || !a.D || aux16 || (a.flags & UVC_EPI_BLEND);   // features only the CTA-pair kernel has
   UVC_REQUIRE(!(f16_v1 && need_v2), UVC_ERR_BAD_ARG, "gemm: fp16 MN-major / split-K / batched operands cannot be combined with D16, fp16 aux or COLSUM under a GELU / residual epilogue");
   UVC_REQUIRE(!need_v2 || v2_legal(a), UVC_ERR_BAD_ARG, "gemm: fp16 operands / D16 / UVC_EPI_COLSUM with GELU or residual epilogues need unbatched, 16 B-aligned operands and N % 4 == 0");
   // Split-K weight gradients (few output tiles, K = all tokens) stay on the 128 x 128 kernel: its tiles fit the C-multiple weight shapes without
@@ -928,6 +956,8 @@ int gemm_tf32(const uvc_gemm_args& a, cudaStream_t st) {
   kp.D = a.D; kp.ldd = a.ldd; kp.d_bs1 = a.d_bs1; kp.d_bs2 = a.d_bs2;
   kp.bias = a.bias;
   kp.R = (a.flags & UVC_EPI_RESIDUAL) ? a.R : nullptr; kp.ldr = a.ldr; kp.r_bs1 = a.r_bs1; kp.r_bs2 = a.r_bs2;
+  const bool blend = (a.flags & UVC_EPI_BLEND) != 0;
+  kp.R2 = blend ? a.R2 : nullptr; kp.ldr2 = a.ldr2; kp.D2 = blend ? a.D2 : nullptr; kp.ldd2 = a.ldd2; kp.blend_dev = blend ? a.blend_dev : nullptr;
   kp.aux = (a.flags & (UVC_EPI_GELU | UVC_EPI_GELU_BWD)) ? a.aux : nullptr; kp.ldaux = a.ldaux; kp.aux_bs1 = a.aux_bs1; kp.aux_bs2 = a.aux_bs2;
   kp.alpha_dev = a.alpha_dev; kp.beta_dev = a.beta_dev; kp.alpha_dev2 = a.alpha_dev2; kp.colsum_scale_dev = a.colsum_scale_dev;
   kp.colsum = (a.flags & UVC_EPI_COLSUM) ? a.colsum : nullptr;

@@ -20,7 +20,8 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
                   cudaStream_t st, float* cs_r1 = nullptr, float* cs_out = nullptr,    // cs_*: fused column sums of r1 / of dx (bias gradients)
                   const void* dy16 = nullptr, float dy_scale = 1.0f,                    // dy16: dy as fp16 (row stride lddy), multiplied by dy_scale on load
                   void* dx16 = nullptr, float out_scale = 1.0f,                         // dx16: also write fp16(out_scale * dx), row stride lddx
-                  const float* scales_dev = nullptr);                                   // device {S, 1/S}: out_scale *= S, dy_scale *= 1/S
+                  const float* scales_dev = nullptr,                                    // device {S, 1/S}: out_scale *= S, dy_scale *= 1/S
+                  const float* dot_t = nullptr, float* dots = nullptr, int dot_x = 0);  // gate gradients: dots[0] += <r2, x> (dot_x), dots[1] += <r2, dot_t>
 int softmax_fwd(float* S, long long ld, long long rows, int n, cudaStream_t st, int round_out = 0);
 int softmax_bwd(const float* P, float* dP, long long ld, long long rows, int n, float scale, cudaStream_t st, int round_out = 0);
 int colsum(const float* X, long long ld, int M, int N, const float* scale_dev, float* out, cudaStream_t st);

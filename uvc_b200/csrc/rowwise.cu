@@ -89,14 +89,18 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // DY16: dy holds fp16 values that carry the loss scale (dy_scale = 1 / scale takes it out on load).  dx16 (optional): an fp16 copy of
 // out_scale * dx for the GEMMs that consume the stream gradient as an operand; the fp32 dx stays unscaled.
 template <int NV, bool CS, bool DY16>
-__global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+#ifndef UVC_LN_BWD_MINB
+#define UVC_LN_BWD_MINB 3
+#endif
+__global__ void __launch_bounds__(256, (NV <= 3 ? UVC_LN_BWD_MINB : 2)) layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ r1, const float* __restrict__ r2,
                                                             const float* __restrict__ s2_dev, float* __restrict__ dx, long long lddx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ cs_r1,
                                                             float* __restrict__ cs_out, int M, int C, int rows_per_block,
                                                             float dy_scale, __half* __restrict__ dx16, float out_scale,
-                                                            const float* __restrict__ scales_dev) {
+                                                            const float* __restrict__ scales_dev, const float* __restrict__ dot_t, float* __restrict__ dots,
+                                                            int dot_x) {
   __shared__ float red[4][8][32 * 4 + 4];
   pdl_launch_dependents();
   pdl_wait();
@@ -114,12 +118,16 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(c
   const int row0 = blockIdx.x * rows_per_block;
   const int row1 = min(M, row0 + rows_per_block);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  // block-gate gradients ride along (models/model_distilled.py:493: x_out = d1 t + d0 x -> dd0 = <g, x>, dd1 = <g, t>): r2 is g, x is this
+  // norm's input (norm1: the block input) and dot_t the un-blended block output t (norm2), all streamed here anyway except t
+  float acc_dx = 0.f, acc_dt = 0.f;
   for (int row = row0 + warp; row < row1; row += nwarps) {
     const float4* dyr = reinterpret_cast<const float4*>(dy + (long long)row * lddy);
     const uint2* dyr16 = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(dy) + (long long)row * lddy);
     const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
     const float4* r1r = r1 ? reinterpret_cast<const float4*>(r1 + (long long)row * lddx) : nullptr;
     const float4* r2r = r2 ? reinterpret_cast<const float4*>(r2 + (long long)row * lddx) : nullptr;
+    const float4* dtr = dot_t ? reinterpret_cast<const float4*>(dot_t + (long long)row * lddx) : nullptr;
     const float mu = mean[row], rs = rstd[row];
     float4 xh[NV], gg[NV], res[NV];
     float sg = 0.f, sgx = 0.f;
@@ -138,7 +146,12 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(c
         }
         const float4 xv = xr[c], gm = __ldg(g4 + c);
         if (r1r) res[i] = r1r[c];
-        if (r2r) { const float4 a = r2r[c]; res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w; }
+        if (r2r) {
+          const float4 a = r2r[c];
+          res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w;
+          if (dot_x) acc_dx += (a.x * xv.x + a.y * xv.y) + (a.z * xv.z + a.w * xv.w);
+          if (dtr) { const float4 tv = dtr[c]; acc_dt += (a.x * tv.x + a.y * tv.y) + (a.z * tv.z + a.w * tv.w); }
+        }
         if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
         xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
         gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
@@ -162,6 +175,10 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_bwd_kernel(c
         if (dx16) reinterpret_cast<uint2*>(dx16 + (long long)row * lddx)[c] = pack_half4(o.x * out_scale, o.y * out_scale, o.z * out_scale, o.w * out_scale);
       }
     }
+  }
+  if (dots) {
+    if (dot_x) { acc_dx = warp_sum(acc_dx); if (lane == 0) atomicAdd(dots, acc_dx); }
+    if (dot_t) { acc_dt = warp_sum(acc_dt); if (lane == 0) atomicAdd(dots + 1, acc_dt); }
   }
   if (!dgamma && !(CS && (cs_r1 || cs_out))) return;
   // cross-warp reduction of the per-lane column partials, one 128-column slab (i) at a time
@@ -528,14 +545,16 @@ int layernorm_fwd(const float* x, long long ldx, const float* gamma, const float
 
 int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* mean, const float* rstd, const float* gamma,
                   const float* r1, const float* r2, const float* s2_dev, float* dx, long long lddx, float* dgamma, float* dbeta, int M, int C,
-                  cudaStream_t st, float* cs_r1, float* cs_out, const void* dy16, float dy_scale, void* dx16, float out_scale, const float* scales_dev) {
+                  cudaStream_t st, float* cs_r1, float* cs_out, const void* dy16, float dy_scale, void* dx16, float out_scale, const float* scales_dev,
+                  const float* dot_t, float* dots, int dot_x) {
+  UVC_REQUIRE(!(dot_t || dot_x) || (dots && r2), UVC_ERR_BAD_ARG, "layernorm_bwd: the gate-gradient dot products need r2 and an output pointer");
   UVC_REQUIRE(C > 0 && (C & 3) == 0 && C <= kMaxVec * 128, UVC_ERR_BAD_SHAPE, "layernorm_bwd: C=%d unsupported", C);
   UVC_REQUIRE((ldx & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0, UVC_ERR_BAD_SHAPE, "layernorm_bwd: row strides must be multiples of 4");
   UVC_REQUIRE(!cs_r1 || r1 || r2, UVC_ERR_BAD_ARG, "layernorm_bwd: cs_r1 without a residual input");
   if (M <= 0) return UVC_OK;
   // one wave of 3 resident blocks per SM (the kernel is compiled for 80 registers): each warp has one row (4 x 1.5 KB) in flight, so the
   // bytes in flight per SM, not the column reductions, set the rate (measured: no gain from dropping the atomics, +8..15 % from 16 -> 24 warps)
-  int blocks = 148 * (C <= 384 ? 3 : 2);           // resident blocks per SM the kernel is compiled for (wider rows need more registers)
+  int blocks = 148 * (C <= 384 ? UVC_LN_BWD_MINB : 2);           // resident blocks per SM the kernel is compiled for (wider rows need more registers)
   int rpb = (M + blocks - 1) / blocks;
   if (rpb < 8) rpb = 8;
   blocks = (M + rpb - 1) / rpb;
@@ -543,13 +562,13 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
   if (dy16) {
     const float* d16 = static_cast<const float*>(dy16);
     if (cs_r1 || cs_out)
-      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale, scales_dev));
+      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, dy_scale, h16, out_scale, scales_dev, dot_t, dots, dot_x));
     else
-      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale, scales_dev));
+      UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, true>, dim3(blocks), dim3(256), 0, st, d16, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, dy_scale, h16, out_scale, scales_dev, dot_t, dots, dot_x));
   } else if (cs_r1 || cs_out)
-    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale, scales_dev));
+    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, true, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, cs_r1, cs_out, M, C, rpb, 1.0f, h16, out_scale, scales_dev, dot_t, dots, dot_x));
   else
-    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale, scales_dev));
+    UVC_LN_DISPATCH(C, launch_pdl(layernorm_bwd_kernel<NV, false, false>, dim3(blocks), dim3(256), 0, st, dy, lddy, x, ldx, mean, rstd, gamma, r1, r2, s2_dev, dx, lddx, dgamma, dbeta, nullptr, nullptr, M, C, rpb, 1.0f, h16, out_scale, scales_dev, dot_t, dots, dot_x));
   return check_launch("layernorm_bwd");
 }
 

@@ -447,7 +447,8 @@ inline uvc_operand op16_mn(const h16* p, long long ld) { return uvc_operand{rein
 // Y = epilogue(X16 W16^T): fp32 output D (with optional fp32 residual R) and / or fp16 output D16
 int linear16(const h16* X, long long ldx, const h16* W, const float* bias, float* Dout, void* D16, long long ldd, int M, int N, int K, cudaStream_t st,
              int extra_flags = 0, void* aux16 = nullptr, const float* R = nullptr, long long ldr = 0, const float* alpha_dev = nullptr,
-             float* colsum_out = nullptr, const float* colsum_scale_dev = nullptr) {
+             float* colsum_out = nullptr, const float* colsum_scale_dev = nullptr, const float* blend_dev = nullptr, const float* R2 = nullptr,
+             float* D2 = nullptr) {
   uvc_gemm_args a = gemm_args(M, N, K, op16_k(X, ldx), op16_k(W, K), Dout, ldd);
   a.flags = extra_flags | UVC_GEMM_F16;
   a.D16 = D16; a.ldd16 = ldd;
@@ -456,6 +457,7 @@ int linear16(const h16* X, long long ldx, const h16* W, const float* bias, float
   if (aux16) { a.aux = static_cast<float*>(aux16); a.ldaux = ldd; a.flags |= UVC_EPI_AUX_F16; }
   if (R) { a.R = R; a.ldr = ldr; a.flags |= UVC_EPI_RESIDUAL; }
   if (colsum_out) { a.colsum = colsum_out; a.colsum_scale_dev = colsum_scale_dev; a.flags |= UVC_EPI_COLSUM; }
+  if (blend_dev) { a.blend_dev = blend_dev; a.R2 = R2; a.ldr2 = ldd; a.D2 = D2; a.ldd2 = ldd; a.flags |= UVC_EPI_BLEND; }
   return gemm_tf32(a, st);
 }
 // dW[N,K] += (*inv_scale_dev) * dY16[M,N]^T X16[M,K]   (both operands MN-major fp16, split-K with fp32 atomics)
@@ -541,8 +543,9 @@ int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t s
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, nullptr, C, L.mean2, L.rstd2, M, C, st, 0, L.ln2));
       UVC_TRY(linear16(L.ln2, C, w.fc1_w[l], p.fc1_b, nullptr, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU, L.hpre));         // h = gelu(fc1) (fp16); hpre = gelu'(fc1) (fp16)
       if (a.blend) {
-        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.t, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C));          // t = x1 + fc2(h)
-        UVC_TRY(blend_fwd(L.t, x, a.blend + 2 * l, L.xout, (long long)M * C, st));                                    // x <- d1 t + d0 x
+        // t = x1 + fc2(h) and the gate blend x <- d1 t + d0 x in ONE epilogue (t is kept only for the backward's gate gradient)
+        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C, nullptr, nullptr, nullptr, a.blend + 2 * l, x,
+                         save ? L.t : nullptr));
       } else {
         UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C));
       }
@@ -607,15 +610,15 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
       const float* x = xin[l];
       const float* d = a.blend ? a.blend + 2 * l : nullptr;
       const float* d1 = d ? d + 1 : nullptr;
-      if (d) UVC_TRY(blend_dots(g, L.t, x, a.d_blend + 2 * l, (long long)M * C, st));
-      // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2))); dt = d1 g is never materialised (d1 rides as a device-scalar alpha)
+      // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2))); dt = d1 g is never materialised (d1 rides as a device-scalar alpha).  The gate gradients
+      // dd1 = <g, t>, dd0 = <g, x> are folded into the two LayerNorm backward kernels below, which stream g (and x) anyway.
       UVC_TRY(linear_wgrad16(w.g16, C, L.h, Fh, gp.fc2_w, M, C, Fh, invSd, st, d1));
       UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, Fh, M, Fh, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, gp.fc1_b, invSd));   // dhpre (x S)
       UVC_TRY(linear_wgrad16(w.dh16, Fh, L.ln2, C, gp.fc1_w, M, Fh, C, invSd, st));
       UVC_TRY(linear16(w.dh16, Fh, w.fc1_wT[l], nullptr, nullptr, w.dln16, C, M, C, Fh, st));                                                          // dln2 (x S)
       // dx1 = dt + LN2'(dln2); fc2.bias / proj.bias gradients ride along as column sums
       UVC_TRY(layernorm_bwd(nullptr, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, d ? nullptr : g, d ? g : nullptr, d1, spare2, C, gp.norm2_w, gp.norm2_b,
-                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, 1.0f, w.dx1_16, 1.0f, w.scales));
+                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, 1.0f, w.dx1_16, 1.0f, w.scales, d ? L.t : nullptr, d ? a.d_blend + 2 * l : nullptr, 0));
       float* dx1 = spare2;
       // ---- attention:  x1 = x + proj(ctx)
       UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, C, gp.proj_w, M, C, C, invSd, st));
@@ -625,7 +628,7 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
       UVC_TRY(linear16(w.dqkv16, 3 * C, w.qkv_wT[l], nullptr, nullptr, w.dln16, C, M, C, 3 * C, st));                                                  // dln1 (x S)
       // dx = dx1 + LN1'(dln1) + d0 g   (written over spare1); its fp16 operand copy replaces g16 (last read by the fc2 GEMMs above)
       UVC_TRY(layernorm_bwd(nullptr, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st,
-                            nullptr, nullptr, w.dln16, 1.0f, w.g16, 1.0f, w.scales));
+                            nullptr, nullptr, w.dln16, 1.0f, w.g16, 1.0f, w.scales, nullptr, d ? a.d_blend + 2 * l : nullptr, d ? 1 : 0));
       float* old = g; g = spare1; spare1 = old;
     }
     if (g_jump && l > 0) {

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GEMM_F16, EPI_AUX_F16, GemmArgs, Operand  # noqa: F401
+from ._lib import EPI_ATOMIC, EPI_BIAS, EPI_BLEND, EPI_COLSUM, EPI_GELU, EPI_GELU_BWD, EPI_RESIDUAL, EPI_ROUND_TF32, GEMM_F16, EPI_AUX_F16, GemmArgs, Operand  # noqa: F401
 
 
 def _stream():
@@ -32,7 +32,7 @@ def operand(t, ld=None, bs1=0, bs2=0, mn_major=False):
 
 def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=None, ldr=None, r_bs=(0, 0),
          aux=None, ldaux=None, aux_bs=(0, 0), alpha=1.0, beta=1.0, alpha_dev=None, beta_dev=None, flags=0, splits=1, colsum=None, D16=None,
-         colsum_scale=0.0):
+         colsum_scale=0.0, blend=None, R2=None, D2=None):
     """D[z] = epilogue(alpha * A[z] @ B[z]^T) with A:[M,K], B:[N,K] (see include/uvc_b200.h)."""
     lib = _lib.load()
     a = GemmArgs()
@@ -65,6 +65,10 @@ def gemm(A, B, D, M, N, K, *, ldd=None, d_bs=(0, 0), batch=(1, 1), bias=None, R=
     if colsum is not None:
         a.colsum = colsum.data_ptr(); flags |= EPI_COLSUM
         a.colsum_scale = float(colsum_scale)
+    if blend is not None:       # fused block-gate blend: D = blend[1] * t + blend[0] * R2, D2 = t
+        a.blend_dev = blend.data_ptr(); a.R2 = R2.data_ptr(); a.ldr2 = int(R2.stride(-2)); flags |= EPI_BLEND
+        if D2 is not None:
+            a.D2 = D2.data_ptr(); a.ldd2 = int(D2.stride(-2))
     a.flags = int(flags)
     _lib.check(lib.uvc_gemm_tf32(C.byref(a), _stream()), "uvc_gemm_tf32")
     return D
