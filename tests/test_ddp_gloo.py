@@ -65,6 +65,15 @@ def _worker(rank, world, port, q):
         m.flat_grad.zero_(); m.gate.grad = None
         ddp(x).backward()
         torch.testing.assert_close(m.w.grad, exp_w)
+        # wrapping the same module again (Stage 2 inside joint_train) replaces the first wrapper's hooks: still ONE exchange per backward
+        ddp2 = DDP(m, gradient_predivide_factor=world)
+        calls = []
+        orig = ddp._finalize
+        ddp._finalize = lambda: (calls.append(1), orig())
+        m.flat_grad.zero_(); m.gate.grad = None
+        ddp2(x).backward()
+        torch.testing.assert_close(m.w.grad, exp_w)
+        assert not calls and ddp2.bytes_reduced == m.flat_grad.numel() * 4 + m.gate.numel() * 4
         q.put((rank, "ok"))
     except Exception as e:       # surface the failure in the parent
         q.put((rank, repr(e)))

@@ -21,7 +21,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ..._lib import VitDims, operand_f16_for
-from ...models.model_distilled import DistilledVisionTransformer, _VitFunction, _engine_param_list, gumbel_softmax
+from ...models.model_distilled import DistilledVisionTransformer, _VitFunction, _engine_param_list, gumbel_softmax, hard_skip_list
 from .token_performer import Token_performer
 
 
@@ -121,8 +121,7 @@ class T2T_ViT(DistilledVisionTransformer):
             if self.use_gumbel:
                 return F.gumbel_softmax(self.block_skip_gating, tau=0.5, hard=self.gumbel_hard, eps=1e-10, dim=-1).contiguous(), None
             return F.softmax(self.block_skip_gating, dim=-1).contiguous(), None
-        gate = self.block_skip_gating.detach().tolist()
-        return None, [not (g[1] > g[0]) for g in gate]
+        return None, hard_skip_list(self)
 
     def forward_logits(self, x, tau=-1, ratio=0.9):
         B = x.shape[0]

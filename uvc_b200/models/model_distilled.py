@@ -462,8 +462,7 @@ class DistilledVisionTransformer(VisionTransformer):
             g1 = self.block_skip_gating[:, 1] ** 2
             d1 = g1 / (g1 + self.eps)
             return torch.stack([1 - d1, d1], dim=1).contiguous(), None
-        gate = self.block_skip_gating.detach().tolist()     # one host read: the skip decision shapes the launch sequence
-        return None, [not (g[1] > g[0]) for g in gate]
+        return None, hard_skip_list(self)
 
     def forward_logits(self, x, tau=-1, ratio=0.9):
         B = x.shape[0]
@@ -493,6 +492,21 @@ class DistilledVisionTransformer(VisionTransformer):
         if self.training:
             return (x, x_dist), macs_list
         return (x + x_dist) / 2, macs_list
+
+
+def hard_skip_list(model):
+    """Hard-skip decisions of `block_skip_gating` (reference models/model_distilled.py:496-500: a block runs iff gate[1] > gate[0]).
+    The decision shapes the launch sequence, so it needs a host read -- per CHANGE of the gates, not per forward: in eval mode (the frozen
+    teacher of every training step, validation) the list is cached on the parameter's storage and version counter, so the teacher
+    forward issues no device-to-host read inside the training loop.  A training-mode model re-reads every time (the optimiser kernels
+    write parameters through raw pointers, which does not move the version counter)."""
+    g = model.block_skip_gating
+    key = (g.data_ptr(), g._version)
+    cached = getattr(model, "_skip_cache", None)
+    if model.training or cached is None or cached[0] != key:
+        cached = (key, [not (v[1] > v[0]) for v in g.detach().tolist()])
+        model._skip_cache = cached
+    return list(cached[1])
 
 
 def _deit(embed_dim, depth, num_heads, **kw):

@@ -44,9 +44,21 @@ class DistributedDataParallel(nn.Module):
                 rest = [p.data for p in module.parameters() if id(p) not in eng] + [b.data for b in module.buffers()]
                 for t in rest:
                     dist.broadcast(t, 0, group=self.group)
-            for p in module.parameters():
-                if p.requires_grad:
-                    p.register_post_accumulate_grad_hook(self._on_grad)
+            # one live wrapper per module: wrapping the same model again (Stage 2 inside joint_train wraps the Stage-1 model a second time)
+            # detaches the earlier wrapper's hooks first, otherwise every backward would all-reduce the arena once per wrapper
+            prev = getattr(module, "_uvc_ddp_wrapper", None)
+            if prev is not None and prev is not self:
+                prev.remove()
+            self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in module.parameters() if p.requires_grad]
+            object.__setattr__(module, "_uvc_ddp_wrapper", self)
+
+    def remove(self):
+        """Detach this wrapper's gradient hooks (the module stays usable, un-synchronised)."""
+        for h in getattr(self, "_handles", []):
+            h.remove()
+        self._handles = []
+        if getattr(self.module, "_uvc_ddp_wrapper", None) is self:
+            object.__setattr__(self.module, "_uvc_ddp_wrapper", None)
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
