@@ -223,6 +223,14 @@ def build_gpu_step(cfg, device, world):
         model.block_skip_gating.requires_grad = False
         model.flatten_parameters()
         apply_masks(model)
+        from uvc_b200.post_train import set_compact_training
+        mode = {"dense": 0, "compact": 1, "exact": 2}[os.environ.get("UVC_STAGE2", "compact")]
+        elay = set_compact_training(model, mode)
+        info["stage2_execution"] = {0: "masked-dense (the reference's arithmetic: zeros are multiplied)",
+                                    1: "physically compacted: skipped blocks, fully pruned heads and pruned neurons are not computed",
+                                    2: "physically compacted (blocks + neurons; pruned heads kept for the reference's exact clip norm)"}[mode]
+        if elay is not None:
+            info["executed_macs_ratio"] = round(float(elay.executed_macs_ratio()), 4)
         masks = {m.weight: m.mask for _, m in model.named_modules() if hasattr(m, "mask")}
         lr = 5e-4 * cfg["batch"] * world / 512.0
         optimizer = FusedClipAdamW(param_groups_weight_decay(model, args.weight_decay), lr=lr, weight_decay=args.weight_decay,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 7
+#define UVC_ABI_VERSION 8
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -295,6 +295,23 @@ typedef struct {
                                     The workspace layout depends on it: use the same value for workspace_bytes / forward / backward. */
 } uvc_vit_dims;
 
+/* Stage-2 physical compaction for TRAINING.  The reference re-masks dense weights before every step (post_train.py:357-360) and
+ * multiplies by the zeros; with a layout the engine gathers, per block, the live heads (64-wide q / k / v row groups of attn.qkv.weight and
+ * the matching 64 input columns of attn.proj.weight) and the live neurons (rows of mlp.fc1.weight, columns of mlp.fc2.weight) into compact
+ * fp16 operand copies while it converts the weights, runs every GEMM / attention kernel of the block at the compact widths
+ * (3*64*n_heads, 64*n_heads, n_neurons) and scatters the compact weight / bias gradients back into the dense gradient tensors.
+ * Entries outside the live lists receive no gradient ("clip norm under compaction").  operand_f16 only.
+ *   head_idx   device [L, H]  int32: row l lists the n_heads[l]   live head numbers   (ascending; the rest of the row is ignored)
+ *   neuron_idx device [L, Fh] int32: row l lists the n_neurons[l] live neuron numbers (ascending)
+ * 1 <= n_heads[l] <= H;  64 <= n_neurons[l] <= Fh and n_neurons[l] % 64 == 0: a caller tops the lists up with pruned entries -- their masked
+ * weights are zero, so they change nothing.  Hard-skipped blocks are not looked at. */
+typedef struct {
+  int32_t n_heads[UVC_MAX_DEPTH];
+  int32_t n_neurons[UVC_MAX_DEPTH];
+  const int32_t* head_idx;
+  const int32_t* neuron_idx;
+} uvc_vit_layout;
+
 typedef struct {
   uvc_vit_dims dims;
   uvc_vit_tensors w;
@@ -311,6 +328,7 @@ typedef struct {
   const float* pe_in;            /* optional [B*np, C]: token embeddings computed by the caller; replaces x -> im2col -> patch GEMM.
                                     This is how the T2T-ViT backbone (T2TViT/models/t2t_vit.py:168-208: cls + sinusoid pos-embed, 14 Blocks,
                                     norm, head) runs behind the same entry point, fed by tokens_to_token (:46-105).  x, w.patch_* may be NULL. */
+  const uvc_vit_layout* layout;  /* host struct or NULL (dense): Stage-2 compaction, see uvc_vit_layout */
 } uvc_vit_forward_args;
 
 typedef struct {
@@ -332,6 +350,7 @@ typedef struct {
   float* d_token_mask;           /* [B, np] written, or NULL */
   void* workspace; uint64_t workspace_bytes;   /* the workspace the forward ran with */
   float* d_pe;                   /* forward ran with pe_in: gradient w.r.t. pe_in, [B*np, C] WRITTEN (g.patch_* untouched); else NULL */
+  const uvc_vit_layout* layout;  /* the layout the forward ran with, or NULL */
 } uvc_vit_backward_args;
 
 UVC_API uint64_t uvc_vit_workspace_bytes(const uvc_vit_dims* dims, int32_t save_for_backward);

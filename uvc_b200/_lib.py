@@ -52,17 +52,26 @@ class VitDims(C.Structure):
                 ("ln_eps", C.c_float), ("operand_f16", C.c_int32)]
 
 
+UVC_MAX_DEPTH = 32
+
+
+class VitLayout(C.Structure):
+    """uvc_vit_layout: Stage-2 compaction (live heads / neurons per block)"""
+    _fields_ = [("n_heads", C.c_int32 * UVC_MAX_DEPTH), ("n_neurons", C.c_int32 * UVC_MAX_DEPTH), ("head_idx", C.c_void_p), ("neuron_idx", C.c_void_p)]
+
+
 class VitForwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("x", _F), ("blend", _F), ("skip_host", C.c_void_p),
                 ("patch_scale", _F), ("token_mask", _F), ("save_for_backward", C.c_int32), ("enable_jumping", C.c_int32),
-                ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("pe_in", _F)]
+                ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("pe_in", _F),
+                ("layout", C.POINTER(VitLayout))]
 
 
 class VitBackwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("g", VitTensors), ("dlogits", _F), ("blend", _F),
                 ("skip_host", C.c_void_p), ("patch_scale", _F), ("token_mask", _F), ("enable_jumping", C.c_int32),
                 ("grad_scale", C.c_float), ("d_blend", _F), ("d_patch_scale", _F), ("d_token_mask", _F),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("d_pe", _F)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("d_pe", _F), ("layout", C.POINTER(VitLayout))]
 
 
 class AdmmArgs(C.Structure):
@@ -80,10 +89,8 @@ class AdmmArgs(C.Structure):
 
 
 _ABI_STRUCTS = {"uvc_admm_args": AdmmArgs, "uvc_operand": Operand, "uvc_gemm_args": GemmArgs, "uvc_block_tensors": BlockTensors,
-                "uvc_vit_tensors": VitTensors, "uvc_vit_dims": VitDims, "uvc_vit_forward_args": VitForwardArgs,
+                "uvc_vit_tensors": VitTensors, "uvc_vit_dims": VitDims, "uvc_vit_layout": VitLayout, "uvc_vit_forward_args": VitForwardArgs,
                 "uvc_vit_backward_args": VitBackwardArgs}
-
-UVC_MAX_DEPTH = 32
 
 # every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -60,6 +60,60 @@ def _pad_index(idx, total, multiple=8):
     return torch.sort(torch.cat([idx, pad]))[0]
 
 
+class EngineLayout:
+    """`uvc_vit_layout` for the whole-model engine (include/uvc_b200.h): Stage-2 TRAINING on the physically compacted model.  Built from a
+    `compile_layout` result; owns the device index arrays the C struct points to.
+
+    Rules the engine asks for: every executed block keeps >= 1 head and a multiple of 64 (>= 64) neurons -- the lists are topped up with
+    pruned entries, whose masked weights are zero and therefore change nothing (post_train.py:357-360 keeps them zero).  Each row of
+    `neuron_idx` / `head_idx` is a permutation: the live entries first (ascending), then the pruned ones.
+    `keep_pruned_heads=True` keeps all heads (only blocks and neurons are compacted): the exact-clip-norm mode, see DESIGN.md."""
+
+    def __init__(self, layout, device, keep_pruned_heads=False):
+        from ._lib import VitLayout
+        L, H, Fh = layout["L"], layout["H"], layout["Fh"]
+        head_idx = torch.zeros(L, H, dtype=torch.int32)
+        neuron_idx = torch.zeros(L, Fh, dtype=torch.int32)
+        st = VitLayout()
+        self.heads, self.neurons = [], []
+        for l, b in enumerate(layout["blocks"]):
+            if b is None:                                   # hard-skipped: never looked at
+                heads, neurons = list(range(H)), torch.arange(Fh)
+            else:
+                heads = list(range(H)) if keep_pruned_heads else (list(b["heads"]) or [0])
+                neurons = b["neurons"] if b["neurons"].numel() else torch.arange(0)
+                neurons = _pad_index(neurons, Fh, 64) if neurons.numel() else torch.arange(min(64, Fh))
+            dead_h = [h for h in range(H) if h not in set(heads)]
+            head_idx[l] = torch.tensor(heads + dead_h, dtype=torch.int32)
+            live = torch.zeros(Fh, dtype=torch.bool); live[neurons] = True
+            neuron_idx[l] = torch.cat([torch.nonzero(live).flatten(), torch.nonzero(~live).flatten()]).to(torch.int32)
+            st.n_heads[l], st.n_neurons[l] = len(heads), int(neurons.numel())
+            self.heads.append(heads); self.neurons.append(neurons)
+        self.head_idx, self.neuron_idx = head_idx.to(device).contiguous(), neuron_idx.to(device).contiguous()
+        st.head_idx, st.neuron_idx = self.head_idx.data_ptr(), self.neuron_idx.data_ptr()
+        self.struct, self.layout, self.keep_pruned_heads = st, layout, keep_pruned_heads
+
+    def executed_macs_ratio(self, n_tokens=197):
+        """MACs the compacted engine executes per image / dense MACs (heads at full width, neurons as padded)."""
+        lay = self.layout
+        C_, H, Fh, d, N = lay["C"], lay["H"], lay["Fh"], lay["head_dim"], n_tokens
+        embed = (N - 1) * 768 * C_
+        dense = embed + lay["L"] * (N * C_ * 3 * C_ + 2 * H * N * N * d + N * C_ * C_ + 2 * N * C_ * Fh)
+        comp = embed
+        for b, hs, ns in zip(lay["blocks"], self.heads, self.neurons):
+            if b is not None:
+                h, f = len(hs), int(ns.numel())
+                comp += N * C_ * 3 * h * d + 2 * h * N * N * d + N * h * d * C_ + 2 * N * C_ * f
+        return comp / dense
+
+
+def engine_layout_for(model, keep_pruned_heads=False):
+    """Masks + gates of a live Stage-2 model -> EngineLayout on the model's device."""
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()
+          if k.endswith(".mask") or k == "block_skip_gating" or k in ("blocks.0.attn.proj.weight", "blocks.0.mlp.fc1.weight")}
+    return EngineLayout(compile_layout(sd, model.blocks[0].attn.num_heads), model.cls_token.device, keep_pruned_heads)
+
+
 def _masked(sd, key):
     w = sd[key]
     m = sd.get(key[:-len("weight")] + "mask") if key.endswith("weight") else None

@@ -105,6 +105,7 @@ extern "C" int uvc_abi_sizeof(const char* name) {
   UVC_SZ(uvc_block_tensors);
   UVC_SZ(uvc_vit_tensors);
   UVC_SZ(uvc_vit_dims);
+  UVC_SZ(uvc_vit_layout);
   UVC_SZ(uvc_vit_forward_args);
   UVC_SZ(uvc_vit_backward_args);
   UVC_SZ(uvc_admm_args);

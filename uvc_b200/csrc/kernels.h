@@ -2,6 +2,7 @@
 // its arguments, enqueues on `st` and returns a uvc_status; the extern "C" entry points in
 // include/uvc_b200.h are thin wrappers over these, and vit_engine.cu composes them into the model.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace uvc {
@@ -55,6 +56,26 @@ int attention_fwd_f16(const void* qkv16, void* ctx16, float* lse, int B, int H, 
 // dqkv_bias (optional, fp32 [3*H*64]) += db_scale * column sums of dqkv
 int attention_bwd_f16(const void* qkv16, const float* lse, const void* ctx16, const void* dctx16, float* Dv, void* dqkv16, int B, int H, int N,
                       float scale, cudaStream_t st, float* dqkv_bias = nullptr, float db_scale = 1.0f, const float* db_scale_dev = nullptr);
+
+// Stage-2 compaction (compact.cu).  AxisMap sends a compact row / column number to its dense one: the axis is `nsect` sections of
+// `per` = n_live * group compact entries; entry w of a section is member (w % group) of live group idx[w / group]; dense sections are
+// sect_stride apart.  (heads: group 64, qkv rows: 3 sections C apart; neurons: group 1.)  idx == NULL: identity.
+struct AxisMap { const int* idx; int per, group, sect_stride; };
+struct GatherSeg {            // dst[r, c] = src[rmap(r) * src_ld + cmap(c)] for a compact [rows, cols] matrix; any of the three outputs may be NULL
+  const float* src; long long src_ld;
+  __half* dst16; __half* dstT16; float* dst32;
+  int rows, cols;
+  AxisMap rmap, cmap;
+};
+struct ScatterSeg {           // dst[rmap(r) * dst_ld + cmap(c)] += src[r, c]
+  const float* src; float* dst; long long dst_ld;
+  int rows, cols;
+  AxisMap rmap, cmap;
+};
+int gather_cvt(const GatherSeg* segs, int nseg, cudaStream_t st);
+int scatter_add(const ScatterSeg* segs, int nseg, cudaStream_t st);
+// dW[:, dead[j]] += gelu(fc1_b[dead[j]]) * db_call[:] ; db += db_call   (closed-form gradient of the masked fc2 columns, see compact.cu)
+int pruned_fc2_grad(float* dW, long long ldw, float* db, const float* db_call, const float* fc1_b, const int* dead, int n_dead, int C, cudaStream_t st);
 
 // timm batch-mode mixup / cutmix + mixed smoothed targets (input_pipeline.cu)
 int mixup_batch(float* x, const long long* y, float* targets, int B, int C, int H, int W, int NC, float lam, float smoothing, int use_cutmix, int yl, int yh,

@@ -207,6 +207,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
   if (a.dims.operand_f16) return vit_forward_f16(a, D, st);
+  UVC_REQUIRE(!a.layout, UVC_ERR_BAD_ARG, "vit_forward: a compaction layout needs operand_f16 = 1");
   UVC_TRY(check_tensors(a.w, D.L, "w", a.pe_in == nullptr));
   UVC_REQUIRE((a.x || a.pe_in) && a.logits && a.workspace, UVC_ERR_BAD_ARG, "vit_forward: NULL x / logits / workspace");
   const bool save = a.save_for_backward != 0;
@@ -273,6 +274,7 @@ int vit_backward(const uvc_vit_backward_args& a, cudaStream_t st) {
   Dims D;
   UVC_TRY(check_dims(a.dims, &D));
   if (a.dims.operand_f16) return vit_backward_f16(a, D, st);
+  UVC_REQUIRE(!a.layout, UVC_ERR_BAD_ARG, "vit_backward: a compaction layout needs operand_f16 = 1");
   UVC_TRY(check_tensors(a.w, D.L, "w", a.d_pe == nullptr));
   UVC_TRY(check_tensors(a.g, D.L, "g", a.d_pe == nullptr));
   UVC_REQUIRE(a.dlogits && a.workspace, UVC_ERR_BAD_ARG, "vit_backward: NULL dlogits / workspace");
@@ -391,8 +393,31 @@ struct Ws16 {
   Layer16 layer[UVC_MAX_DEPTH];
   float *g_a, *g_b, *g_c, *Dv, *dcls_ln, *dpe, *dlog_pad, *scales;
   h16 *g16, *dx1_16, *dln16, *dctx16, *dh16, *dqkv16;
+  // Stage-2 compaction (uvc_vit_layout): gathered qkv / fc1 biases per block, and one block's compact weight / bias gradients
+  float *qkv_bc[UVC_MAX_DEPTH], *fc1_bc[UVC_MAX_DEPTH];
+  float *cg_qkv_w, *cg_qkv_b, *cg_proj_w, *cg_fc1_w, *cg_fc1_b, *cg_fc2_w, *cg_fc2_b; size_t cg_floats;
   size_t bytes;
 };
+
+// widths of block l: dense, or the live widths of a compacted block
+struct BlockShape { int Hl, Cl, Ql, Fl; const int* hidx; const int* nidx; };
+inline BlockShape block_shape(const Dims& D, const uvc_vit_layout* lay, int l) {
+  BlockShape s;
+  s.Hl = lay ? lay->n_heads[l] : D.H; s.Cl = s.Hl * D.d; s.Ql = 3 * s.Cl; s.Fl = lay ? lay->n_neurons[l] : D.Fh;
+  s.hidx = lay ? lay->head_idx + (size_t)l * D.H : nullptr; s.nidx = lay ? lay->neuron_idx + (size_t)l * D.Fh : nullptr;
+  return s;
+}
+int check_layout(const uvc_vit_layout* lay, const Dims& D, const uint8_t* skip_host) {
+  if (!lay) return UVC_OK;
+  UVC_REQUIRE(lay->head_idx && lay->neuron_idx, UVC_ERR_BAD_ARG, "vit: layout without index arrays");
+  for (int l = 0; l < D.L; ++l) {
+    if (skip_host && skip_host[l]) continue;
+    UVC_REQUIRE(lay->n_heads[l] >= 1 && lay->n_heads[l] <= D.H, UVC_ERR_BAD_SHAPE, "vit: layout block %d keeps %d heads (1..%d)", l, lay->n_heads[l], D.H);
+    UVC_REQUIRE(lay->n_neurons[l] >= 64 && lay->n_neurons[l] <= D.Fh && lay->n_neurons[l] % 64 == 0, UVC_ERR_BAD_SHAPE,
+                "vit: layout block %d keeps %d neurons (64..%d, a multiple of 64)", l, lay->n_neurons[l], D.Fh);
+  }
+  return UVC_OK;
+}
 
 struct Bump16 : Bump {
   using Bump::Bump;
@@ -409,13 +434,20 @@ void carve16(const Dims& D, bool save, void* base, size_t cap, Ws16* w) {
     if (save) { w->qkv_wT[l] = b.h(3 * C * C); w->proj_wT[l] = b.h(C * C); w->fc1_wT[l] = b.h(Fh * C); w->fc2_wT[l] = b.h(C * Fh); }
     else w->qkv_wT[l] = w->proj_wT[l] = w->fc1_wT[l] = w->fc2_wT[l] = nullptr;
   }
+  for (int l = 0; l < D.L; ++l) { w->qkv_bc[l] = b.f(3 * C); w->fc1_bc[l] = b.f(Fh); }
   w->cols = b.f((size_t)D.B * D.np * D.Kp);
   w->pe = b.f((size_t)D.B * D.np * C);
   w->tok = b.f(M * C);
   w->mean_f = b.f(D.B); w->rstd_f = b.f(D.B);
   w->cls_ln = b.f((size_t)D.B * C);
   w->accum = b.f(M * C);
+  w->cg_qkv_w = w->cg_qkv_b = w->cg_proj_w = w->cg_fc1_w = w->cg_fc1_b = w->cg_fc2_w = w->cg_fc2_b = nullptr; w->cg_floats = 0;
   if (save) {
+    // one contiguous run (zeroed by one memset per block)
+    const size_t cg0 = b.off;
+    w->cg_qkv_w = b.f(3 * C * C); w->cg_qkv_b = b.f(3 * C); w->cg_proj_w = b.f(C * C); w->cg_fc1_w = b.f(Fh * C); w->cg_fc1_b = b.f(Fh);
+    w->cg_fc2_w = b.f(C * Fh); w->cg_fc2_b = b.f(C);
+    w->cg_floats = (b.off - cg0) / sizeof(float);
     for (int l = 0; l < D.L; ++l) {
       Layer16& L = w->layer[l];
       L.mean1 = b.f(M); L.rstd1 = b.f(M); L.mean2 = b.f(M); L.rstd2 = b.f(M); L.lse = b.f(lsz);
@@ -471,17 +503,39 @@ int linear_wgrad16(const h16* dY, long long lddy, const h16* X, long long ldx, f
   return gemm_tf32(a, st);
 }
 
-int convert_weights16(const uvc_vit_tensors& p, const Dims& D, const Ws16& w, bool save, cudaStream_t st) {
-  const float* src[4 * UVC_MAX_DEPTH]; void* dst[4 * UVC_MAX_DEPTH]; void* dstT[4 * UVC_MAX_DEPTH]; int rows[4 * UVC_MAX_DEPTH], cols[4 * UVC_MAX_DEPTH];
-  int k = 0;
-  for (int l = 0; l < D.L; ++l) {
-    const uvc_block_tensors& b = p.blocks[l];
-    src[k] = b.qkv_w; dst[k] = w.qkv_w[l]; dstT[k] = w.qkv_wT[l]; rows[k] = 3 * D.C; cols[k++] = D.C;
-    src[k] = b.proj_w; dst[k] = w.proj_w[l]; dstT[k] = w.proj_wT[l]; rows[k] = D.C; cols[k++] = D.C;
-    src[k] = b.fc1_w; dst[k] = w.fc1_w[l]; dstT[k] = w.fc1_wT[l]; rows[k] = D.Fh; cols[k++] = D.C;
-    src[k] = b.fc2_w; dst[k] = w.fc2_w[l]; dstT[k] = w.fc2_wT[l]; rows[k] = D.C; cols[k++] = D.Fh;
+int convert_weights16(const uvc_vit_tensors& p, const Dims& D, const Ws16& w, bool save, cudaStream_t st, const uvc_vit_layout* lay = nullptr,
+                      const uint8_t* skip_host = nullptr) {
+  if (lay) {
+    // compacted blocks: gather the live rows / columns while converting (compact.cu); biases of the compacted outputs ride along
+    GatherSeg seg[6 * UVC_MAX_DEPTH];
+    int k = 0;
+    const int C = D.C, d = D.d;
+    for (int l = 0; l < D.L; ++l) {
+      if (skip_host && skip_host[l]) continue;
+      const uvc_block_tensors& b = p.blocks[l];
+      const BlockShape s = block_shape(D, lay, l);
+      const AxisMap none{nullptr, 0, 0, 0};
+      const AxisMap qrows{s.hidx, s.Cl, d, C}, hcols{s.hidx, s.Cl, d, 0}, nmap{s.nidx, s.Fl, 1, 0};
+      seg[k++] = GatherSeg{b.qkv_w, C, w.qkv_w[l], save ? w.qkv_wT[l] : nullptr, nullptr, s.Ql, C, qrows, none};
+      seg[k++] = GatherSeg{b.proj_w, C, w.proj_w[l], save ? w.proj_wT[l] : nullptr, nullptr, C, s.Cl, none, hcols};
+      seg[k++] = GatherSeg{b.fc1_w, C, w.fc1_w[l], save ? w.fc1_wT[l] : nullptr, nullptr, s.Fl, C, nmap, none};
+      seg[k++] = GatherSeg{b.fc2_w, D.Fh, w.fc2_w[l], save ? w.fc2_wT[l] : nullptr, nullptr, C, s.Fl, none, nmap};
+      if (b.qkv_b) seg[k++] = GatherSeg{b.qkv_b, 3 * C, nullptr, nullptr, w.qkv_bc[l], 1, s.Ql, none, AxisMap{s.hidx, s.Cl, d, C}};
+      seg[k++] = GatherSeg{b.fc1_b, D.Fh, nullptr, nullptr, w.fc1_bc[l], 1, s.Fl, none, nmap};
+    }
+    UVC_TRY(gather_cvt(seg, k, st));
+  } else {
+    const float* src[4 * UVC_MAX_DEPTH]; void* dst[4 * UVC_MAX_DEPTH]; void* dstT[4 * UVC_MAX_DEPTH]; int rows[4 * UVC_MAX_DEPTH], cols[4 * UVC_MAX_DEPTH];
+    int k = 0;
+    for (int l = 0; l < D.L; ++l) {
+      const uvc_block_tensors& b = p.blocks[l];
+      src[k] = b.qkv_w; dst[k] = w.qkv_w[l]; dstT[k] = w.qkv_wT[l]; rows[k] = 3 * D.C; cols[k++] = D.C;
+      src[k] = b.proj_w; dst[k] = w.proj_w[l]; dstT[k] = w.proj_wT[l]; rows[k] = D.C; cols[k++] = D.C;
+      src[k] = b.fc1_w; dst[k] = w.fc1_w[l]; dstT[k] = w.fc1_wT[l]; rows[k] = D.Fh; cols[k++] = D.C;
+      src[k] = b.fc2_w; dst[k] = w.fc2_w[l]; dstT[k] = w.fc2_wT[l]; rows[k] = D.C; cols[k++] = D.Fh;
+    }
+    UVC_TRY(cvt_f16_segs(src, dst, save ? dstT : nullptr, rows, cols, k, st));
   }
-  UVC_TRY(cvt_f16_segs(src, dst, save ? dstT : nullptr, rows, cols, k, st));
   // patch embed / head stay TF32
   const float* s2[2]; float* d2[2]; long long n2[2]; int m = 0;
   if (p.patch_w) { s2[m] = p.patch_w; d2[m] = w.patch_w; n2[m++] = (long long)D.C * D.Kp; }
@@ -505,11 +559,13 @@ int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t s
   carve16(D, save, a.workspace, a.workspace_bytes, &w);
   UVC_REQUIRE(w.bytes <= a.workspace_bytes, UVC_ERR_WORKSPACE, "vit_forward: workspace %llu bytes < required %llu",
               (unsigned long long)a.workspace_bytes, (unsigned long long)w.bytes);
-  const int M = (int)D.M, C = D.C, Fh = D.Fh;
+  const int M = (int)D.M, C = D.C;
   const float eps = a.dims.ln_eps;
   const float scale = 1.0f / sqrtf((float)D.d);
 
-  UVC_TRY(convert_weights16(a.w, D, w, save, st));
+  const uvc_vit_layout* lay = a.layout;
+  UVC_TRY(check_layout(lay, D, a.skip_host));
+  UVC_TRY(convert_weights16(a.w, D, w, save, st, lay, a.skip_host));
   const float* pe = a.pe_in;
   if (!pe) {
     UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
@@ -536,18 +592,22 @@ int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t s
     if (!skipped) {
       const uvc_block_tensors& p = a.w.blocks[l];
       Layer16& L = w.layer[l];
+      // widths of this block: dense, or (Stage-2 layout) its live heads / neurons -- the operand copies were gathered to these widths above
+      const BlockShape s = block_shape(D, lay, l);
+      const float* qkv_b = (lay && p.qkv_b) ? w.qkv_bc[l] : p.qkv_b;
+      const float* fc1_b = lay ? w.fc1_bc[l] : p.fc1_b;
       UVC_TRY(layernorm_fwd(x, C, p.norm1_w, p.norm1_b, eps, nullptr, C, L.mean1, L.rstd1, M, C, st, 0, L.ln1));
-      UVC_TRY(linear16(L.ln1, C, w.qkv_w[l], p.qkv_b, nullptr, L.qkv, 3 * C, M, 3 * C, C, st));
-      UVC_TRY(attention_fwd_f16(L.qkv, L.ctx, save ? L.lse : nullptr, D.B, D.H, D.ntok, scale, st));
-      UVC_TRY(linear16(L.ctx, C, w.proj_w[l], p.proj_b, L.x1, nullptr, C, M, C, C, st, 0, nullptr, x, C));            // x1 = x + proj(ctx)
+      UVC_TRY(linear16(L.ln1, C, w.qkv_w[l], qkv_b, nullptr, L.qkv, s.Ql, M, s.Ql, C, st));
+      UVC_TRY(attention_fwd_f16(L.qkv, L.ctx, save ? L.lse : nullptr, D.B, s.Hl, D.ntok, scale, st));
+      UVC_TRY(linear16(L.ctx, s.Cl, w.proj_w[l], p.proj_b, L.x1, nullptr, C, M, C, s.Cl, st, 0, nullptr, x, C));        // x1 = x + proj(ctx)
       UVC_TRY(layernorm_fwd(L.x1, C, p.norm2_w, p.norm2_b, eps, nullptr, C, L.mean2, L.rstd2, M, C, st, 0, L.ln2));
-      UVC_TRY(linear16(L.ln2, C, w.fc1_w[l], p.fc1_b, nullptr, L.h, Fh, M, Fh, C, st, UVC_EPI_GELU, L.hpre));         // h = gelu(fc1) (fp16); hpre = gelu'(fc1) (fp16)
+      UVC_TRY(linear16(L.ln2, C, w.fc1_w[l], fc1_b, nullptr, L.h, s.Fl, M, s.Fl, C, st, UVC_EPI_GELU, L.hpre));         // h = gelu(fc1) (fp16); hpre = gelu'(fc1) (fp16)
       if (a.blend) {
         // t = x1 + fc2(h) and the gate blend x <- d1 t + d0 x in ONE epilogue (t is kept only for the backward's gate gradient)
-        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C, nullptr, nullptr, nullptr, a.blend + 2 * l, x,
+        UVC_TRY(linear16(L.h, s.Fl, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, s.Fl, st, 0, nullptr, L.x1, C, nullptr, nullptr, nullptr, a.blend + 2 * l, x,
                          save ? L.t : nullptr));
       } else {
-        UVC_TRY(linear16(L.h, Fh, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, Fh, st, 0, nullptr, L.x1, C));
+        UVC_TRY(linear16(L.h, s.Fl, w.fc2_w[l], p.fc2_b, L.xout, nullptr, C, M, C, s.Fl, st, 0, nullptr, L.x1, C));
       }
       x = L.xout;
     }
@@ -568,8 +628,10 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
   carve16(D, true, a.workspace, a.workspace_bytes, &w);
   UVC_REQUIRE(w.bytes <= a.workspace_bytes, UVC_ERR_WORKSPACE, "vit_backward: workspace %llu bytes < required %llu",
               (unsigned long long)a.workspace_bytes, (unsigned long long)w.bytes);
-  const int M = (int)D.M, C = D.C, Fh = D.Fh;
+  const int M = (int)D.M, C = D.C;
   const float scale = 1.0f / sqrtf((float)D.d);
+  const uvc_vit_layout* lay = a.layout;
+  UVC_TRY(check_layout(lay, D, a.skip_host));
   const size_t xbytes = (size_t)M * C * sizeof(float);
   // loss scale of the fp16 gradient operands: device scalars {S, 1/S} (fixed by the caller, or the largest power of two with S max|dlogits| <= 128)
   const float* Sd = w.scales; const float* invSd = w.scales + 1;
@@ -610,25 +672,51 @@ int vit_backward_f16(const uvc_vit_backward_args& a, const Dims& D, cudaStream_t
       const float* x = xin[l];
       const float* d = a.blend ? a.blend + 2 * l : nullptr;
       const float* d1 = d ? d + 1 : nullptr;
+      // Stage-2 layout: the block ran at its live widths; its weight / bias gradients are formed compact in scratch (zeroed here, the split-K
+      // GEMMs accumulate) and scattered into the dense gradient tensors at the end of the block.
+      const BlockShape s = block_shape(D, lay, l);
+      float* g_qkv_w = lay ? w.cg_qkv_w : gp.qkv_w; float* g_qkv_b = lay ? (gp.qkv_b ? w.cg_qkv_b : nullptr) : gp.qkv_b;
+      float* g_proj_w = lay ? w.cg_proj_w : gp.proj_w;
+      float* g_fc1_w = lay ? w.cg_fc1_w : gp.fc1_w; float* g_fc1_b = lay ? w.cg_fc1_b : gp.fc1_b;
+      float* g_fc2_w = lay ? w.cg_fc2_w : gp.fc2_w;
+      if (lay) {
+        e = cudaMemsetAsync(w.cg_qkv_w, 0, w.cg_floats * sizeof(float), st);
+        UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "vit_backward: memset (compact gradients): %s", cudaGetErrorString(e));
+      }
       // ---- MLP:  t = x1 + fc2(gelu(fc1(ln2))); dt = d1 g is never materialised (d1 rides as a device-scalar alpha).  The gate gradients
       // dd1 = <g, t>, dd0 = <g, x> are folded into the two LayerNorm backward kernels below, which stream g (and x) anyway.
-      UVC_TRY(linear_wgrad16(w.g16, C, L.h, Fh, gp.fc2_w, M, C, Fh, invSd, st, d1));
-      UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, Fh, M, Fh, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, gp.fc1_b, invSd));   // dhpre (x S)
-      UVC_TRY(linear_wgrad16(w.dh16, Fh, L.ln2, C, gp.fc1_w, M, Fh, C, invSd, st));
-      UVC_TRY(linear16(w.dh16, Fh, w.fc1_wT[l], nullptr, nullptr, w.dln16, C, M, C, Fh, st));                                                          // dln2 (x S)
+      UVC_TRY(linear_wgrad16(w.g16, C, L.h, s.Fl, g_fc2_w, M, C, s.Fl, invSd, st, d1));
+      UVC_TRY(linear16(w.g16, C, w.fc2_wT[l], nullptr, nullptr, w.dh16, s.Fl, M, s.Fl, C, st, UVC_EPI_GELU_BWD, L.hpre, nullptr, 0, d1, g_fc1_b, invSd));   // dhpre (x S)
+      UVC_TRY(linear_wgrad16(w.dh16, s.Fl, L.ln2, C, g_fc1_w, M, s.Fl, C, invSd, st));
+      UVC_TRY(linear16(w.dh16, s.Fl, w.fc1_wT[l], nullptr, nullptr, w.dln16, C, M, C, s.Fl, st));                                                      // dln2 (x S)
       // dx1 = dt + LN2'(dln2); fc2.bias / proj.bias gradients ride along as column sums
       UVC_TRY(layernorm_bwd(nullptr, C, L.x1, C, L.mean2, L.rstd2, p.norm2_w, d ? nullptr : g, d ? g : nullptr, d1, spare2, C, gp.norm2_w, gp.norm2_b,
-                            M, C, st, gp.fc2_b, gp.proj_b, w.dln16, 1.0f, w.dx1_16, 1.0f, w.scales, d ? L.t : nullptr, d ? a.d_blend + 2 * l : nullptr, 0));
+                            M, C, st, lay ? w.cg_fc2_b : gp.fc2_b, gp.proj_b, w.dln16, 1.0f, w.dx1_16, 1.0f, w.scales, d ? L.t : nullptr,
+                            d ? a.d_blend + 2 * l : nullptr, 0));
+      // compacted block: the masked fc2 columns still have the reference's (closed-form) gradient; this call's d fc2.bias joins the dense one
+      if (lay) UVC_TRY(pruned_fc2_grad(gp.fc2_w, D.Fh, gp.fc2_b, w.cg_fc2_b, p.fc1_b, s.nidx + s.Fl, D.Fh - s.Fl, C, st));
       float* dx1 = spare2;
       // ---- attention:  x1 = x + proj(ctx)
-      UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, C, gp.proj_w, M, C, C, invSd, st));
-      UVC_TRY(linear16(w.dx1_16, C, w.proj_wT[l], nullptr, nullptr, w.dctx16, C, M, C, C, st));                                                        // dctx (x S)
-      UVC_TRY(attention_bwd_f16(L.qkv, L.lse, L.ctx, w.dctx16, w.Dv, w.dqkv16, D.B, D.H, D.ntok, scale, st, gp.qkv_b, 1.0f, invSd));
-      UVC_TRY(linear_wgrad16(w.dqkv16, 3 * C, L.ln1, C, gp.qkv_w, M, 3 * C, C, invSd, st));
-      UVC_TRY(linear16(w.dqkv16, 3 * C, w.qkv_wT[l], nullptr, nullptr, w.dln16, C, M, C, 3 * C, st));                                                  // dln1 (x S)
+      UVC_TRY(linear_wgrad16(w.dx1_16, C, L.ctx, s.Cl, g_proj_w, M, C, s.Cl, invSd, st));
+      UVC_TRY(linear16(w.dx1_16, C, w.proj_wT[l], nullptr, nullptr, w.dctx16, s.Cl, M, s.Cl, C, st));                                                  // dctx (x S)
+      UVC_TRY(attention_bwd_f16(L.qkv, L.lse, L.ctx, w.dctx16, w.Dv, w.dqkv16, D.B, s.Hl, D.ntok, scale, st, g_qkv_b, 1.0f, invSd));
+      UVC_TRY(linear_wgrad16(w.dqkv16, s.Ql, L.ln1, C, g_qkv_w, M, s.Ql, C, invSd, st));
+      UVC_TRY(linear16(w.dqkv16, s.Ql, w.qkv_wT[l], nullptr, nullptr, w.dln16, C, M, C, s.Ql, st));                                                    // dln1 (x S)
       // dx = dx1 + LN1'(dln1) + d0 g   (written over spare1); its fp16 operand copy replaces g16 (last read by the fc2 GEMMs above)
       UVC_TRY(layernorm_bwd(nullptr, C, x, C, L.mean1, L.rstd1, p.norm1_w, dx1, d ? g : nullptr, d, spare1, C, gp.norm1_w, gp.norm1_b, M, C, st,
                             nullptr, nullptr, w.dln16, 1.0f, w.g16, 1.0f, w.scales, nullptr, d ? a.d_blend + 2 * l : nullptr, d ? 1 : 0));
+      if (lay) {
+        const AxisMap none{nullptr, 0, 0, 0};
+        const AxisMap qrows{s.hidx, s.Cl, D.d, C}, hcols{s.hidx, s.Cl, D.d, 0}, nmap{s.nidx, s.Fl, 1, 0};
+        ScatterSeg seg[6]; int k = 0;
+        seg[k++] = ScatterSeg{w.cg_qkv_w, gp.qkv_w, C, s.Ql, C, qrows, none};
+        seg[k++] = ScatterSeg{w.cg_proj_w, gp.proj_w, C, C, s.Cl, none, hcols};
+        seg[k++] = ScatterSeg{w.cg_fc1_w, gp.fc1_w, C, s.Fl, C, nmap, none};
+        seg[k++] = ScatterSeg{w.cg_fc2_w, gp.fc2_w, D.Fh, C, s.Fl, none, nmap};
+        if (gp.qkv_b) seg[k++] = ScatterSeg{w.cg_qkv_b, gp.qkv_b, 3 * C, 1, s.Ql, none, qrows};
+        seg[k++] = ScatterSeg{w.cg_fc1_b, gp.fc1_b, D.Fh, 1, s.Fl, none, nmap};
+        UVC_TRY(scatter_add(seg, k, st));
+      }
       float* old = g; g = spare1; spare1 = old;
     }
     if (g_jump && l > 0) {

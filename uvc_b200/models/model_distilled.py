@@ -348,6 +348,9 @@ class DistilledVisionTransformer(VisionTransformer):
         a.enable_jumping = 1 if self.enable_jumping else 0
         logits = torch.empty(B, self.num_classes, device=x.device, dtype=torch.float32)
         a.logits = logits.data_ptr()
+        lay = getattr(self, "compact_layout", None)      # Stage-2 physical compaction (uvc_b200/compact.py:EngineLayout), or None = dense
+        if lay is not None:
+            a.layout = C.pointer(lay.struct)
         ws = self._workspace(B, save)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.uvc_vit_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_forward")
@@ -388,6 +391,9 @@ class DistilledVisionTransformer(VisionTransformer):
             a.d_token_mask = d_tm.data_ptr()
         a.enable_jumping = 1 if self.enable_jumping else 0
         a.grad_scale = float(getattr(self, "grad_scale", 0.0))      # 0: the engine picks the fp16 loss scale from max|dlogits| on the device
+        lay = getattr(self, "compact_layout", None)
+        if lay is not None:
+            a.layout = C.pointer(lay.struct)
         ws = self._workspace(B, True)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.check(lib.uvc_vit_backward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_backward")

@@ -84,6 +84,21 @@ class Stage2Step:
         return {"loss": loss}
 
 
+def set_compact_training(model, mode):
+    """Stage-2 training on the physically compacted model (uvc_b200/compact.py:EngineLayout; include/uvc_b200.h uvc_vit_layout).
+    mode 0: masked-dense, the reference's arithmetic (post_train.py:357-360 multiplies by the zeros);
+    mode 1: skipped blocks, fully pruned heads and pruned neurons are not computed -- same logits, same gradients at every live position; the
+            attn.proj columns of fully pruned heads receive no gradient (they are re-masked to zero anyway, but the reference's clip norm counts them);
+    mode 2: as 1 but pruned heads stay computed, which reproduces the reference's gradient -- and clip norm -- everywhere."""
+    mode = int(mode or 0)
+    if mode == 0:
+        model.compact_layout = None
+        return None
+    from .compact import engine_layout_for
+    model.compact_layout = engine_layout_for(model, keep_pruned_heads=(mode == 2))
+    return model.compact_layout
+
+
 def post_training(args, model, mixup_fn=None, criterion=None, lr=None, weight_decay=None, epochs=None):
     """post_train.py:270-402"""
     epochs = epochs if epochs is not None else args.epochs
@@ -96,6 +111,7 @@ def post_training(args, model, mixup_fn=None, criterion=None, lr=None, weight_de
     model.enable_block_gating = 0            # hard skip by gate comparison, as the Stage-2 constructor default does
     model.block_skip_gating.requires_grad = False
     apply_masks(model)
+    set_compact_training(model, getattr(args, "compact_train", 0))
     ddp_model = DDP(model, message_size=250000000, gradient_predivide_factor=get_world_size(), delay_allreduce=True) \
         if args.local_rank != -1 and get_world_size() > 1 else model
     args.lr = lr * args.train_batch_size * get_world_size() / 512.0
@@ -161,6 +177,9 @@ def build_parser():
     p = jt.build_parser()
     p.add_argument("--checkpoint_dir", default=None, type=str, help="Stage-1 checkpoint (state dict with masks and gates)")
     p.add_argument("--epochs", default=120, type=int)
+    p.add_argument("--compact_train", default=0, type=int, choices=[0, 1, 2],
+                   help="train Stage 2 on the physically compacted model: 1 = blocks + pruned heads + pruned neurons removed, 2 = blocks + neurons only "
+                        "(exact reference clip norm); 0 = masked-dense as the reference")
     p.add_argument("--compact_eval", default=0, type=int,
                    help="validate through the physically compacted model (skipped blocks / pruned heads / pruned neurons removed; same logits)")
     return p
