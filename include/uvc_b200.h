@@ -358,6 +358,55 @@ UVC_API int uvc_vit_forward(const uvc_vit_forward_args* args, void* stream);
 UVC_API int uvc_vit_backward(const uvc_vit_backward_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Tokens-to-token front end of T2T-ViT (T2TViT/models/t2t_vit.py:46-105 with tokens_type = 'performer', token_performer.py:8-69):
+ *   x [B, in_chans, img, img] -> Unfold 7x7/4/2 -> Token_performer(in_chans*49 -> 64) -> Unfold 3x3/2/1 -> Token_performer(576 -> 64)
+ *     -> Unfold 3x3/2/1 -> Linear(576, C) -> tokens [B * (img/16)^2, C]      (token_dim 64, 32 random features, as T2T_module builds them).
+ * One call per pass: soft split + LayerNorm fused into one gather kernel (the unfolded tensor is never materialised), tcgen05 GEMMs with fp16
+ * operands for kqv / proj / mlp / project, the linear attention on CUDA cores with the random features recomputed in the backward.
+ * tokens feed uvc_vit_forward as `pe_in`; its `d_pe` comes back here as d_tokens.  Gradients are ACCUMULATED into g (caller zeroes); `w` of a
+ * Token_performer (the fixed random features) has no gradient.  dropout_p > 0 applies the reference's nn.Dropout(0.1) sites (training mode) with a
+ * stateless hash of (seed, element) -- use the same seed in the forward and the backward call; the random stream is not torch's.
+ */
+typedef struct {
+  const float *norm1_w, *norm1_b;        /* [dim] */
+  const float *kqv_w, *kqv_b;            /* [192, dim], [192]  (k | q | v) */
+  const float *w;                        /* [32, 64] random features */
+  const float *proj_w, *proj_b;          /* [64, 64], [64] */
+  const float *norm2_w, *norm2_b;        /* [64] */
+  const float *mlp0_w, *mlp0_b, *mlp2_w, *mlp2_b;   /* [64, 64], [64] */
+} uvc_performer_tensors;
+typedef struct {
+  uvc_performer_tensors attn1, attn2;    /* tokens_to_token.attention1 / attention2 */
+  const float *project_w, *project_b;    /* [C, 576], [C] */
+} uvc_t2t_tensors;
+typedef struct {
+  int32_t B, img, in_chans, C;
+  float ln_eps;                          /* nn.LayerNorm default 1e-5 */
+} uvc_t2t_dims;
+typedef struct {
+  uvc_t2t_dims dims;
+  uvc_t2t_tensors w;
+  const float* x;                        /* [B, in_chans, img, img] */
+  float* tokens;                         /* [B * (img/16)^2, C] written */
+  int32_t save_for_backward;
+  float dropout_p; uint64_t seed;
+  void* workspace; uint64_t workspace_bytes;
+} uvc_t2t_forward_args;
+typedef struct {
+  uvc_t2t_dims dims;
+  uvc_t2t_tensors w;
+  uvc_t2t_tensors g;                     /* gradients, accumulated into (the `w` slots are ignored); pointers are written through */
+  const float* x;
+  const float* d_tokens;                 /* [B * (img/16)^2, C] */
+  float dropout_p; uint64_t seed;
+  float grad_scale;                      /* loss scale of the fp16 gradient operands; <= 0: picked on the device from max|d_tokens| */
+  void* workspace; uint64_t workspace_bytes;     /* the workspace the forward ran with (save_for_backward = 1) */
+} uvc_t2t_backward_args;
+UVC_API uint64_t uvc_t2t_workspace_bytes(const uvc_t2t_dims* dims, int32_t save_for_backward);
+UVC_API int uvc_t2t_forward(const uvc_t2t_forward_args* args, void* stream);
+UVC_API int uvc_t2t_backward(const uvc_t2t_backward_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * ADMM primal-dual update (uvc_optimizer.py:37-144 + uvc_utils.py:54-73,177-269,315-471) on the device.
  * One argument block for all six entry points; each reads the fields it needs.
  *   W1[l] = blocks[l].attn.proj.weight [C, C] (prunable input columns, grouped in H heads of d),

@@ -124,3 +124,70 @@ def test_t2t_gumbel_gate_training_step_matches_oracle():
     assert rel(blend_g.grad, blend_o.grad) < GRAD_TOL
     for k in ("blocks.0.attn.qkv.weight", "blocks.2.mlp.fc2.weight", "blocks.1.norm2.bias", "cls_token", "head.weight"):
         assert rel(dict(m.named_parameters())[k].grad, sdo[k].grad) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_front_end_tokens_and_gradients_match_oracle(B):
+    """tokens_to_token alone (uvc_t2t_forward / uvc_t2t_backward, csrc/t2t_frontend.cu) against the oracle's restatement of
+    t2t_vit.py:46-105 + token_performer.py:31-69 -- the restatement that is pinned bit for bit to the unmodified reference in test_t2t_oracle.py.
+    Tokens within 1e-3 of the maximum, every parameter gradient within 5e-3 of its maximum."""
+    sd, _ = fx.make_state_dict("t2t_vit_14", 1, seed=41)
+    x, _ = fx.make_batch(B, seed=733)
+    m = build(1, sd).eval()
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point() and k.startswith("tokens_to_token.") and not k.endswith(".w")) for k, v in sd.items()}
+    tok_o, macs_o = vo.t2t_tokens(sdo, x)
+    r = torch.randn(B, 196, 384, generator=fx._gen(733, "dtok")) * 0.05
+    (tok_o * r).sum().backward()
+    n0 = _launches()
+    tok, macs = m.tokens_to_token(x.cuda())
+    assert _launches() > n0 and int(macs) == int(macs_o)
+    assert rel(tok, tok_o) < LOGIT_TOL
+    (tok * r.cuda()).sum().backward()
+    named = dict(m.named_parameters())
+    worst = 0.0
+    for k, v in sdo.items():
+        if not v.requires_grad:
+            continue
+        assert named[k].grad is not None, k
+        e = rel(named[k].grad, v.grad)
+        worst = max(worst, e)
+        assert e < GRAD_TOL, (k, e)
+    assert named["tokens_to_token.attention1.w"].grad is None
+    print(f"t2t front end B={B}: tokens rel err {rel(tok, tok_o):.2e}, worst gradient rel err {worst:.2e}")
+
+
+def test_front_end_dropout_is_train_only_unbiased_and_replayed_in_backward():
+    """nn.Dropout(0.1) of the two Token_performers (token_performer.py:20,28,51,66): off in eval; in train mode the tokens change, their mean over
+    many draws approaches the eval tokens (keep / (1 - p) is unbiased to first order), and the backward replays the forward's mask
+    (finite-difference check of one bias gradient along the same seed)."""
+    sd, _ = fx.make_state_dict("t2t_vit_14", 1, seed=43)
+    x, _ = fx.make_batch(2, seed=734)
+    m = build(1, sd)
+    t2t = m.tokens_to_token
+    xe = x.cuda()
+    with torch.no_grad():
+        t_eval = t2t.eval()(xe)[0]
+        t2t.train()
+        torch.manual_seed(5)
+        t_a = t2t(xe)[0]
+        torch.manual_seed(5)
+        t_b = t2t(xe)[0]
+        t_c = t2t(xe)[0]
+    # the seed comes from torch's (CPU) generator: same seed -> same mask (the per-image kptv sums are fp32 atomics, so equal up to summation order)
+    assert rel(t_a, t_b) < 1e-5 and rel(t_a, t_c) > 1e-2
+    assert rel(t_a, t_eval) > 1e-2                                      # dropout is really on
+    # backward consistency: d/d(project.bias) of sum(tokens * r) is colsum(r) whatever the mask; d/d(attention2.mlp.2.bias) depends on the mask
+    r = torch.randn(2, 196, 384, generator=fx._gen(734, "r")).cuda() * 0.05
+    torch.manual_seed(9)
+    tok = t2t(xe)[0]
+    (tok * r).sum().backward()
+    g = t2t.attention2.mlp[2].bias.grad.clone()
+    base = float((tok.detach() * r).sum())
+    j = int(g.abs().argmax())
+    h = 1e-2
+    with torch.no_grad():
+        t2t.attention2.mlp[2].bias[j] += h
+        torch.manual_seed(9)
+        up = float((t2t(xe)[0] * r).sum())
+    fd = (up - base) / h
+    assert abs(fd - float(g[j])) < 0.05 * abs(float(g[j])) + 1e-3, (fd, float(g[j]))

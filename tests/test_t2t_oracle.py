@@ -76,19 +76,24 @@ def test_host_mirror_state_dict_matches_reference_keys():
     assert all(b.attn.qkv.bias is None for b in m.blocks) and m.norm.eps == 1e-5
 
 
-def test_host_front_end_matches_oracle_on_cpu(cases):
-    """tokens_to_token is host-side torch in this round; its arithmetic must equal the reference's (through the oracle)."""
+def test_front_end_has_no_host_path_and_counts_macs_like_the_oracle(cases):
+    """tokens_to_token runs behind uvc_t2t_forward (csrc/t2t_frontend.cu): on a CPU tensor it must fail loudly, never compute.  Its MAC
+    bookkeeping is host arithmetic and must equal the reference's (through the oracle)."""
     from uvc_b200.T2TViT.models import T2T_ViT
     c = cases["t2t14_d2_b4_grads"]
     sd, x = _inputs(c)
     m = T2T_ViT(tokens_type='performer', embed_dim=384, depth=2, num_heads=6, mlp_ratio=3.).eval()
     m.load_state_dict(sd, strict=False)
     with torch.no_grad():
-        tok, macs = m.tokens_to_token(x)
-        ref, macs_o = vo.t2t_tokens(sd, x)
-    assert (tok - ref).abs().max() <= 2e-5 * ref.abs().max() and int(macs) == int(macs_o)
+        _, macs_o = vo.t2t_tokens(sd, x)
+    t2t = m.tokens_to_token
+    assert t2t.attention1.macs(x.shape[0], 56 * 56) + t2t.attention2.macs(x.shape[0], 28 * 28) == int(macs_o)
     with pytest.raises(Exception, match="CUDA"):
-        m(x)                                       # no CPU path for the backbone
+        t2t(x)
+    with pytest.raises(Exception, match="CUDA"):
+        m(x)                                       # no CPU path for the backbone either
+    with pytest.raises(RuntimeError, match="parameter container"):
+        t2t.attention1(x)
 
 
 @pytest.mark.skipif(not __import__("oracle.ref_shim", fromlist=["x"]).available(), reason="/root/reference not present on this machine")

@@ -35,14 +35,36 @@ def get_sinusoid_encoding(n_position, d_hid):
     return torch.where(even, torch.sin(ang), torch.cos(ang)).float().unsqueeze(0)
 
 
+class _T2TFrontFn(torch.autograd.Function):
+    """One autograd node for the whole front end: forward = uvc_t2t_forward, backward = uvc_t2t_backward."""
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        need_grad = any(ctx.needs_input_grad)
+        tokens, p, seed = mod._engine_forward(x, save=need_grad)
+        ctx.mod, ctx.p, ctx.seed = mod, p, seed
+        ctx.save_for_backward(x)
+        ctx.requires = [q.requires_grad for q in params]
+        return tokens
+
+    @staticmethod
+    def backward(ctx, d_tokens):
+        (x,) = ctx.saved_tensors
+        grads = ctx.mod._engine_backward(x, d_tokens.contiguous().float(), ctx.p, ctx.seed)
+        return (None, None, *[g if r else None for g, r in zip(grads, ctx.requires)])
+
+
 class T2T_module(nn.Module):
-    """Tokens-to-token front end, tokens_type='performer' (t2t_vit.py:46-105): three soft splits (Unfold 7x7/4, 3x3/2, 3x3/2)
-    with a Token_performer after the first two, then a Linear to the embedding width.  Torch device ops (see token_performer.py)."""
+    """Tokens-to-token front end, tokens_type='performer' (t2t_vit.py:46-105): three soft splits (Unfold 7x7/4, 3x3/2, 3x3/2) with a
+    Token_performer after the first two, then a Linear to the embedding width -- on the device ONE call per pass into libuvc_sm100.so
+    (uvc_t2t_forward / uvc_t2t_backward, csrc/t2t_frontend.cu); the sub-modules hold the parameters under the reference's names."""
 
     def __init__(self, img_size=224, tokens_type='performer', in_chans=3, embed_dim=768, token_dim=64):
         super().__init__()
         if tokens_type != 'performer':
             raise NotImplementedError(f"tokens_type={tokens_type!r}: UVC builds t2t_vit_14, which uses 'performer' (t2t_vit.py:248)")
+        if token_dim != 64:
+            raise NotImplementedError("token_dim: the sm_100a front end implements T2T_module's default of 64")
         self.soft_split0 = nn.Unfold(kernel_size=(7, 7), stride=(4, 4), padding=(2, 2))
         self.soft_split1 = nn.Unfold(kernel_size=(3, 3), stride=(2, 2), padding=(1, 1))
         self.soft_split2 = nn.Unfold(kernel_size=(3, 3), stride=(2, 2), padding=(1, 1))
@@ -50,17 +72,99 @@ class T2T_module(nn.Module):
         self.attention2 = Token_performer(dim=token_dim * 3 * 3, in_dim=token_dim, kernel_ratio=0.5)
         self.project = nn.Linear(token_dim * 3 * 3, embed_dim)
         self.num_patches = (img_size // 16) * (img_size // 16)
+        self._ws = {}
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _params(self):
+        return self.attention1.engine_tensors() + self.attention2.engine_tensors() + [self.project.weight, self.project.bias]
+
+    @staticmethod
+    def _fill(tensors):
+        from ..._lib import PerformerTensors, T2TTensors
+        t = T2TTensors()
+        for blk, chunk in ((t.attn1, tensors[:13]), (t.attn2, tensors[13:26])):
+            for name, v in zip(PerformerTensors.NAMES, chunk):
+                setattr(blk, name, None if v is None else v.data_ptr())
+        t.project_w, t.project_b = tensors[26].data_ptr(), tensors[27].data_ptr()
+        return t
+
+    def _dims(self, x):
+        from ..._lib import T2TDims
+        d = T2TDims()
+        d.B, d.in_chans, d.img, d.C = int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), int(self.project.out_features)
+        d.ln_eps = float(self.attention1.norm1.eps)
+        return d
+
+    def _workspace(self, dims, save):
+        import ctypes as C_
+        from ... import _lib
+        key = (dims.B, dims.img, bool(save))
+        ws = self._ws.get(key)
+        dev = self.project.weight.device
+        if ws is None or ws.device != dev:
+            n = int(_lib.load().uvc_t2t_workspace_bytes(C_.byref(dims), 1 if save else 0))
+            if n == 0:
+                raise _lib.UvcError("uvc_t2t_workspace_bytes: " + _lib.load().uvc_last_error().decode())
+            ws = torch.empty(n, dtype=torch.uint8, device=dev)
+            self._ws = {k: v for k, v in self._ws.items() if k[2] != key[2]}
+            self._ws[key] = ws
+        return ws
+
+    def _check(self, x, tensors):
+        from ..._lib import UvcError
+        if not x.is_cuda:
+            raise UvcError("uvc_b200 runs on CUDA tensors only (no CPU fallback): move the model and the batch to a B200")
+        if x.shape[2] != x.shape[3]:
+            raise UvcError("the tokens-to-token front end takes square images")
+        for t in tensors:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise UvcError("tokens_to_token parameters must be contiguous CUDA fp32 tensors")
+
+    def _engine_forward(self, x, save):
+        import ctypes as C_
+        from ... import _lib
+        from ..._lib import T2TForwardArgs
+        params = [p.detach() for p in self._params()]
+        self._check(x, params)
+        a = T2TForwardArgs()
+        a.dims = self._dims(x)
+        a.w = self._fill(params)
+        a.x = x.data_ptr()
+        tokens = torch.empty(x.shape[0], self.num_patches, a.dims.C, device=x.device, dtype=torch.float32)
+        a.tokens = tokens.data_ptr()
+        a.save_for_backward = 1 if save else 0
+        p = float(self.attention1.dp.p) if self.training else 0.0        # the reference's nn.Dropout(0.1) sites are active in train mode only
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0   # CPU generator: reproducible under torch.manual_seed, no device sync
+        a.dropout_p, a.seed = p, seed
+        ws = self._workspace(a.dims, save)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(_lib.load().uvc_t2t_forward(C_.byref(a), C_.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_t2t_forward")
+        return tokens, p, seed
+
+    def _engine_backward(self, x, d_tokens, p, seed):
+        import ctypes as C_
+        from ... import _lib
+        from ..._lib import T2TBackwardArgs
+        params = [q.detach() for q in self._params()]
+        grads = [torch.zeros_like(q) for q in params]
+        a = T2TBackwardArgs()
+        a.dims = self._dims(x)
+        a.w, a.g = self._fill(params), self._fill(grads)
+        a.x, a.d_tokens = x.data_ptr(), d_tokens.data_ptr()
+        a.dropout_p, a.seed = p, seed
+        a.grad_scale = float(getattr(self, "grad_scale", 0.0))
+        ws = self._workspace(a.dims, True)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.check(_lib.load().uvc_t2t_backward(C_.byref(a), C_.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_t2t_backward")
+        return grads
 
     def forward(self, x):
         B = x.shape[0]
-        x = self.soft_split0(x).transpose(1, 2)
-        macs = 0
-        for attn, split in ((self.attention1, self.soft_split1), (self.attention2, self.soft_split2)):
-            x, m = attn(x)
-            macs += m
-            side = math.isqrt(x.shape[1])
-            x = split(x.transpose(1, 2).reshape(B, x.shape[2], side, side)).transpose(1, 2)
-        return self.project(x), macs          # the reference does not count project's MACs either (:105)
+        x = x.contiguous().float()
+        tokens = _T2TFrontFn.apply(self, x, *self._params())
+        side = x.shape[2] // 4
+        macs = self.attention1.macs(B, side * side) + self.attention2.macs(B, (side // 2) ** 2)
+        return tokens, macs          # the reference does not count project's MACs either (:105)
 
 
 class T2T_ViT(DistilledVisionTransformer):

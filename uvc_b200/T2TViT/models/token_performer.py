@@ -1,9 +1,9 @@
-"""Token_performer — the linear-attention layer of the tokens-to-token front end
+"""Token_performer -- the linear-attention layer of the tokens-to-token front end
 (reference UVC/T2TViT/models/token_performer.py:8-69): same constructor, attribute names and state-dict keys.
 
-Scope note (SURVEY.md §8 row a-T / §8f row 2): the front end is ~6 % of T2T-ViT-14's FLOPs and is the NEXT row to move
-behind the C ABI; in this round it is plain torch device ops feeding the engine's `pe_in`.  The 14 backbone blocks —
-where the time goes — run through uvc_vit_forward / uvc_vit_backward.
+The module only HOLDS parameters: the whole front end (both soft splits, both Token_performers, the last soft split and the projection)
+runs as one `uvc_t2t_forward` / `uvc_t2t_backward` call issued by `T2T_module` (uvc_b200/csrc/t2t_frontend.cu).  `macs()` restates the
+reference's own MAC accounting (:54-63, :67).
 """
 import math
 
@@ -25,25 +25,20 @@ class Token_performer(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(self.emb, self.emb), nn.GELU(), nn.Linear(self.emb, self.emb), nn.Dropout(dp2))
         self.m = int(self.emb * kernel_ratio)
         self.w = nn.Parameter(nn.init.orthogonal_(torch.randn(self.m, self.emb)) * math.sqrt(self.m), requires_grad=False)
+        if self.emb != 64 or self.m != 32 or head_cnt != 1 or dp1 != dp2:
+            raise NotImplementedError("the sm_100a front end implements the Token_performer T2T_module builds: emb 64, 32 random features, one head")
 
-    def prm_exp(self, x):
-        """Positive random features of the softmax kernel: exp(w^T x - |x|^2 / 2) / sqrt(m)   (:31-43)."""
-        xd = (x * x).sum(dim=-1, keepdim=True) / 2
-        return torch.exp(x.float() @ self.w.t() - xd) / math.sqrt(self.m)
+    def engine_tensors(self):
+        """parameters in the order of `uvc_performer_tensors` (include/uvc_b200.h)"""
+        return [self.norm1.weight, self.norm1.bias, self.kqv.weight, self.kqv.bias, self.w, self.proj.weight, self.proj.bias,
+                self.norm2.weight, self.norm2.bias, self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias]
 
-    def single_attn(self, x):
-        k, q, v = torch.split(self.kqv(x), self.emb, dim=-1)
-        kp, qp = self.prm_exp(k), self.prm_exp(q)                       # [B, T, m]
-        D = (qp @ kp.sum(dim=1).unsqueeze(-1))                           # [B, T, 1]
-        kptv = v.float().transpose(1, 2) @ kp                            # [B, emb, m]
-        y = (qp @ kptv.transpose(1, 2)) / (D + self.epsilon)             # [B, T, emb]
-        y = v + self.dp(self.proj(y))                                    # v is the skip connection (:51)
-        B, T, dim = x.shape
-        macs = B * (T * dim * 3 * self.emb + 2 * (T * self.emb + self.emb * T * self.emb) + T * self.m + T * self.emb * self.m
-                    + T * self.m * self.emb + T * self.emb * self.emb)   # :54-63
-        return y, macs
+    def macs(self, B, T):
+        """token_performer.py:54-63 (single_attn) + :67 (mlp), for an input [B, T, dim]"""
+        dim = self.kqv.in_features
+        m = B * (T * dim * 3 * self.emb + 2 * (T * self.emb + self.emb * T * self.emb) + T * self.m + T * self.emb * self.m
+                 + T * self.m * self.emb + T * self.emb * self.emb)
+        return m + B * (T * self.emb * self.emb + self.emb * self.emb * self.emb)
 
-    def forward(self, x):
-        x, macs = self.single_attn(self.norm1(x))
-        x = x + self.mlp(self.norm2(x))
-        return x, macs + x.shape[0] * (x.shape[1] * x.shape[2] * self.emb + x.shape[2] * self.emb * self.emb)   # :67
+    def forward(self, *a, **k):
+        raise RuntimeError("Token_performer is a parameter container: run the enclosing T2T_module (one uvc_t2t_forward call)")

@@ -74,6 +74,29 @@ class VitBackwardArgs(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("d_pe", _F), ("layout", C.POINTER(VitLayout))]
 
 
+class PerformerTensors(C.Structure):
+    NAMES = ("norm1_w", "norm1_b", "kqv_w", "kqv_b", "w", "proj_w", "proj_b", "norm2_w", "norm2_b", "mlp0_w", "mlp0_b", "mlp2_w", "mlp2_b")
+    _fields_ = [(n, _F) for n in NAMES]
+
+
+class T2TTensors(C.Structure):
+    _fields_ = [("attn1", PerformerTensors), ("attn2", PerformerTensors), ("project_w", _F), ("project_b", _F)]
+
+
+class T2TDims(C.Structure):
+    _fields_ = [("B", C.c_int32), ("img", C.c_int32), ("in_chans", C.c_int32), ("C", C.c_int32), ("ln_eps", C.c_float)]
+
+
+class T2TForwardArgs(C.Structure):
+    _fields_ = [("dims", T2TDims), ("w", T2TTensors), ("x", _F), ("tokens", _F), ("save_for_backward", C.c_int32), ("dropout_p", C.c_float),
+                ("seed", C.c_uint64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
+class T2TBackwardArgs(C.Structure):
+    _fields_ = [("dims", T2TDims), ("w", T2TTensors), ("g", T2TTensors), ("x", _F), ("d_tokens", _F), ("dropout_p", C.c_float), ("seed", C.c_uint64),
+                ("grad_scale", C.c_float), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
 class AdmmArgs(C.Structure):
     _PP = C.POINTER(C.c_void_p)
     _fields_ = [("L", C.c_int32), ("H", C.c_int32), ("d", C.c_int32), ("Fh", C.c_int32),
@@ -90,7 +113,8 @@ class AdmmArgs(C.Structure):
 
 _ABI_STRUCTS = {"uvc_admm_args": AdmmArgs, "uvc_operand": Operand, "uvc_gemm_args": GemmArgs, "uvc_block_tensors": BlockTensors,
                 "uvc_vit_tensors": VitTensors, "uvc_vit_dims": VitDims, "uvc_vit_layout": VitLayout, "uvc_vit_forward_args": VitForwardArgs,
-                "uvc_vit_backward_args": VitBackwardArgs}
+                "uvc_vit_backward_args": VitBackwardArgs, "uvc_t2t_tensors": T2TTensors, "uvc_t2t_forward_args": T2TForwardArgs,
+                "uvc_t2t_backward_args": T2TBackwardArgs}
 
 # every symbol include/uvc_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -102,6 +126,7 @@ EXPORTS = [
     "uvc_layernorm_fwd_f16", "uvc_layernorm_bwd_f16", "uvc_cvt_f16", "uvc_attention_fwd_f16", "uvc_attention_bwd_f16",
     "uvc_token_gate_fold", "uvc_token_gate_fwd", "uvc_token_gate_bwd", "uvc_token_gate_apply",
     "uvc_mixup",
+    "uvc_t2t_workspace_bytes", "uvc_t2t_forward", "uvc_t2t_backward",
     "uvc_admm_scores", "uvc_admm_prox", "uvc_admm_masks", "uvc_admm_primal", "uvc_admm_dual", "uvc_admm_resource",
 ]
 
@@ -186,6 +211,8 @@ def load():
         "uvc_clip_adamw": [vp, vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, f32, i32, vp],
         "uvc_vit_forward": [C.POINTER(VitForwardArgs), vp],
         "uvc_vit_backward": [C.POINTER(VitBackwardArgs), vp],
+        "uvc_t2t_forward": [C.POINTER(T2TForwardArgs), vp],
+        "uvc_t2t_backward": [C.POINTER(T2TBackwardArgs), vp],
     }
     for name in ("scores", "prox", "masks", "primal", "dual", "resource"):
         protos["uvc_admm_" + name] = [C.POINTER(AdmmArgs), vp]
@@ -201,6 +228,7 @@ def load():
     lib.uvc_gemm_profile_read_kind.restype = C.c_int
     lib.uvc_attn_ldp.argtypes = [i32]; lib.uvc_attn_ldp.restype = i32
     lib.uvc_vit_workspace_bytes.argtypes = [C.POINTER(VitDims), i32]; lib.uvc_vit_workspace_bytes.restype = C.c_uint64
+    lib.uvc_t2t_workspace_bytes.argtypes = [C.POINTER(T2TDims), i32]; lib.uvc_t2t_workspace_bytes.restype = C.c_uint64
     _lib = lib
     return lib
 

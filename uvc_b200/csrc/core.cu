@@ -106,6 +106,9 @@ extern "C" int uvc_abi_sizeof(const char* name) {
   UVC_SZ(uvc_vit_tensors);
   UVC_SZ(uvc_vit_dims);
   UVC_SZ(uvc_vit_layout);
+  UVC_SZ(uvc_t2t_tensors);
+  UVC_SZ(uvc_t2t_forward_args);
+  UVC_SZ(uvc_t2t_backward_args);
   UVC_SZ(uvc_vit_forward_args);
   UVC_SZ(uvc_vit_backward_args);
   UVC_SZ(uvc_admm_args);
