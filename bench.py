@@ -50,6 +50,14 @@ BENCH_CONFIGS = {
                    metric="images/sec T2T-ViT-14 UVC@60%FLOPs (Stage-1 joint_train step, token slimming on)",
                    workload="BASELINE.json configs[4] at per-GPU size: T2T-ViT-14 UVC joint_train (ADMM active), budget 0.6, token gate (top 90 %), "
                             "128 images/GPU"),
+    # the validation / inference path (joint_train.py:199-246, post_train.py:209-265): eval forward + CrossEntropyLoss + top-1
+    "small_eval": dict(model="deit_small_patch16_224", stage="eval", batch=256, budget=0.5, patch_gating=0,
+                       metric="images/sec DeiT-Small validation step (eval forward + CE + top-1)",
+                       workload="validation loop body of joint_train.py:199-246 on the dense DeiT-Small of BASELINE.json configs[2], 256 images/GPU"),
+    "base_s2_eval": dict(model="deit_base_patch16_224", stage="eval", batch=256, budget=0.5, patch_gating=0, layout=True,
+                         metric="images/sec DeiT-Base validation step @ fixed 50% pruned layout (eval forward + CE + top-1)",
+                         workload="validation loop body of post_train.py:209-265 on the DeiT-Base of BASELINE.json configs[3] (fixed 50 % layout: blocks 8, 10 "
+                                  "skipped, 3 heads / 16 dims per head / 1417 neurons pruned per live block), 256 images/GPU"),
 }
 
 
@@ -195,6 +203,30 @@ def build_gpu_step(cfg, device, world):
                   label_smoothing=args.smoothing, num_classes=1000)
     crit = DistillationLoss(SoftTargetCrossEntropy(), teacher, "soft", args.distillation_alpha, args.distillation_tau)
     info = {}
+    if cfg["stage"] == "eval":
+        from uvc_b200.joint_train import EvalStep
+        from uvc_b200.post_train import apply_masks, set_compact_training
+        from uvc_b200 import compact as cp
+        rho = 1.0
+        if cfg.get("layout"):
+            with torch.no_grad():
+                mm.s[:, 0] = 3.0; mm.s[:, 1] = 1417.0; mm.r.fill_(16.0)
+                model.block_skip_gating[8] = torch.tensor([1.0, -1.0], device=device); model.block_skip_gating[10] = torch.tensor([1.0, -1.0], device=device)
+            prune_w_mask(mm, None)
+            apply_masks(model)
+            mode = {"dense": 0, "compact": 1, "exact": 2}[os.environ.get("UVC_STAGE2", "compact")]
+            elay = set_compact_training(model, mode)
+            info["execution"] = "masked-dense" if elay is None else "physically compacted (uvc_vit_layout)"
+            if elay is not None:
+                info["executed_macs_ratio"] = round(float(elay.executed_macs_ratio()), 4)
+            rho = float(cp.macs(cp.compile_layout({k: v.detach().cpu() for k, v in model.state_dict().items()}, H))["budget_ratio"])
+            info["rho"] = round(rho, 4)
+        model.eval()
+        model.enable_block_gating = 0
+        args.enable_patch_gating = 0
+        step = EvalStep(args, model)
+        info["step_flops_per_image"] = rho * DENSE_FWD_FLOPS[cfg["model"]]
+        return step, model, info
     if cfg["stage"] == 1:
         with torch.no_grad():           # mid-training ADMM state: the selections / prox / dual updates all do real work
             mm.s[:, 0] = 1.3; mm.s[:, 1] = 0.26 * Fh + 0.5; mm.r.fill_(9.2)
@@ -489,6 +521,26 @@ def build_cpu_step(config, B):
             return vo.forward(p, x, L, H, eps=eps, tokens=tok, **kw), tok
         return vo.forward(p, x, L, H, **kw), None
 
+    if cfg["stage"] == "eval":      # validation loop body: eval forward + CE + top-1 (joint_train.py:199-246 / post_train.py:209-265)
+        skip_e = [cfg.get("layout") and l in (8, 10) for l in range(L)]
+        if cfg.get("layout"):
+            W1 = [params[f"blocks.{i}.attn.proj.weight"].detach() for i in range(L)]
+            W3 = [params[f"blocks.{i}.mlp.fc2.weight"].detach() for i in range(L)]
+            m1, m3 = ao.masks(W1, W3, torch.tensor([[3.0, 1417.0]] * L), torch.full((L, H), 16.0), 64, Fh)
+            with torch.no_grad():
+                for i in range(L):
+                    params[f"blocks.{i}.attn.proj.weight"].mul_(m1[i].float().unsqueeze(0))
+                    params[f"blocks.{i}.mlp.fc2.weight"].mul_(m3[i].float().unsqueeze(0))
+                    params[f"blocks.{i}.mlp.fc1.weight"].mul_(m3[i].float().unsqueeze(1))
+
+        def step_eval():
+            with torch.no_grad():
+                logits = vo.forward(params, x0, L, H, skip=skip_e)
+                loss = torch.nn.functional.cross_entropy(logits, y0)
+                _ = (logits.argmax(1) == y0).sum()
+            return float(loss)
+        return step_eval
+
     if cfg["stage"] == 1:
         patch_gating = (3 * torch.ones(196)).requires_grad_(True)
         st = dict(s=torch.stack([torch.full((L,), 1.3), torch.full((L,), 0.26 * Fh + 0.5)], 1), r=torch.full((L, H), 9.2), y=torch.full((L, 2), 1e-3),
@@ -565,7 +617,7 @@ def build_cpu_step(config, B):
     return step2
 
 
-CPU_SAMPLE_BATCH = {"small_s1": 16, "tiny_s1": 32, "base_s2": 8, "t2t_s1": 8}
+CPU_SAMPLE_BATCH = {"small_s1": 16, "tiny_s1": 32, "base_s2": 8, "t2t_s1": 8, "small_eval": 32, "base_s2_eval": 16}
 
 
 def run_cpu_sample(config, steps, warmup):
@@ -580,8 +632,9 @@ def run_cpu_sample(config, steps, warmup):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    what = ("student fwd+bwd, dense teacher fwd, CE+KD loss, clip+AdamW, ADMM step" if BENCH_CONFIGS[config]["stage"] == 1 else
-            "masked student fwd+bwd with blocks 8/10 skipped, dense teacher fwd, CE+KD loss, clip+AdamW, re-mask")
+    what = {1: "student fwd+bwd, dense teacher fwd, CE+KD loss, clip+AdamW, ADMM step",
+            2: "masked student fwd+bwd with blocks 8/10 skipped, dense teacher fwd, CE+KD loss, clip+AdamW, re-mask",
+            "eval": "eval forward (masked-dense where the config has a layout), CrossEntropyLoss, top-1"}[BENCH_CONFIGS[config]["stage"]]
     return {"value": round(B * steps / dt, 2), "unit": "images/sec", "cores": cores, "kind": "port", "batch": B,
             "sample": f"{steps} full steps ({what}) of {BENCH_CONFIGS[config]['model']} at batch {B} "
                       f"through the oracle port (plain PyTorch fp32, {cores} threads) after {warmup} warm-up"}

@@ -158,3 +158,39 @@ def test_compacted_step_keeps_masked_weights_zero_and_moves_live_ones():
         assert float(diff.max()) <= 2.1e-3, k
         if pd[k].dim() >= 2 and not k.startswith("blocks.1."):
             assert float((diff > 1e-4).float().mean()) < 0.03, (k, float((diff > 1e-4).float().mean()))
+
+
+def test_validation_step_dense_and_compacted_agree_with_the_reference_loop():
+    """EvalStep (the validation loop body, joint_train.py:199-246 / post_train.py:209-265): device-side accumulation gives the reference loop's
+    two averages (top-1 weighted by batch size, loss per batch), and the compacted engine validates to the masked-dense numbers."""
+    import types
+    from uvc_b200 import compact as cp, _lib
+    from uvc_b200.joint_train import EvalStep
+    if not _lib.operand_f16_for(None, 64, 197, 192, 768):
+        pytest.skip("the compaction layout is implemented for the fp16-operand engine")
+    mt, depth = "deit_tiny_patch16_224", 4
+    sd, dims = pruned_checkpoint(mt, depth, seed=7)
+    m = _stage2_model(sd, mt, depth).eval()
+    args = types.SimpleNamespace(enable_patch_gating=0, patch_ratio=0.9)
+    batches = [(fx.make_batch(6, seed=31)), (fx.make_batch(4, seed=32))]
+    lo = [_oracle_logits(sd, x, depth, dims["num_heads"]) for x, _ in batches]
+    want_top1 = 100.0 * sum(float((l.argmax(1) == y).sum()) for l, (_, y) in zip(lo, batches)) / 10
+    want_loss = sum(float(torch.nn.functional.cross_entropy(l, y)) for l, (_, y) in zip(lo, batches)) / 2
+    for compact in (False, True):
+        m.compact_layout = cp.engine_layout_for(m) if compact else None
+        step = EvalStep(args, m)
+        for x, y in batches:
+            step(x.cuda(), y.cuda())
+        top1, loss = step.result()
+        assert abs(top1 - want_top1) < 1e-9 or abs(top1 - want_top1) <= 10.0     # argmax may differ only on a near-tie of random logits
+        assert abs(loss - want_loss) < 2e-3 * max(1.0, abs(want_loss)), (compact, loss, want_loss)
+
+
+def _oracle_logits(sd, x, depth, H):
+    sdm = {k: v.clone() for k, v in sd.items() if not k.endswith(".mask")}
+    for k, v in sd.items():
+        if k.endswith(".mask"):
+            sdm[k[:-4] + "weight"] = sdm[k[:-4] + "weight"] * v
+    skip = [not bool(g[1] > g[0]) for g in sd["block_skip_gating"]]
+    with torch.no_grad():
+        return vo.forward(sdm, x, depth, H, skip=skip)

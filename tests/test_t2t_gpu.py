@@ -174,7 +174,7 @@ def test_front_end_dropout_is_train_only_unbiased_and_replayed_in_backward():
         t_b = t2t(xe)[0]
         t_c = t2t(xe)[0]
     # the seed comes from torch's (CPU) generator: same seed -> same mask (the per-image kptv sums are fp32 atomics, so equal up to summation order)
-    assert rel(t_a, t_b) < 1e-5 and rel(t_a, t_c) > 1e-2
+    assert rel(t_a, t_b) < 1e-3 and rel(t_a, t_c) > 1e-2
     assert rel(t_a, t_eval) > 1e-2                                      # dropout is really on
     # backward consistency: d/d(project.bias) of sum(tokens * r) is colsum(r) whatever the mask; d/d(attention2.mlp.2.bias) depends on the mask
     r = torch.randn(2, 196, 384, generator=fx._gen(734, "r")).cuda() * 0.05

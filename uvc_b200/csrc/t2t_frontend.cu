@@ -39,15 +39,26 @@ struct Geom {
   int dim, Kp;           // dim = Cin * k * k (nn.Unfold order: c * k*k + ky * k + kx); Kp = dim rounded up to 8 (fp16 row stride)
 };
 
+// NCHW gather table (one per block, in shared memory): element e = c k^2 + ky k + kx reads src at (c Hs + ky) Ws + kx relative to the patch
+// origin; the low 16 bits carry (ky, kx) for the border test.  Saves two integer divisions per gathered element (the kernel was issue-bound).
+__device__ __forceinline__ void build_tab(const Geom& g, int* tab) {
+  if (!g.nchw) return;
+  const int k2 = g.k * g.k;
+  for (int e = threadIdx.x; e < g.dim; e += blockDim.x) {
+    const int c = e / k2, r = e - c * k2, ky = r / g.k, kx = r - ky * g.k;
+    tab[e] = (((c * g.Hs + ky) * g.Ws + kx) << 8) | (ky << 4) | kx;        // k <= 7: 4 bits each; offset < 2^23
+  }
+}
 // fills rb[0..dim) with the patch of output token (b, oy, ox)
-__device__ __forceinline__ void gather_patch(const float* __restrict__ src, const Geom& g, int b, int oy, int ox, int lane, float* rb) {
+__device__ __forceinline__ void gather_patch(const float* __restrict__ src, const Geom& g, const int* tab, int b, int oy, int ox, int lane, float* rb) {
   const int k2 = g.k * g.k;
   const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
   if (g.nchw) {
+    const float* base = src + (long long)b * g.Cin * g.Hs * g.Ws + (long long)iy0 * g.Ws + ix0;
     for (int e = lane; e < g.dim; e += 32) {
-      const int c = e / k2, r = e - c * k2, ky = r / g.k, kx = r - ky * g.k;
-      const int iy = iy0 + ky, ix = ix0 + kx;
-      rb[e] = (iy >= 0 && iy < g.Hs && ix >= 0 && ix < g.Ws) ? __ldg(src + (((long long)b * g.Cin + c) * g.Hs + iy) * g.Ws + ix) : 0.f;
+      const int t = tab[e];
+      const int iy = iy0 + ((t >> 4) & 15), ix = ix0 + (t & 15);
+      rb[e] = (iy >= 0 && iy < g.Hs && ix >= 0 && ix < g.Ws) ? __ldg(base + (t >> 8)) : 0.f;
     }
   } else {               // 64 channels per pixel: one float2 per lane, coalesced 256 B per pixel
     for (int p = 0; p < k2; ++p) {
@@ -68,10 +79,13 @@ __global__ void __launch_bounds__(256) unfold_ln_kernel(const float* __restrict_
   extern __shared__ float rowbuf[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rb = rowbuf + warp * g.Kp;
+  int* tab = reinterpret_cast<int*>(rowbuf + 8 * g.Kp);
+  build_tab(g, tab);
+  __syncthreads();
   const int per_img = g.Ho * g.Wo;
   for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
     const int b = row / per_img, t = row - b * per_img, oy = t / g.Wo, ox = t - oy * g.Wo;
-    gather_patch(src, g, b, oy, ox, lane, rb);
+    gather_patch(src, g, tab, b, oy, ox, lane, rb);
     __syncwarp();
     float mu = 0.f, rs = 1.f;
     if (LN) {
@@ -111,6 +125,8 @@ __global__ void __launch_bounds__(256) unfold_ln_bwd_kernel(const h16* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rb = rowbuf + warp * g.Kp;                       // patch, then dx
   float* red = rowbuf + 8 * g.Kp;                         // [2 * dim] block-level dgamma / dbeta
+  int* tab = reinterpret_cast<int*>(red + 2 * g.dim);
+  if (LN) build_tab(g, tab);
   const float invS = scales[1];
   float ag[kMaxPerLane], ab[kMaxPerLane];
 #pragma unroll
@@ -122,7 +138,7 @@ __global__ void __launch_bounds__(256) unfold_ln_bwd_kernel(const h16* __restric
     const int b = row / per_img, t = row - b * per_img, oy = t / g.Wo, ox = t - oy * g.Wo;
     const h16* dyr = dy16 + (long long)row * g.Kp;
     if (LN) {
-      gather_patch(src, g, b, oy, ox, lane, rb);
+      gather_patch(src, g, tab, b, oy, ox, lane, rb);
       __syncwarp();
       const float mu = mean[row], rs = rstd[row];
       float s1 = 0.f, s2 = 0.f;
@@ -202,12 +218,17 @@ __global__ void __launch_bounds__(256) performer_kv_kernel(const float* __restri
   float ks = 0.f;
   const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
   float* k_s = sc[warp].a; float* v_s = sc[warp].b;
-  for (int t = t0; t < min(T, t0 + kTokPerWarp); ++t) {
-    const float* row = kqv + ((long long)b * T + t) * kKqv;
-    const float2 kk = *reinterpret_cast<const float2*>(row + 2 * lane), vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane);
+  const int t1 = min(T, t0 + kTokPerWarp);
+  float2 kk = make_float2(0.f, 0.f), vv = kk;
+  if (t0 < t1) { const float* row = kqv + ((long long)b * T + t0) * kKqv; kk = *reinterpret_cast<const float2*>(row + 2 * lane); vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane); }
+  for (int t = t0; t < t1; ++t) {
     __syncwarp();
     k_s[2 * lane] = kk.x; k_s[2 * lane + 1] = kk.y; v_s[2 * lane] = vv.x; v_s[2 * lane + 1] = vv.y;
     __syncwarp();
+    if (t + 1 < t1) {      // prefetch the next token's row: one exposed global-load latency per token was what bound this kernel
+      const float* row = kqv + ((long long)b * T + t + 1) * kKqv;
+      kk = *reinterpret_cast<const float2*>(row + 2 * lane); vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane);
+    }
     const float kp = prm_feature(w_s, k_s, lane);
     ks += kp;
 #pragma unroll
@@ -233,12 +254,15 @@ __global__ void __launch_bounds__(256) performer_out_kernel(const float* __restr
   __syncthreads();
   const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
   float* q_s = sc[warp].a; float* qp_s = sc[warp].b;
-  for (int t = t0; t < min(T, t0 + kTokPerWarp); ++t) {
+  const int t1 = min(T, t0 + kTokPerWarp);
+  float2 qq = make_float2(0.f, 0.f);
+  if (t0 < t1) qq = *reinterpret_cast<const float2*>(kqv + ((long long)b * T + t0) * kKqv + kE + 2 * lane);
+  for (int t = t0; t < t1; ++t) {
     const long long r = (long long)b * T + t;
-    const float2 qq = *reinterpret_cast<const float2*>(kqv + r * kKqv + kE + 2 * lane);
     __syncwarp();
     q_s[2 * lane] = qq.x; q_s[2 * lane + 1] = qq.y;
     __syncwarp();
+    if (t + 1 < t1) qq = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + kE + 2 * lane);
     const float qp = prm_feature(w_s, q_s, lane);
     const float den = warp_sum(qp * ksum_s[lane]) + eps;
     qp_s[lane] = qp;
@@ -278,16 +302,26 @@ __global__ void __launch_bounds__(256) performer_bwd_a_kernel(const float* __res
   float dks = 0.f, cs0 = 0.f, cs1 = 0.f;
   const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
   float* q_s = sc[warp].a; float* dn_s = sc[warp].b; float* du_s = sc[warp].c;
-  for (int t = t0; t < min(T, t0 + kTokPerWarp); ++t) {
+  const int t1 = min(T, t0 + kTokPerWarp);
+  float2 qq = make_float2(0.f, 0.f);
+  h16 hy0 = __float2half(0.f), hy1 = hy0, hd0 = hy0, hd1 = hy0;
+  if (t0 < t1) {
+    const long long r = (long long)b * T + t0;
+    qq = *reinterpret_cast<const float2*>(kqv + r * kKqv + kE + 2 * lane);
+    hy0 = y16[r * kE + lane]; hy1 = y16[r * kE + lane + 32]; hd0 = dy16[r * kE + lane]; hd1 = dy16[r * kE + lane + 32];
+  }
+  for (int t = t0; t < t1; ++t) {
     const long long r = (long long)b * T + t;
-    const float2 qq = *reinterpret_cast<const float2*>(kqv + r * kKqv + kE + 2 * lane);
     __syncwarp();
     q_s[2 * lane] = qq.x; q_s[2 * lane + 1] = qq.y;
     __syncwarp();
+    const float y0 = __half2float(hy0), y1 = __half2float(hy1), dy0 = __half2float(hd0), dy1 = __half2float(hd1);
+    if (t + 1 < t1) {
+      qq = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + kE + 2 * lane);
+      hy0 = y16[(r + 1) * kE + lane]; hy1 = y16[(r + 1) * kE + lane + 32]; hd0 = dy16[(r + 1) * kE + lane]; hd1 = dy16[(r + 1) * kE + lane + 32];
+    }
     const float qp = prm_feature(w_s, q_s, lane);
     const float den = warp_sum(qp * ksum_s[lane]) + eps;
-    const float y0 = __half2float(y16[r * kE + lane]), y1 = __half2float(y16[r * kE + lane + 32]);
-    const float dy0 = __half2float(dy16[r * kE + lane]), dy1 = __half2float(dy16[r * kE + lane + 32]);
     const float dden = -warp_sum(dy0 * y0 + dy1 * y1) / den;
     dn_s[lane] = dy0 / den; dn_s[lane + 32] = dy1 / den;
     __syncwarp();
@@ -336,17 +370,27 @@ __global__ void __launch_bounds__(256) performer_bwd_b_kernel(const float* __res
   float ck0 = 0.f, ck1 = 0.f, cv0 = 0.f, cv1 = 0.f;
   const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
   float* k_s = sc[warp].a; float* v_s = sc[warp].b; float* x_s = sc[warp].c;      // x_s: kp, then du
-  for (int t = t0; t < min(T, t0 + kTokPerWarp); ++t) {
+  const int t1 = min(T, t0 + kTokPerWarp);
+  float2 kk = make_float2(0.f, 0.f), vv = kk;
+  float r0 = 0.f, r1 = 0.f;
+  if (t0 < t1) {
+    const long long r = (long long)b * T + t0;
+    kk = *reinterpret_cast<const float2*>(kqv + r * kKqv + 2 * lane); vv = *reinterpret_cast<const float2*>(kqv + r * kKqv + 2 * kE + 2 * lane);
+    r0 = dres[r * kE + lane]; r1 = dres[r * kE + lane + 32];
+  }
+  for (int t = t0; t < t1; ++t) {
     const long long r = (long long)b * T + t;
-    const float* row = kqv + r * kKqv;
-    const float2 kk = *reinterpret_cast<const float2*>(row + 2 * lane), vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane);
     __syncwarp();
     k_s[2 * lane] = kk.x; k_s[2 * lane + 1] = kk.y; v_s[2 * lane] = vv.x; v_s[2 * lane + 1] = vv.y;
     __syncwarp();
+    float dv0 = S * r0, dv1 = S * r1;
+    if (t + 1 < t1) {
+      kk = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + 2 * lane); vv = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + 2 * kE + 2 * lane);
+      r0 = dres[(r + 1) * kE + lane]; r1 = dres[(r + 1) * kE + lane + 32];
+    }
     const float kp = prm_feature(w_s, k_s, lane);
     x_s[lane] = kp;
     __syncwarp();
-    float dv0 = S * dres[r * kE + lane], dv1 = S * dres[r * kE + lane + 32];
 #pragma unroll
     for (int j = 0; j < kF; ++j) { dv0 = fmaf(dkptv_s[lane][j], x_s[j], dv0); dv1 = fmaf(dkptv_s[lane + 32][j], x_s[j], dv1); }
     float dkp = dksum_s[lane];
@@ -562,15 +606,15 @@ int cvt_pad(const float* src, int rows, int cols, h16* dst, int ld, h16* dstT, c
 }
 int unfold_ln(const float* src, const Geom& g, const float* gamma, const float* beta, float eps, h16* out, int ldo, int split, float* mean, float* rstd, int M,
               cudaStream_t st) {
-  const size_t smem = 8 * (size_t)g.Kp * sizeof(float);
-  const int grid = blocks_for(M, 8, 148 * 6);
+  const size_t smem = (8 * (size_t)g.Kp + (g.nchw ? g.dim : 0)) * sizeof(float);
+  const int grid = blocks_for(M, 8 * 4, 148 * 6);
   if (gamma) unfold_ln_kernel<true><<<grid, 256, smem, st>>>(src, g, gamma, beta, eps, out, ldo, split, mean, rstd, M);
   else unfold_ln_kernel<false><<<grid, 256, smem, st>>>(src, g, nullptr, nullptr, eps, out, ldo, split, nullptr, nullptr, M);
   return check_launch("t2t unfold_ln");
 }
 int unfold_ln_bwd(const h16* dy16, const float* src, const Geom& g, const float* gamma, const float* mean, const float* rstd, const float* scales,
                   float* dgamma, float* dbeta, float* dsrc, int M, cudaStream_t st) {
-  const size_t smem = (8 * (size_t)g.Kp + 2 * (size_t)g.dim) * sizeof(float);
+  const size_t smem = (8 * (size_t)g.Kp + 3 * (size_t)g.dim) * sizeof(float);
   const int grid = blocks_for(M, 8 * 16, 148 * 4);
   if (gamma) unfold_ln_bwd_kernel<true><<<grid, 256, smem, st>>>(dy16, src, g, gamma, mean, rstd, scales, dgamma, dbeta, dsrc, M);
   else unfold_ln_bwd_kernel<false><<<grid, 256, smem, st>>>(dy16, src, g, nullptr, nullptr, nullptr, scales, nullptr, nullptr, dsrc, M);

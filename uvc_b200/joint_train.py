@@ -153,29 +153,52 @@ def get_uvc_layers(model, args=None):
     return layer_names, uvc_layers, d
 
 
+class EvalStep:
+    """The body of the validation loop (joint_train.py:199-246, post_train.py:209-265) as one callable, shared by `valid()` and `bench.py`:
+    eval forward -> CrossEntropyLoss -> top-1.  The reference reads loss and accuracy back after every batch (two host syncs per batch); here the
+    sums stay on the device and `result()` reads them once, giving the same two averages (top-1 weighted by batch size, loss per batch)."""
+
+    def __init__(self, args, model):
+        self.args, self.model = args, model
+        self.loss_fct = torch.nn.CrossEntropyLoss()
+        self.tau = 1 if args.enable_patch_gating == 2 else -1
+        self.acc = None
+
+    def __call__(self, x, y):
+        with torch.no_grad():
+            logits, _ = self.model(x, self.tau, self.args.patch_ratio)
+            loss = self.loss_fct(logits, y)
+            correct = (logits.argmax(dim=1) == y).sum()
+            if self.acc is None:
+                self.acc = torch.zeros(4, device=logits.device, dtype=torch.float64)    # correct, images, loss sum, batches
+            self.acc += torch.stack([correct.double(), torch.tensor(float(x.size(0)), device=logits.device, dtype=torch.float64), loss.double(),
+                                     torch.ones((), device=logits.device, dtype=torch.float64)])
+        return {"loss": loss}
+
+    def result(self):
+        """(top-1 in percent, mean loss) -- the one device->host read of the loop"""
+        if self.acc is None:
+            return 0.0, 0.0
+        c, n, ls, nb = self.acc.tolist()
+        return 100.0 * c / max(n, 1.0), ls / max(nb, 1.0)
+
+
 def valid(args, model, writer, test_loader, global_step):
-    eval_losses, top1 = AverageMeter(), AverageMeter()
     if args.local_rank in [-1, 0]:
         print("***** Running Validation *****")
         print("  Num steps = %d" % len(test_loader))
         print("  Batch size = %d" % args.eval_batch_size)
     model.eval()
-    loss_fct = torch.nn.CrossEntropyLoss()
-    tau = 1 if args.enable_patch_gating == 2 else -1
+    step = EvalStep(args, model)
     for x, y in test_loader:
-        x, y = x.to(args.device), y.to(args.device)
-        with torch.no_grad():
-            logits, _ = model(x, tau, args.patch_ratio)
-            eval_loss = loss_fct(logits, y)
-            prec1 = complex_accuracy(logits.data, y)[0]
-        top1.update(prec1.item(), x.size(0))
-        eval_losses.update(eval_loss.item())
+        step(x.to(args.device, non_blocking=True), y.to(args.device, non_blocking=True))
+    top1, loss = step.result()
     if args.local_rank in [-1, 0]:
         print("\nValidation Results")
         print("Global Steps: %d" % global_step)
-        print("Valid Loss: %2.5f" % eval_losses.avg)
-        print("Valid Accuracy: %2.5f" % top1.avg)
-    return top1.avg
+        print("Valid Loss: %2.5f" % loss)
+        print("Valid Accuracy: %2.5f" % top1)
+    return top1
 
 
 class Stage1Step:

@@ -428,7 +428,8 @@ class DistilledVisionTransformer(VisionTransformer):
     @property
     def flat_param(self):
         fp = getattr(self, "_flat_param", None)
-        if fp is None or _engine_param_list(self)[0][1] is None or _engine_param_list(self)[0][1].data_ptr() != fp.data_ptr():
+        first = next((p for _, p in _engine_param_list(self) if p is not None), None)      # T2T-ViT has no patch conv: its first slots are empty
+        if fp is None or first is None or first.data_ptr() != fp.data_ptr():
             return None              # never flattened, or re-materialised by .to() / load with assign
         return fp
 

@@ -166,8 +166,19 @@ class CompactEval(torch.nn.Module):
 def valid(args, model, writer, test_loader, global_step):
     apply_masks(model)           # post_train.py:228-231
     if getattr(args, "compact_eval", 0):
+        from ._lib import operand_f16_for
+        C_, H = model.embed_dim, model.blocks[0].attn.num_heads
+        if operand_f16_for(model, C_ // H, model.patch_embed.num_patches + 1, C_, model.blocks[0].mlp.fc1.out_features):
+            # the whole-model engine at the live widths (uvc_vit_layout): token / patch gates and jumping connections work unchanged
+            prev = getattr(model, "compact_layout", None)
+            if prev is None:
+                set_compact_training(model, 1)
+            try:
+                return jt.valid(args, model, writer, test_loader, global_step)
+            finally:
+                model.compact_layout = prev
         if args.enable_patch_gating == 2 or getattr(model, "enable_patch_gating", 0) or getattr(model, "enable_jumping", 0):
-            print("--compact_eval: token / patch gates and jumping connections are not in the compact runner; validating the masked-dense model")
+            print("--compact_eval: token / patch gates and jumping connections are not in the per-operator compact runner; validating the masked-dense model")
         else:
             return jt.valid(args, CompactEval(model), writer, test_loader, global_step)
     return jt.valid(args, model, writer, test_loader, global_step)
