@@ -115,13 +115,12 @@ __global__ void __launch_bounds__(256) unfold_ln_kernel(const float* __restrict_
 // LN: dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dy gamma; dgamma += dy xhat, dbeta += dy  (xhat recomputed from the gathered patch).
 // dsrc (token-major [B, Hs*Ws, 64], zeroed by the caller; NULL for the image stage) receives the fold: every patch element is added to the
 // pixel it was read from (float2 vector atomics; a pixel is touched by <= 4 patches).
-template <bool LN>
-__global__ void __launch_bounds__(256) unfold_ln_bwd_kernel(const h16* __restrict__ dy16, const float* __restrict__ src, const Geom g,
+template <bool LN, int kMaxPerLane>       // kMaxPerLane = ceil(dim / 32): 5 for the 147-wide image stage (40 fewer registers, twice the resident warps), 18 for 576
+__global__ void __launch_bounds__(256, (kMaxPerLane <= 5 ? 4 : 2)) unfold_ln_bwd_kernel(const h16* __restrict__ dy16, const float* __restrict__ src, const Geom g,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ scales,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dsrc, int M) {
   extern __shared__ float rowbuf[];
-  constexpr int kMaxPerLane = 18;                         // dim <= 576
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* rb = rowbuf + warp * g.Kp;                       // patch, then dx
   float* red = rowbuf + 8 * g.Kp;                         // [2 * dim] block-level dgamma / dbeta
@@ -190,18 +189,49 @@ __global__ void __launch_bounds__(256) unfold_ln_bwd_kernel(const h16* __restric
 constexpr int kWsPerImg = kE * kF + kF;
 constexpr int kTokPerWarp = 16;
 
-struct WarpScratch { float a[kE]; float b[kE]; float c[kE]; };
+// These kernels are bound by the shared-memory pipe (ncu: l1tex throughput 73-83 %, profiles/r02_ncu_t2t_frontend.txt): every FMA of a
+// 64 x 32 contraction reads one DISTINCT word per lane (this lane's element of w / kptv: 128 B per warp instruction) plus one broadcast word.
+// So each warp works on TWO tokens at a time -- every distinct read feeds two FMAs -- and the per-token vectors are read as 128-bit
+// broadcasts (one wavefront for four values): ~60-140 shared-memory wavefronts per token instead of ~200-330.
+struct __align__(16) WarpScratch { float a[2][kE]; float b[2][kE]; float c[2][kE]; };
 
 __device__ __forceinline__ void load_w(const float* __restrict__ w, float (*w_s)[kE + 1]) {
   for (int i = threadIdx.x; i < kF * kE; i += blockDim.x) w_s[i / kE][i % kE] = __ldg(w + i);
 }
-// random feature of one token for this lane's feature j = lane: exp(w_j . x - |x|^2 / 2) / sqrt(m); x_s holds the 64-vector
-__device__ __forceinline__ float prm_feature(const float (*w_s)[kE + 1], const float* x_s, int lane) {
-  float u = 0.f;
-#pragma unroll 16
-  for (int e = 0; e < kE; ++e) u = fmaf(w_s[lane][e], x_s[e], u);
-  const float n2 = warp_sum(x_s[lane] * x_s[lane] + x_s[lane + 32] * x_s[lane + 32]) * 0.5f;
-  return expf(u - n2) * 0.17677669529663687f;     // 1 / sqrt(32)
+// random features of two tokens for this lane's feature j = lane: exp(w_j . x - |x|^2 / 2) / sqrt(m); xa / xb hold the two 64-vectors
+__device__ __forceinline__ void prm_feature2(const float (*w_s)[kE + 1], const float* xa, const float* xb, int lane, float& fa, float& fb) {
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int e = 0; e < kE; e += 4) {
+    const float4 A = *reinterpret_cast<const float4*>(xa + e), B = *reinterpret_cast<const float4*>(xb + e);
+    const float w0 = w_s[lane][e], w1 = w_s[lane][e + 1], w2 = w_s[lane][e + 2], w3 = w_s[lane][e + 3];
+    a0 = fmaf(w0, A.x, a0); a1 = fmaf(w1, A.y, a1); a0 = fmaf(w2, A.z, a0); a1 = fmaf(w3, A.w, a1);
+    b0 = fmaf(w0, B.x, b0); b1 = fmaf(w1, B.y, b1); b0 = fmaf(w2, B.z, b0); b1 = fmaf(w3, B.w, b1);
+  }
+  float na = xa[lane] * xa[lane] + xa[lane + 32] * xa[lane + 32], nb = xb[lane] * xb[lane] + xb[lane + 32] * xb[lane + 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { na += __shfl_xor_sync(0xffffffffu, na, o); nb += __shfl_xor_sync(0xffffffffu, nb, o); }
+  fa = expf((a0 + a1) - 0.5f * na) * 0.17677669529663687f;     // 1 / sqrt(32)
+  fb = expf((b0 + b1) - 0.5f * nb) * 0.17677669529663687f;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+}
+// out_e = sum_j u[j] w_s[j][e] for e = lane, lane + 32 and two tokens (u vectors in shared memory)
+__device__ __forceinline__ void wT_times2(const float (*w_s)[kE + 1], const float* ua, const float* ub, int lane, float& a0, float& a1, float& b0, float& b1) {
+#pragma unroll
+  for (int j = 0; j < kF; j += 4) {
+    const float4 A = *reinterpret_cast<const float4*>(ua + j), B = *reinterpret_cast<const float4*>(ub + j);
+    float w0 = w_s[j][lane], w1 = w_s[j][lane + 32];
+    a0 = fmaf(A.x, w0, a0); a1 = fmaf(A.x, w1, a1); b0 = fmaf(B.x, w0, b0); b1 = fmaf(B.x, w1, b1);
+    w0 = w_s[j + 1][lane]; w1 = w_s[j + 1][lane + 32];
+    a0 = fmaf(A.y, w0, a0); a1 = fmaf(A.y, w1, a1); b0 = fmaf(B.y, w0, b0); b1 = fmaf(B.y, w1, b1);
+    w0 = w_s[j + 2][lane]; w1 = w_s[j + 2][lane + 32];
+    a0 = fmaf(A.z, w0, a0); a1 = fmaf(A.z, w1, a1); b0 = fmaf(B.z, w0, b0); b1 = fmaf(B.z, w1, b1);
+    w0 = w_s[j + 3][lane]; w1 = w_s[j + 3][lane + 32];
+    a0 = fmaf(A.w, w0, a0); a1 = fmaf(A.w, w1, a1); b0 = fmaf(B.w, w0, b0); b1 = fmaf(B.w, w1, b1);
+  }
 }
 
 __global__ void __launch_bounds__(256) performer_kv_kernel(const float* __restrict__ kqv, const float* __restrict__ w, float* __restrict__ ws, int T) {
@@ -216,23 +246,27 @@ __global__ void __launch_bounds__(256) performer_kv_kernel(const float* __restri
 #pragma unroll
   for (int e = 0; e < kE; ++e) acc[e] = 0.f;
   float ks = 0.f;
-  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
-  float* k_s = sc[warp].a; float* v_s = sc[warp].b;
-  const int t1 = min(T, t0 + kTokPerWarp);
-  float2 kk = make_float2(0.f, 0.f), vv = kk;
-  if (t0 < t1) { const float* row = kqv + ((long long)b * T + t0) * kKqv; kk = *reinterpret_cast<const float2*>(row + 2 * lane); vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane); }
-  for (int t = t0; t < t1; ++t) {
+  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp, t1 = min(T, t0 + kTokPerWarp);
+  for (int t = t0; t < t1; t += 2) {
+    const bool two = t + 1 < t1;
+    const float* ra = kqv + ((long long)b * T + t) * kKqv;
+    const float* rb = two ? ra + kKqv : ra;
+    const float2 ka = *reinterpret_cast<const float2*>(ra + 2 * lane), va = *reinterpret_cast<const float2*>(ra + 2 * kE + 2 * lane);
+    const float2 kb = *reinterpret_cast<const float2*>(rb + 2 * lane), vb = *reinterpret_cast<const float2*>(rb + 2 * kE + 2 * lane);
     __syncwarp();
-    k_s[2 * lane] = kk.x; k_s[2 * lane + 1] = kk.y; v_s[2 * lane] = vv.x; v_s[2 * lane + 1] = vv.y;
+    *reinterpret_cast<float2*>(sc[warp].a[0] + 2 * lane) = ka; *reinterpret_cast<float2*>(sc[warp].a[1] + 2 * lane) = kb;
+    *reinterpret_cast<float2*>(sc[warp].b[0] + 2 * lane) = va; *reinterpret_cast<float2*>(sc[warp].b[1] + 2 * lane) = vb;
     __syncwarp();
-    if (t + 1 < t1) {      // prefetch the next token's row: one exposed global-load latency per token was what bound this kernel
-      const float* row = kqv + ((long long)b * T + t + 1) * kKqv;
-      kk = *reinterpret_cast<const float2*>(row + 2 * lane); vv = *reinterpret_cast<const float2*>(row + 2 * kE + 2 * lane);
-    }
-    const float kp = prm_feature(w_s, k_s, lane);
-    ks += kp;
+    float kpa, kpb;
+    prm_feature2(w_s, sc[warp].a[0], sc[warp].a[1], lane, kpa, kpb);
+    if (!two) kpb = 0.f;
+    ks += kpa + kpb;
 #pragma unroll
-    for (int e = 0; e < kE; ++e) acc[e] = fmaf(v_s[e], kp, acc[e]);
+    for (int e = 0; e < kE; e += 4) {
+      const float4 A = *reinterpret_cast<const float4*>(sc[warp].b[0] + e), B = *reinterpret_cast<const float4*>(sc[warp].b[1] + e);
+      acc[e] = fmaf(A.x, kpa, fmaf(B.x, kpb, acc[e])); acc[e + 1] = fmaf(A.y, kpa, fmaf(B.y, kpb, acc[e + 1]));
+      acc[e + 2] = fmaf(A.z, kpa, fmaf(B.z, kpb, acc[e + 2])); acc[e + 3] = fmaf(A.w, kpa, fmaf(B.w, kpb, acc[e + 3]));
+    }
   }
 #pragma unroll
   for (int e = 0; e < kE; ++e) atomicAdd(&red[e * kF + lane], acc[e]);
@@ -244,34 +278,45 @@ __global__ void __launch_bounds__(256) performer_kv_kernel(const float* __restri
 __global__ void __launch_bounds__(256) performer_out_kernel(const float* __restrict__ kqv, const float* __restrict__ w, const float* __restrict__ ws,
                                                             h16* __restrict__ y16, int T, float eps) {
   __shared__ float w_s[kF][kE + 1];
-  __shared__ float kptv_s[kE][kF + 1];
-  __shared__ float ksum_s[kF];
   __shared__ WarpScratch sc[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
   load_w(w, w_s);
-  for (int i = threadIdx.x; i < kE * kF; i += blockDim.x) kptv_s[i / kF][i % kF] = ws[(long long)b * kWsPerImg + i];
-  if (threadIdx.x < kF) ksum_s[threadIdx.x] = ws[(long long)b * kWsPerImg + kE * kF + threadIdx.x];
-  __syncthreads();
-  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
-  float* q_s = sc[warp].a; float* qp_s = sc[warp].b;
-  const int t1 = min(T, t0 + kTokPerWarp);
-  float2 qq = make_float2(0.f, 0.f);
-  if (t0 < t1) qq = *reinterpret_cast<const float2*>(kqv + ((long long)b * T + t0) * kKqv + kE + 2 * lane);
-  for (int t = t0; t < t1; ++t) {
-    const long long r = (long long)b * T + t;
-    __syncwarp();
-    q_s[2 * lane] = qq.x; q_s[2 * lane + 1] = qq.y;
-    __syncwarp();
-    if (t + 1 < t1) qq = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + kE + 2 * lane);
-    const float qp = prm_feature(w_s, q_s, lane);
-    const float den = warp_sum(qp * ksum_s[lane]) + eps;
-    qp_s[lane] = qp;
-    __syncwarp();
-    float n0 = 0.f, n1 = 0.f;
+  const float* wsb = ws + (long long)b * kWsPerImg;
+  float kr0[kF], kr1[kF];                               // rows `lane`, `lane + 32` of this image's kptv
 #pragma unroll
-    for (int j = 0; j < kF; ++j) { n0 = fmaf(kptv_s[lane][j], qp_s[j], n0); n1 = fmaf(kptv_s[lane + 32][j], qp_s[j], n1); }
-    y16[r * kE + lane] = __float2half_rn(n0 / den);
-    y16[r * kE + lane + 32] = __float2half_rn(n1 / den);
+  for (int j = 0; j < kF; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(wsb + lane * kF + j), c = *reinterpret_cast<const float4*>(wsb + (lane + 32) * kF + j);
+    kr0[j] = a.x; kr0[j + 1] = a.y; kr0[j + 2] = a.z; kr0[j + 3] = a.w; kr1[j] = c.x; kr1[j + 1] = c.y; kr1[j + 2] = c.z; kr1[j + 3] = c.w;
+  }
+  const float ksum = wsb[kE * kF + lane];
+  __syncthreads();
+  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp, t1 = min(T, t0 + kTokPerWarp);
+  for (int t = t0; t < t1; t += 2) {
+    const bool two = t + 1 < t1;
+    const long long r = (long long)b * T + t;
+    const float2 qa = *reinterpret_cast<const float2*>(kqv + r * kKqv + kE + 2 * lane);
+    const float2 qb = *reinterpret_cast<const float2*>(kqv + (two ? r + 1 : r) * kKqv + kE + 2 * lane);
+    __syncwarp();
+    *reinterpret_cast<float2*>(sc[warp].a[0] + 2 * lane) = qa; *reinterpret_cast<float2*>(sc[warp].a[1] + 2 * lane) = qb;
+    __syncwarp();
+    float qpa, qpb;
+    prm_feature2(w_s, sc[warp].a[0], sc[warp].a[1], lane, qpa, qpb);
+    float dena = qpa * ksum, denb = qpb * ksum;
+    warp_sum2(dena, denb);
+    sc[warp].b[0][lane] = qpa; sc[warp].b[1][lane] = qpb;
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kF; j += 4) {
+      const float4 A = *reinterpret_cast<const float4*>(sc[warp].b[0] + j), B = *reinterpret_cast<const float4*>(sc[warp].b[1] + j);
+      a0 = fmaf(kr0[j], A.x, a0); a1 = fmaf(kr1[j], A.x, a1); b0 = fmaf(kr0[j], B.x, b0); b1 = fmaf(kr1[j], B.x, b1);
+      a0 = fmaf(kr0[j + 1], A.y, a0); a1 = fmaf(kr1[j + 1], A.y, a1); b0 = fmaf(kr0[j + 1], B.y, b0); b1 = fmaf(kr1[j + 1], B.y, b1);
+      a0 = fmaf(kr0[j + 2], A.z, a0); a1 = fmaf(kr1[j + 2], A.z, a1); b0 = fmaf(kr0[j + 2], B.z, b0); b1 = fmaf(kr1[j + 2], B.z, b1);
+      a0 = fmaf(kr0[j + 3], A.w, a0); a1 = fmaf(kr1[j + 3], A.w, a1); b0 = fmaf(kr0[j + 3], B.w, b0); b1 = fmaf(kr1[j + 3], B.w, b1);
+    }
+    dena += eps; denb += eps;
+    y16[r * kE + lane] = __float2half_rn(a0 / dena); y16[r * kE + lane + 32] = __float2half_rn(a1 / dena);
+    if (two) { y16[(r + 1) * kE + lane] = __float2half_rn(b0 / denb); y16[(r + 1) * kE + lane + 32] = __float2half_rn(b1 / denb); }
   }
 }
 
@@ -285,60 +330,64 @@ __global__ void __launch_bounds__(256) performer_bwd_a_kernel(const float* __res
                                                               int T, float eps) {
   __shared__ float w_s[kF][kE + 1];
   __shared__ float kptv_s[kE][kF + 1];
-  __shared__ float ksum_s[kF];
   __shared__ float red[kWsPerImg];
   __shared__ float cs_s[kE];
   __shared__ WarpScratch sc[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
   load_w(w, w_s);
-  for (int i = threadIdx.x; i < kE * kF; i += blockDim.x) kptv_s[i / kF][i % kF] = ws[(long long)b * kWsPerImg + i];
-  if (threadIdx.x < kF) ksum_s[threadIdx.x] = ws[(long long)b * kWsPerImg + kE * kF + threadIdx.x];
+  const float* wsb = ws + (long long)b * kWsPerImg;
+  for (int i = threadIdx.x; i < kE * kF; i += blockDim.x) kptv_s[i / kF][i % kF] = wsb[i];
   for (int i = threadIdx.x; i < kWsPerImg; i += blockDim.x) red[i] = 0.f;
   if (threadIdx.x < kE) cs_s[threadIdx.x] = 0.f;
   __syncthreads();
+  const float ksum = wsb[kE * kF + lane];
   float acc[kE];
 #pragma unroll
   for (int e = 0; e < kE; ++e) acc[e] = 0.f;
   float dks = 0.f, cs0 = 0.f, cs1 = 0.f;
-  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
-  float* q_s = sc[warp].a; float* dn_s = sc[warp].b; float* du_s = sc[warp].c;
-  const int t1 = min(T, t0 + kTokPerWarp);
-  float2 qq = make_float2(0.f, 0.f);
-  h16 hy0 = __float2half(0.f), hy1 = hy0, hd0 = hy0, hd1 = hy0;
-  if (t0 < t1) {
-    const long long r = (long long)b * T + t0;
-    qq = *reinterpret_cast<const float2*>(kqv + r * kKqv + kE + 2 * lane);
-    hy0 = y16[r * kE + lane]; hy1 = y16[r * kE + lane + 32]; hd0 = dy16[r * kE + lane]; hd1 = dy16[r * kE + lane + 32];
-  }
-  for (int t = t0; t < t1; ++t) {
-    const long long r = (long long)b * T + t;
+  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp, t1 = min(T, t0 + kTokPerWarp);
+  for (int t = t0; t < t1; t += 2) {
+    const bool two = t + 1 < t1;
+    const long long ra = (long long)b * T + t, rb = two ? ra + 1 : ra;
+    const float2 qa = *reinterpret_cast<const float2*>(kqv + ra * kKqv + kE + 2 * lane), qb = *reinterpret_cast<const float2*>(kqv + rb * kKqv + kE + 2 * lane);
+    const float ya0 = __half2float(y16[ra * kE + lane]), ya1 = __half2float(y16[ra * kE + lane + 32]);
+    const float yb0 = __half2float(y16[rb * kE + lane]), yb1 = __half2float(y16[rb * kE + lane + 32]);
+    const float da0 = __half2float(dy16[ra * kE + lane]), da1 = __half2float(dy16[ra * kE + lane + 32]);
+    const float db0 = two ? __half2float(dy16[rb * kE + lane]) : 0.f, db1 = two ? __half2float(dy16[rb * kE + lane + 32]) : 0.f;
     __syncwarp();
-    q_s[2 * lane] = qq.x; q_s[2 * lane + 1] = qq.y;
+    *reinterpret_cast<float2*>(sc[warp].a[0] + 2 * lane) = qa; *reinterpret_cast<float2*>(sc[warp].a[1] + 2 * lane) = qb;
     __syncwarp();
-    const float y0 = __half2float(hy0), y1 = __half2float(hy1), dy0 = __half2float(hd0), dy1 = __half2float(hd1);
-    if (t + 1 < t1) {
-      qq = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + kE + 2 * lane);
-      hy0 = y16[(r + 1) * kE + lane]; hy1 = y16[(r + 1) * kE + lane + 32]; hd0 = dy16[(r + 1) * kE + lane]; hd1 = dy16[(r + 1) * kE + lane + 32];
+    float qpa, qpb;
+    prm_feature2(w_s, sc[warp].a[0], sc[warp].a[1], lane, qpa, qpb);
+    float dena = qpa * ksum, denb = qpb * ksum;
+    warp_sum2(dena, denb);
+    dena += eps; denb += eps;
+    float dda = da0 * ya0 + da1 * ya1, ddb = db0 * yb0 + db1 * yb1;
+    warp_sum2(dda, ddb);
+    dda = -dda / dena; ddb = -ddb / denb;                        // dden of the two tokens (zero for a missing second token: its dy is zero)
+    sc[warp].b[0][lane] = da0 / dena; sc[warp].b[0][lane + 32] = da1 / dena; sc[warp].b[1][lane] = db0 / denb; sc[warp].b[1][lane + 32] = db1 / denb;
+    __syncwarp();
+    float dqa = dda * ksum, dqb = ddb * ksum, dqa1 = 0.f, dqb1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < kE; e += 4) {
+      const float4 A = *reinterpret_cast<const float4*>(sc[warp].b[0] + e), B = *reinterpret_cast<const float4*>(sc[warp].b[1] + e);
+      const float k0 = kptv_s[e][lane], k1 = kptv_s[e + 1][lane], k2 = kptv_s[e + 2][lane], k3 = kptv_s[e + 3][lane];
+      dqa = fmaf(A.x, k0, dqa); dqa1 = fmaf(A.y, k1, dqa1); dqa = fmaf(A.z, k2, dqa); dqa1 = fmaf(A.w, k3, dqa1);
+      dqb = fmaf(B.x, k0, dqb); dqb1 = fmaf(B.y, k1, dqb1); dqb = fmaf(B.z, k2, dqb); dqb1 = fmaf(B.w, k3, dqb1);
+      acc[e] = fmaf(A.x, qpa, fmaf(B.x, qpb, acc[e])); acc[e + 1] = fmaf(A.y, qpa, fmaf(B.y, qpb, acc[e + 1]));
+      acc[e + 2] = fmaf(A.z, qpa, fmaf(B.z, qpb, acc[e + 2])); acc[e + 3] = fmaf(A.w, qpa, fmaf(B.w, qpb, acc[e + 3]));
     }
-    const float qp = prm_feature(w_s, q_s, lane);
-    const float den = warp_sum(qp * ksum_s[lane]) + eps;
-    const float dden = -warp_sum(dy0 * y0 + dy1 * y1) / den;
-    dn_s[lane] = dy0 / den; dn_s[lane + 32] = dy1 / den;
+    dqa += dqa1; dqb += dqb1;
+    dks = fmaf(dda, qpa, fmaf(ddb, qpb, dks));
+    float dua = dqa * qpa, dub = dqb * qpb;
+    sc[warp].c[0][lane] = dua; sc[warp].c[1][lane] = dub;
+    warp_sum2(dua, dub);                                         // sum_j du
     __syncwarp();
-    float dqp = dden * ksum_s[lane];
-#pragma unroll
-    for (int e = 0; e < kE; ++e) { dqp = fmaf(dn_s[e], kptv_s[e][lane], dqp); acc[e] = fmaf(dn_s[e], qp, acc[e]); }
-    dks = fmaf(dden, qp, dks);
-    const float du = dqp * qp;
-    const float su = warp_sum(du);
-    du_s[lane] = du;
-    __syncwarp();
-    float d0 = -su * q_s[lane], d1 = -su * q_s[lane + 32];
-#pragma unroll
-    for (int j = 0; j < kF; ++j) { d0 = fmaf(du_s[j], w_s[j][lane], d0); d1 = fmaf(du_s[j], w_s[j][lane + 32], d1); }
-    dkqv16[r * kKqv + kE + lane] = __float2half_rn(d0);
-    dkqv16[r * kKqv + kE + lane + 32] = __float2half_rn(d1);
-    cs0 += d0; cs1 += d1;
+    float a0 = -dua * sc[warp].a[0][lane], a1 = -dua * sc[warp].a[0][lane + 32], b0 = -dub * sc[warp].a[1][lane], b1 = -dub * sc[warp].a[1][lane + 32];
+    wT_times2(w_s, sc[warp].c[0], sc[warp].c[1], lane, a0, a1, b0, b1);
+    dkqv16[ra * kKqv + kE + lane] = __float2half_rn(a0); dkqv16[ra * kKqv + kE + lane + 32] = __float2half_rn(a1);
+    cs0 += a0; cs1 += a1;
+    if (two) { dkqv16[rb * kKqv + kE + lane] = __float2half_rn(b0); dkqv16[rb * kKqv + kE + lane + 32] = __float2half_rn(b1); cs0 += b0; cs1 += b1; }
   }
 #pragma unroll
   for (int e = 0; e < kE; ++e) atomicAdd(&red[e * kF + lane], acc[e]);
@@ -357,57 +406,69 @@ __global__ void __launch_bounds__(256) performer_bwd_b_kernel(const float* __res
                                                               const float* __restrict__ scales, int T) {
   __shared__ float w_s[kF][kE + 1];
   __shared__ float dkptv_s[kE][kF + 1];
-  __shared__ float dksum_s[kF];
   __shared__ float cs_s[2 * kE];
   __shared__ WarpScratch sc[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, b = blockIdx.y;
   load_w(w, w_s);
-  for (int i = threadIdx.x; i < kE * kF; i += blockDim.x) dkptv_s[i / kF][i % kF] = dws[(long long)b * kWsPerImg + i];
-  if (threadIdx.x < kF) dksum_s[threadIdx.x] = dws[(long long)b * kWsPerImg + kE * kF + threadIdx.x];
+  const float* dwsb = dws + (long long)b * kWsPerImg;
+  for (int i = threadIdx.x; i < kE * kF; i += blockDim.x) dkptv_s[i / kF][i % kF] = dwsb[i];
   if (threadIdx.x < 2 * kE) cs_s[threadIdx.x] = 0.f;
+  float kr0[kF], kr1[kF];                               // rows `lane`, `lane + 32` of this image's d kptv
+#pragma unroll
+  for (int j = 0; j < kF; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(dwsb + lane * kF + j), c = *reinterpret_cast<const float4*>(dwsb + (lane + 32) * kF + j);
+    kr0[j] = a.x; kr0[j + 1] = a.y; kr0[j + 2] = a.z; kr0[j + 3] = a.w; kr1[j] = c.x; kr1[j + 1] = c.y; kr1[j + 2] = c.z; kr1[j + 3] = c.w;
+  }
+  const float dksum = dwsb[kE * kF + lane];
   __syncthreads();
   const float S = scales[0];
   float ck0 = 0.f, ck1 = 0.f, cv0 = 0.f, cv1 = 0.f;
-  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp;
-  float* k_s = sc[warp].a; float* v_s = sc[warp].b; float* x_s = sc[warp].c;      // x_s: kp, then du
-  const int t1 = min(T, t0 + kTokPerWarp);
-  float2 kk = make_float2(0.f, 0.f), vv = kk;
-  float r0 = 0.f, r1 = 0.f;
-  if (t0 < t1) {
-    const long long r = (long long)b * T + t0;
-    kk = *reinterpret_cast<const float2*>(kqv + r * kKqv + 2 * lane); vv = *reinterpret_cast<const float2*>(kqv + r * kKqv + 2 * kE + 2 * lane);
-    r0 = dres[r * kE + lane]; r1 = dres[r * kE + lane + 32];
-  }
-  for (int t = t0; t < t1; ++t) {
-    const long long r = (long long)b * T + t;
+  const int t0 = (blockIdx.x * 8 + warp) * kTokPerWarp, t1 = min(T, t0 + kTokPerWarp);
+  for (int t = t0; t < t1; t += 2) {
+    const bool two = t + 1 < t1;
+    const long long ra = (long long)b * T + t, rb = two ? ra + 1 : ra;
+    const float2 ka = *reinterpret_cast<const float2*>(kqv + ra * kKqv + 2 * lane), va = *reinterpret_cast<const float2*>(kqv + ra * kKqv + 2 * kE + 2 * lane);
+    const float2 kb = *reinterpret_cast<const float2*>(kqv + rb * kKqv + 2 * lane), vb = *reinterpret_cast<const float2*>(kqv + rb * kKqv + 2 * kE + 2 * lane);
+    float dva0 = S * dres[ra * kE + lane], dva1 = S * dres[ra * kE + lane + 32], dvb0 = S * dres[rb * kE + lane], dvb1 = S * dres[rb * kE + lane + 32];
     __syncwarp();
-    k_s[2 * lane] = kk.x; k_s[2 * lane + 1] = kk.y; v_s[2 * lane] = vv.x; v_s[2 * lane + 1] = vv.y;
+    *reinterpret_cast<float2*>(sc[warp].a[0] + 2 * lane) = ka; *reinterpret_cast<float2*>(sc[warp].a[1] + 2 * lane) = kb;
+    *reinterpret_cast<float2*>(sc[warp].b[0] + 2 * lane) = va; *reinterpret_cast<float2*>(sc[warp].b[1] + 2 * lane) = vb;
     __syncwarp();
-    float dv0 = S * r0, dv1 = S * r1;
-    if (t + 1 < t1) {
-      kk = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + 2 * lane); vv = *reinterpret_cast<const float2*>(kqv + (r + 1) * kKqv + 2 * kE + 2 * lane);
-      r0 = dres[(r + 1) * kE + lane]; r1 = dres[(r + 1) * kE + lane + 32];
+    float kpa, kpb;
+    prm_feature2(w_s, sc[warp].a[0], sc[warp].a[1], lane, kpa, kpb);
+    sc[warp].c[0][lane] = kpa; sc[warp].c[1][lane] = kpb;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kF; j += 4) {
+      const float4 A = *reinterpret_cast<const float4*>(sc[warp].c[0] + j), B = *reinterpret_cast<const float4*>(sc[warp].c[1] + j);
+      dva0 = fmaf(kr0[j], A.x, dva0); dva1 = fmaf(kr1[j], A.x, dva1); dvb0 = fmaf(kr0[j], B.x, dvb0); dvb1 = fmaf(kr1[j], B.x, dvb1);
+      dva0 = fmaf(kr0[j + 1], A.y, dva0); dva1 = fmaf(kr1[j + 1], A.y, dva1); dvb0 = fmaf(kr0[j + 1], B.y, dvb0); dvb1 = fmaf(kr1[j + 1], B.y, dvb1);
+      dva0 = fmaf(kr0[j + 2], A.z, dva0); dva1 = fmaf(kr1[j + 2], A.z, dva1); dvb0 = fmaf(kr0[j + 2], B.z, dvb0); dvb1 = fmaf(kr1[j + 2], B.z, dvb1);
+      dva0 = fmaf(kr0[j + 3], A.w, dva0); dva1 = fmaf(kr1[j + 3], A.w, dva1); dvb0 = fmaf(kr0[j + 3], B.w, dvb0); dvb1 = fmaf(kr1[j + 3], B.w, dvb1);
     }
-    const float kp = prm_feature(w_s, k_s, lane);
-    x_s[lane] = kp;
-    __syncwarp();
+    float dka = dksum, dkb = dksum, dka1 = 0.f, dkb1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < kF; ++j) { dv0 = fmaf(dkptv_s[lane][j], x_s[j], dv0); dv1 = fmaf(dkptv_s[lane + 32][j], x_s[j], dv1); }
-    float dkp = dksum_s[lane];
-#pragma unroll
-    for (int e = 0; e < kE; ++e) dkp = fmaf(dkptv_s[e][lane], v_s[e], dkp);
-    const float du = dkp * kp;
-    const float su = warp_sum(du);
+    for (int e = 0; e < kE; e += 4) {
+      const float4 A = *reinterpret_cast<const float4*>(sc[warp].b[0] + e), B = *reinterpret_cast<const float4*>(sc[warp].b[1] + e);
+      const float k0 = dkptv_s[e][lane], k1 = dkptv_s[e + 1][lane], k2 = dkptv_s[e + 2][lane], k3 = dkptv_s[e + 3][lane];
+      dka = fmaf(k0, A.x, dka); dka1 = fmaf(k1, A.y, dka1); dka = fmaf(k2, A.z, dka); dka1 = fmaf(k3, A.w, dka1);
+      dkb = fmaf(k0, B.x, dkb); dkb1 = fmaf(k1, B.y, dkb1); dkb = fmaf(k2, B.z, dkb); dkb1 = fmaf(k3, B.w, dkb1);
+    }
+    float dua = (dka + dka1) * kpa, dub = (dkb + dkb1) * kpb;
     __syncwarp();
-    x_s[lane] = du;
+    sc[warp].c[0][lane] = dua; sc[warp].c[1][lane] = dub;
+    warp_sum2(dua, dub);
     __syncwarp();
-    float d0 = -su * k_s[lane], d1 = -su * k_s[lane + 32];
-#pragma unroll
-    for (int j = 0; j < kF; ++j) { d0 = fmaf(x_s[j], w_s[j][lane], d0); d1 = fmaf(x_s[j], w_s[j][lane + 32], d1); }
-    h16* o = dkqv16 + r * kKqv;
-    o[lane] = __float2half_rn(d0); o[lane + 32] = __float2half_rn(d1);
-    o[2 * kE + lane] = __float2half_rn(dv0); o[2 * kE + lane + 32] = __float2half_rn(dv1);
-    ck0 += d0; ck1 += d1; cv0 += dv0; cv1 += dv1;
+    float a0 = -dua * sc[warp].a[0][lane], a1 = -dua * sc[warp].a[0][lane + 32], b0 = -dub * sc[warp].a[1][lane], b1 = -dub * sc[warp].a[1][lane + 32];
+    wT_times2(w_s, sc[warp].c[0], sc[warp].c[1], lane, a0, a1, b0, b1);
+    h16* oa = dkqv16 + ra * kKqv;
+    oa[lane] = __float2half_rn(a0); oa[lane + 32] = __float2half_rn(a1); oa[2 * kE + lane] = __float2half_rn(dva0); oa[2 * kE + lane + 32] = __float2half_rn(dva1);
+    ck0 += a0; ck1 += a1; cv0 += dva0; cv1 += dva1;
+    if (two) {
+      h16* ob = dkqv16 + rb * kKqv;
+      ob[lane] = __float2half_rn(b0); ob[lane + 32] = __float2half_rn(b1); ob[2 * kE + lane] = __float2half_rn(dvb0); ob[2 * kE + lane + 32] = __float2half_rn(dvb1);
+      ck0 += b0; ck1 += b1; cv0 += dvb0; cv1 += dvb1;
+    }
   }
   atomicAdd(&cs_s[lane], ck0); atomicAdd(&cs_s[lane + 32], ck1); atomicAdd(&cs_s[kE + lane], cv0); atomicAdd(&cs_s[kE + lane + 32], cv1);
   __syncthreads();
@@ -615,9 +676,10 @@ int unfold_ln(const float* src, const Geom& g, const float* gamma, const float* 
 int unfold_ln_bwd(const h16* dy16, const float* src, const Geom& g, const float* gamma, const float* mean, const float* rstd, const float* scales,
                   float* dgamma, float* dbeta, float* dsrc, int M, cudaStream_t st) {
   const size_t smem = (8 * (size_t)g.Kp + 3 * (size_t)g.dim) * sizeof(float);
-  const int grid = blocks_for(M, 8 * 16, 148 * 4);
-  if (gamma) unfold_ln_bwd_kernel<true><<<grid, 256, smem, st>>>(dy16, src, g, gamma, mean, rstd, scales, dgamma, dbeta, dsrc, M);
-  else unfold_ln_bwd_kernel<false><<<grid, 256, smem, st>>>(dy16, src, g, nullptr, nullptr, nullptr, scales, nullptr, nullptr, dsrc, M);
+  const int grid = blocks_for(M, 8 * 16, 148 * (g.dim <= 160 ? 8 : 4));
+  if (gamma && g.dim <= 160) unfold_ln_bwd_kernel<true, 5><<<grid, 256, smem, st>>>(dy16, src, g, gamma, mean, rstd, scales, dgamma, dbeta, dsrc, M);
+  else if (gamma) unfold_ln_bwd_kernel<true, 18><<<grid, 256, smem, st>>>(dy16, src, g, gamma, mean, rstd, scales, dgamma, dbeta, dsrc, M);
+  else unfold_ln_bwd_kernel<false, 1><<<grid, 256, smem, st>>>(dy16, src, g, nullptr, nullptr, nullptr, scales, nullptr, nullptr, dsrc, M);
   return check_launch("t2t unfold_ln_bwd");
 }
 
