@@ -413,7 +413,7 @@ def run_gpu(a):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "gemm2_traffic.json")) as f:     # dram bytes per launch of the same kernel, from an ncu capture of this bench
-            traffic = json.load(f)
+            traffic = json.load(f).get(f"{a.config}:{'f16' if f16_mode else 'tf32'}")      # per configuration and precision mode; None if never captured
     except Exception:
         pass
     imgs = B * world * a.steps
