@@ -668,6 +668,12 @@ def main():
     ap.add_argument("--no-live-peaks", dest="no_live_peaks", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints its version banner there,
+    # the reference's own prints, warnings of C extensions) are sent to stderr for the whole run; the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if a.impl == "reference":
         return run_reference(a)
     run_gpu(a)
