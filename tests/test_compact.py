@@ -263,3 +263,31 @@ def test_random_layouts_compact_equals_masked_dense():
         m = cp.macs(lay)
         assert 0.0 < m["budget_ratio"] <= m["ratio"] + 1e-12 <= 1.0 + 1e-12
     run()
+
+
+def test_engine_layout_rules_on_cpu():
+    """`EngineLayout` (the uvc_vit_layout the engine trains on): every executed block keeps >= 1 head and a multiple of 64 (>= 64) neurons, topped up
+    with pruned entries; each index row is a permutation with the live entries first, ascending; hard-skipped blocks are left dense (never read)."""
+    sd, dims = pruned_checkpoint()
+    H = dims["num_heads"]
+    lay = cp.compile_layout(sd, H)
+    for keep in (False, True):
+        el = cp.EngineLayout(lay, "cpu", keep_pruned_heads=keep)
+        Fh = lay["Fh"]
+        for l, b in enumerate(lay["blocks"]):
+            nh, nn_ = el.struct.n_heads[l], el.struct.n_neurons[l]
+            assert 1 <= nh <= H and 64 <= nn_ <= Fh and nn_ % 64 == 0
+            hrow, nrow = el.head_idx[l].tolist(), el.neuron_idx[l].tolist()
+            assert sorted(hrow) == list(range(H)) and sorted(nrow) == list(range(Fh))           # permutations
+            assert hrow[:nh] == sorted(hrow[:nh]) and nrow[:nn_] == sorted(nrow[:nn_])            # live part ascending
+            if b is None:
+                assert nh == H and nn_ == Fh
+                continue
+            assert set(b["heads"]) <= set(hrow[:nh]) and set(b["neurons"].tolist()) <= set(nrow[:nn_])      # nothing live is dropped
+            if keep:
+                assert nh == H
+            else:
+                assert nh == max(1, len(b["heads"]))
+            assert nn_ - b["neurons"].numel() < 64 or b["neurons"].numel() == 0
+        assert 0 < el.executed_macs_ratio() <= 1.0
+    assert cp.EngineLayout(lay, "cpu", keep_pruned_heads=True).executed_macs_ratio() >= cp.EngineLayout(lay, "cpu").executed_macs_ratio()

@@ -156,3 +156,52 @@ def test_train_step_matches_oracle_at_other_widths(model_type, depth, B):
     bad = [(k, rel(p.grad, sdr[k].grad)) for k, p in m.named_parameters() if p.grad is not None and not rel(p.grad, sdr[k].grad) < GRAD_TOL]
     assert not bad, bad
     assert rel(blend.grad, br.grad) < GRAD_TOL
+
+
+def test_cifar10_shaped_head_trains(precision):
+    """`--dataset cifar10` gives num_classes = 10: the logits / dlogits row stride is not a multiple of 4 floats, which the GEMM operands need.
+    The engine pads the head's gradient operand internally; logits, loss gradient flow and the head's gradients must match the oracle, and an odd
+    batch must work."""
+    nc, B, depth = 10, 3, 1
+    sd, dims = fx.make_state_dict("deit_tiny_patch16_224", depth, seed=6, num_classes=nc)
+    from functools import partial
+    from uvc_b200.models.model_distilled import DistilledVisionTransformer
+    d = dict(dims); d["depth"] = depth
+    m = DistilledVisionTransformer(enable_dist=0, patch_size=16, mlp_ratio=4, qkv_bias=True, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), drop_rate=0,
+                                   num_classes=nc, **d)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda().train()
+    x, _ = fx.make_batch(B, seed=12)
+    r = torch.randn(B, nc, generator=torch.Generator().manual_seed(1)) * 0.1
+    (logits, _), _ = m(x.cuda())
+    assert logits.shape == (B, nc)
+    (logits * r.cuda()).sum().backward()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lo = vo.forward(sdr, x, depth, dims["num_heads"])
+    (lo * r).sum().backward()
+    assert rel(logits.detach(), lo.detach()) < LOGIT_TOL
+    for k in ("head.weight", "head.bias", "norm.weight", "blocks.0.mlp.fc2.weight", "patch_embed.proj.weight", "cls_token"):
+        assert rel(dict(m.named_parameters())[k].grad, sdr[k].grad) < GRAD_TOL, k
+
+
+def test_gate_gradients_same_through_both_layernorm_backward_kernels(monkeypatch):
+    """The block-gate gradients <g, t>, <g, x> ride in the LayerNorm backward kernels; at M >= 1024 rows the fp16 engine uses the streamed kernel.
+    A gated step at B = 8 (1576 rows) must give the same d(blend) and parameter gradients through either kernel."""
+    from uvc_b200.models.model_distilled import _VitFunction, _engine_param_list
+    sd, dims = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=8)
+    x, _ = fx.make_batch(8, seed=14)
+    r = (torch.randn(8, 1000, generator=torch.Generator().manual_seed(2)) * 0.1).cuda()
+    res = {}
+    for mode in ("reg", "stream"):
+        if mode == "reg":
+            monkeypatch.setenv("UVC_LN_BWD_REG", "1")
+        else:
+            monkeypatch.delenv("UVC_LN_BWD_REG", raising=False)
+        m = build("deit_tiny_patch16_224", 2, sd).train()
+        blend = torch.tensor([[0.3, 0.7], [0.55, 0.45]]).cuda().requires_grad_(True)
+        params = [p for _, p in _engine_param_list(m)]
+        logits = _VitFunction.apply(m, x.cuda(), blend, None, None, None, *params)
+        (logits * r).sum().backward()
+        res[mode] = (blend.grad.clone(), m.blocks[0].norm1.weight.grad.clone(), m.blocks[1].mlp.fc2.bias.grad.clone(), m.blocks[0].attn.qkv.weight.grad.clone())
+    for a, b in zip(res["stream"], res["reg"]):
+        assert rel(a, b) < 1e-4

@@ -147,3 +147,34 @@ def test_attention_f16_propagates_nan(ops):
     ctx, lse = ops.attention_fwd_f16(qkv, B, H, N)
     assert torch.isnan(ctx[5, 64:128]).all() and torch.isnan(lse.view(B, H, N)[0, 1, 5])
     assert not torch.isnan(ctx[6]).any() and not torch.isnan(ctx[5, :64]).any()
+
+
+@pytest.mark.parametrize("M,C,use_r1,use_r2,cs", [(8195, 384, True, True, False), (4099, 384, False, True, True), (2051, 768, True, False, True),
+                                                  (1027, 192, True, True, True), (25216, 384, False, True, True)])
+def test_layernorm_bwd_streamed_kernel_equals_register_kernel(ops, monkeypatch, M, C, use_r1, use_r2, cs):
+    """The engine's LayerNorm backward at bench sizes runs `layernorm_bwd_stream_kernel` (bulk-asynchronous staging of 8-row stages through shared
+    memory); small / strided problems run the register-resident kernel.  Same arithmetic: dx, the fp16 operand copy, dgamma / dbeta and the fused
+    column sums must agree to summation order, including a ragged last stage (M % 8 != 0) and rows wider / narrower than the bench's."""
+    x, g, b = rn(M, C) * 2 + 0.3, rn(C), rn(C)
+    _, mean, rstd = ops.layernorm_fwd_f16(x, g, b, 1e-6)
+    S = 256.0
+    dy16 = (rn(M, C, seed=1) * 1e-3 * S).half()
+    r1 = rn(M, C, seed=2) * 1e-3 if use_r1 else None
+    r2 = rn(M, C, seed=3) * 1e-3 if use_r2 else None
+    s2 = torch.tensor([0.7], device="cuda") if use_r2 else None
+    out = {}
+    for mode in ("reg", "stream"):
+        if mode == "reg":
+            monkeypatch.setenv("UVC_LN_BWD_REG", "1")
+        else:
+            monkeypatch.delenv("UVC_LN_BWD_REG", raising=False)
+        dg, db, c1, c2 = (torch.zeros(C, device="cuda") for _ in range(4))
+        dx, dx16 = ops.layernorm_bwd_f16(dy16, 1.0 / S, x, mean, rstd, g, r1=r1, r2=r2, s2=s2, dgamma=dg, dbeta=db, cs_r1=c1 if cs else None,
+                                         cs_out=c2 if cs else None, dx16_scale=S)
+        out[mode] = (dx, dx16.float(), dg, db, c1, c2)
+    names = ("dx", "dx16", "dgamma", "dbeta", "cs_r1", "cs_out")
+    for n, a, bb in zip(names, out["stream"], out["reg"]):
+        if bb.abs().max() == 0:
+            assert a.abs().max() == 0, n
+        else:
+            assert rel(a, bb) < (1e-6 if n == "dx" else 2e-4), (n, rel(a, bb))

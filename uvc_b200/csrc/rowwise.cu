@@ -215,6 +215,160 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? UVC_LN_BWD_MINB : 2)) layernor
   }
 }
 
+// ------------------------------------------------------------------------------------------ LayerNorm bwd, streamed through shared memory
+// The register-resident kernel above keeps one row (4-5 tensors x 1.5 KB) in registers per warp; at the 80 registers that give it 24 warps per
+// SM the compiler cannot hoist all of a row's loads, so a row costs ~3 dependent round trips and the kernel runs at 2.9-4.1 TB/s (0.45-0.63 of
+// the HBM peak, ncu: nothing saturated, 36 % occupancy).  Here the loads cost no registers: one thread issues 1-D bulk-asynchronous copies
+// (cp.async.bulk, completion on an mbarrier) of EIGHT consecutive rows of every input tensor (6-12 KB each) into a two-stage shared-memory
+// ring, so a whole stage (30-54 KB per block, two blocks per SM) is in flight while the eight warps work on the previous one from shared memory.
+// Same arithmetic, same outputs, same fused column sums / gate-gradient dots as layernorm_bwd_kernel<NV, CS, true>; requires contiguous rows.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NV, bool CS>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_stream_kernel(const __half* __restrict__ dy16, const float* __restrict__ x, const float* __restrict__ mean,
+                                                                      const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                      const float* __restrict__ r1, const float* __restrict__ r2, const float* __restrict__ s2_dev,
+                                                                      float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                      float* __restrict__ cs_r1, float* __restrict__ cs_out, int M, int C, int rows_per_block,
+                                                                      float dy_scale, __half* __restrict__ dx16, float out_scale,
+                                                                      const float* __restrict__ scales_dev, const float* __restrict__ dot_t,
+                                                                      float* __restrict__ dots, int dot_x) {
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ float red[4][8][32 * 4 + 4];
+  __shared__ __align__(8) uint64_t bars[2];
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = C >> 2;
+  // stage layout: dy16 [8, C] fp16 | x [8, C] | r1 | r2 | t (the optional ones only when present)
+  const uint32_t b16 = 8u * C * 2u, b32 = 8u * C * 4u;
+  const uint32_t off_x = b16, off_r1 = off_x + b32, off_r2 = off_r1 + (r1 ? b32 : 0u), off_t = off_r2 + (r2 ? b32 : 0u);
+  const uint32_t stage_bytes = off_t + (dot_t ? b32 : 0u);
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_barrier_init(); }
+  __syncthreads();
+  pdl_wait();
+  if (scales_dev) { out_scale *= __ldg(scales_dev); dy_scale *= __ldg(scales_dev + 1); }
+  const float s2 = (r2 && s2_dev) ? __ldg(s2_dev) : 1.0f;
+  const int row0 = blockIdx.x * rows_per_block;
+  const int row1 = min(M, row0 + rows_per_block);
+  const int nst = (row1 - row0 + 7) / 8;
+  auto issue = [&](int st) {          // one thread: expect the stage's bytes, then one bulk copy per tensor
+    const int ra = row0 + st * 8, n = min(8, row1 - ra);
+    const uint32_t base = ring_u32 + (uint32_t)(st & 1) * stage_bytes, bar = bar0 + 8u * (st & 1);
+    const uint32_t n16 = (uint32_t)n * C * 2u, n32 = (uint32_t)n * C * 4u;
+    mbar_expect_tx(bar, n16 + n32 + (r1 ? n32 : 0u) + (r2 ? n32 : 0u) + (dot_t ? n32 : 0u));
+    bulk_g2s(base, dy16 + (long long)ra * C, n16, bar);
+    bulk_g2s(base + off_x, x + (long long)ra * C, n32, bar);
+    if (r1) bulk_g2s(base + off_r1, r1 + (long long)ra * C, n32, bar);
+    if (r2) bulk_g2s(base + off_r2, r2 + (long long)ra * C, n32, bar);
+    if (dot_t) bulk_g2s(base + off_t, dot_t + (long long)ra * C, n32, bar);
+  };
+  if (threadIdx.x == 0 && nst > 0) issue(0);
+  float4 ag[NV], ab[NV], a1[CS ? NV : 1], ao[CS ? NV : 1];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { ag[i] = make_float4(0, 0, 0, 0); ab[i] = make_float4(0, 0, 0, 0); }
+  if (CS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { a1[i] = make_float4(0, 0, 0, 0); ao[i] = make_float4(0, 0, 0, 0); }
+  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float acc_dx = 0.f, acc_dt = 0.f;
+  for (int st = 0; st < nst; ++st) {
+    __syncthreads();                                   // every warp is done with stage st - 1: its buffer may be refilled
+    if (threadIdx.x == 0 && st + 1 < nst) issue(st + 1);
+    mbar_wait(bar0 + 8u * (st & 1), (uint32_t)(st >> 1) & 1u);
+    const int row = row0 + st * 8 + warp;
+    if (row >= row1) continue;
+    const unsigned char* base = ring + (size_t)(st & 1) * stage_bytes;
+    const uint2* dyr = reinterpret_cast<const uint2*>(base) + (size_t)warp * nv;
+    const float4* xr = reinterpret_cast<const float4*>(base + off_x) + (size_t)warp * nv;
+    const float4* r1r = reinterpret_cast<const float4*>(base + off_r1) + (size_t)warp * nv;
+    const float4* r2r = reinterpret_cast<const float4*>(base + off_r2) + (size_t)warp * nv;
+    const float4* dtr = reinterpret_cast<const float4*>(base + off_t) + (size_t)warp * nv;
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[NV], gg[NV], res[NV];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      res[i] = make_float4(0, 0, 0, 0);
+      if (c < nv) {
+        const uint2 u = dyr[c];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        const float4 d = make_float4(lo.x * dy_scale, lo.y * dy_scale, hi.x * dy_scale, hi.y * dy_scale);
+        const float4 xv = xr[c], gm = __ldg(g4 + c);
+        if (r1) res[i] = r1r[c];
+        if (r2) {
+          const float4 a = r2r[c];
+          res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w;
+          if (dot_x) acc_dx += (a.x * xv.x + a.y * xv.y) + (a.z * xv.z + a.w * xv.w);
+          if (dot_t) { const float4 tv = dtr[c]; acc_dt += (a.x * tv.x + a.y * tv.y) + (a.z * tv.z + a.w * tv.w); }
+        }
+        if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
+        xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
+        gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
+        sg += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
+        sgx += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
+        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    const float mg = warp_sum(sg) / (float)C, mgx = warp_sum(sgx) / (float)C;
+    float4* dxr = reinterpret_cast<float4*>(dx + (long long)row * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nv) {
+        float4 o;
+        o.x = res[i].x + rs * (gg[i].x - mg - xh[i].x * mgx); o.y = res[i].y + rs * (gg[i].y - mg - xh[i].y * mgx);
+        o.z = res[i].z + rs * (gg[i].z - mg - xh[i].z * mgx); o.w = res[i].w + rs * (gg[i].w - mg - xh[i].w * mgx);
+        if (CS) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
+        dxr[c] = o;
+        if (dx16) reinterpret_cast<uint2*>(dx16 + (long long)row * C)[c] = pack_half4(o.x * out_scale, o.y * out_scale, o.z * out_scale, o.w * out_scale);
+      }
+    }
+  }
+  if (dots) {
+    if (dot_x) { acc_dx = warp_sum(acc_dx); if (lane == 0) atomicAdd(dots, acc_dx); }
+    if (dot_t) { acc_dt = warp_sum(acc_dt); if (lane == 0) atomicAdd(dots + 1, acc_dt); }
+  }
+  if (!dgamma && !(CS && (cs_r1 || cs_out))) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (i * 32 >= nv) break;
+    __syncthreads();
+    float* rg = &red[0][warp][lane * 4];
+    float* rb = &red[1][warp][lane * 4];
+    rg[0] = ag[i].x; rg[1] = ag[i].y; rg[2] = ag[i].z; rg[3] = ag[i].w;
+    rb[0] = ab[i].x; rb[1] = ab[i].y; rb[2] = ab[i].z; rb[3] = ab[i].w;
+    if (CS) {
+      float* q1 = &red[2][warp][lane * 4];
+      float* qo = &red[3][warp][lane * 4];
+      q1[0] = a1[i].x; q1[1] = a1[i].y; q1[2] = a1[i].z; q1[3] = a1[i].w;
+      qo[0] = ao[i].x; qo[1] = ao[i].y; qo[2] = ao[i].z; qo[3] = ao[i].w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int col = i * 128 + threadIdx.x;
+      if (col < C) {
+        float sgm = 0.f, sbt = 0.f, s1 = 0.f, so = 0.f;
+        for (int w = 0; w < 8; ++w) {
+          sgm += red[0][w][threadIdx.x]; sbt += red[1][w][threadIdx.x];
+          if (CS) { s1 += red[2][w][threadIdx.x]; so += red[3][w][threadIdx.x]; }
+        }
+        if (dgamma) { atomicAdd(dgamma + col, sgm); atomicAdd(dbeta + col, sbt); }
+        if (CS) {
+          if (cs_r1) atomicAdd(cs_r1 + col, s1);
+          if (cs_out) atomicAdd(cs_out + col, so);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ softmax over attention rows
 // in place on S[rows][ld], n valid columns (<= 256); one warp per row
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(float* __restrict__ S, long long ld, long long rows, int n, int rnd) {
@@ -559,6 +713,33 @@ int layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx
   if (rpb < 8) rpb = 8;
   blocks = (M + rpb - 1) / rpb;
   __half* h16 = static_cast<__half*>(dx16);
+  // fp16 dy with contiguous rows (the engine's block loop): the streamed kernel (bulk-asynchronous staging, see layernorm_bwd_stream_kernel)
+  const bool stream_ok = !getenv("UVC_LN_BWD_REG");          // bring-up / tests: force the register-resident kernel
+  if (dy16 && stream_ok && lddy == C && ldx == C && lddx == C && (C & 7) == 0 && M >= 1024 && C >= 128 &&
+      ((reinterpret_cast<uintptr_t>(dy16) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r1) | reinterpret_cast<uintptr_t>(r2) |
+        reinterpret_cast<uintptr_t>(dot_t)) & 15) == 0) {
+    const int ntens32 = 1 + (r1 ? 1 : 0) + (r2 ? 1 : 0) + (dot_t ? 1 : 0);
+    const size_t smem = 2 * (size_t)(8 * C * 2 + ntens32 * 8 * C * 4);
+    if (smem + 18 * 1024 <= 220 * 1024) {                       // two blocks per SM up to C = 384, one block for wider rows
+      int nb = 148 * 2;
+      int rpb2 = ((M + nb - 1) / nb + 7) / 8 * 8;
+      nb = (M + rpb2 - 1) / rpb2;
+      const __half* d16h = static_cast<const __half*>(dy16);
+      __half* h16s = static_cast<__half*>(dx16);
+      cudaError_t e = cudaSuccess;
+      if (cs_r1 || cs_out) {
+        UVC_LN_DISPATCH(C, { e = cudaFuncSetAttribute(layernorm_bwd_stream_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                             launch_pdl(layernorm_bwd_stream_kernel<NV, true>, dim3(nb), dim3(256), smem, st, d16h, x, mean, rstd, gamma, r1, r2, s2_dev, dx, dgamma, dbeta,
+                                        cs_r1, cs_out, M, C, rpb2, dy_scale, h16s, out_scale, scales_dev, dot_t, dots, dot_x); });
+      } else {
+        UVC_LN_DISPATCH(C, { e = cudaFuncSetAttribute(layernorm_bwd_stream_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                             launch_pdl(layernorm_bwd_stream_kernel<NV, false>, dim3(nb), dim3(256), smem, st, d16h, x, mean, rstd, gamma, r1, r2, s2_dev, dx, dgamma, dbeta,
+                                        nullptr, nullptr, M, C, rpb2, dy_scale, h16s, out_scale, scales_dev, dot_t, dots, dot_x); });
+      }
+      UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(layernorm_bwd_stream smem=%zu): %s", smem, cudaGetErrorString(e));
+      return check_launch("layernorm_bwd_stream");
+    }
+  }
   if (dy16) {
     const float* d16 = static_cast<const float*>(dy16);
     if (cs_r1 || cs_out)
