@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define UVC_ABI_VERSION 8
+#define UVC_ABI_VERSION 9
 #define UVC_MAX_DEPTH 32      /* most transformer blocks a uvc_vit_* call accepts */
 
 #if defined(UVC_BUILD_DLL)
@@ -329,6 +329,9 @@ typedef struct {
                                     This is how the T2T-ViT backbone (T2TViT/models/t2t_vit.py:168-208: cls + sinusoid pos-embed, 14 Blocks,
                                     norm, head) runs behind the same entry point, fed by tokens_to_token (:46-105).  x, w.patch_* may be NULL. */
   const uvc_vit_layout* layout;  /* host struct or NULL (dense): Stage-2 compaction, see uvc_vit_layout */
+  int32_t weights_converted;     /* 1: the workspace already holds the operand copies (fp16 / TF32-rounded) of exactly these weights from an earlier call
+                                    with the same workspace -- the caller's promise for a FROZEN model (the distillation teacher, utils/losses.py:47-49);
+                                    the per-forward weight conversion launch is skipped.  0: convert (always correct). */
 } uvc_vit_forward_args;
 
 typedef struct {

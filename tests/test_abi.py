@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
 
 def test_version_and_struct_sizes():
     lib = _lib.load()
-    assert lib.uvc_version() == 8
+    assert lib.uvc_version() == 9
     for name, st in _lib._ABI_STRUCTS.items():
         assert lib.uvc_abi_sizeof(name.encode()) == ctypes.sizeof(st), name
     assert lib.uvc_abi_sizeof(b"no_such_struct") == -1

@@ -205,3 +205,24 @@ def test_gate_gradients_same_through_both_layernorm_backward_kernels(monkeypatch
         res[mode] = (blend.grad.clone(), m.blocks[0].norm1.weight.grad.clone(), m.blocks[1].mlp.fc2.bias.grad.clone(), m.blocks[0].attn.qkv.weight.grad.clone())
     for a, b in zip(res["stream"], res["reg"]):
         assert rel(a, b) < 1e-4
+
+
+def test_frozen_teacher_keeps_its_converted_weights():
+    """`weights_frozen` (set by DistillationLoss on the teacher): the second eval forward skips the weight-conversion launch and must give the same
+    logits; loading new weights (version counters move) converts again."""
+    from uvc_b200 import _lib
+    from uvc_b200.utils.losses import DistillationLoss
+    sd, dims = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=3)
+    t = build("deit_tiny_patch16_224", 2, sd).eval()
+    DistillationLoss(torch.nn.CrossEntropyLoss(), t, "soft", 0.1, 1.0)
+    assert t.weights_frozen
+    x, _ = fx.make_batch(3, seed=4)
+    lib = _lib.load()
+    with torch.no_grad():
+        n0 = lib.uvc_launch_count(); a, _ = t(x.cuda()); n1 = lib.uvc_launch_count(); b, _ = t(x.cuda()); n2 = lib.uvc_launch_count()
+        assert torch.equal(a, b) and (n2 - n1) < (n1 - n0)            # fewer launches: no conversion the second time
+        sd2, _ = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=5)
+        t.load_state_dict(sd2, strict=False)
+        c, _ = t(x.cuda())
+        lo = vo.forward(sd2, x, 2, dims["num_heads"])
+    assert rel(c, lo) < LOGIT_TOL and rel(a, lo) > 0.1

@@ -40,7 +40,7 @@ class _T2TFrontFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mod, x, *params):
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = any(ctx.needs_input_grad) and getattr(mod, "_outer_grad_enabled", True)      # see _VitFunction.forward
         tokens, p, seed = mod._engine_forward(x, save=need_grad)
         ctx.mod, ctx.p, ctx.seed = mod, p, seed
         ctx.save_for_backward(x)
@@ -161,7 +161,11 @@ class T2T_module(nn.Module):
     def forward(self, x):
         B = x.shape[0]
         x = x.contiguous().float()
-        tokens = _T2TFrontFn.apply(self, x, *self._params())
+        self._outer_grad_enabled = torch.is_grad_enabled()
+        try:
+            tokens = _T2TFrontFn.apply(self, x, *self._params())
+        finally:
+            self._outer_grad_enabled = True
         side = x.shape[2] // 4
         macs = self.attention1.macs(B, side * side) + self.attention2.macs(B, (side // 2) ** 2)
         return tokens, macs          # the reference does not count project's MACs either (:105)
@@ -246,7 +250,11 @@ class T2T_ViT(DistilledVisionTransformer):
             token_mask = token_gate_from_tokens(self, pe, patch_scale, tau, int(ratio * np_))
         blend, skip = self._block_gates()
         params = [p for _, p in _engine_param_list(self)]
-        logits = _VitFunction.apply(self, pe.contiguous(), blend, patch_scale, token_mask, skip, *params)
+        self._outer_grad_enabled = torch.is_grad_enabled()
+        try:
+            logits = _VitFunction.apply(self, pe.contiguous(), blend, patch_scale, token_mask, skip, *params)
+        finally:
+            self._outer_grad_enabled = True
         executed = [True] * len(self.blocks) if skip is None else [not s for s in skip]
         return logits, (macs_embed, self._macs_backbone(B, executed))
 

@@ -64,7 +64,7 @@ class VitForwardArgs(C.Structure):
     _fields_ = [("dims", VitDims), ("w", VitTensors), ("x", _F), ("blend", _F), ("skip_host", C.c_void_p),
                 ("patch_scale", _F), ("token_mask", _F), ("save_for_backward", C.c_int32), ("enable_jumping", C.c_int32),
                 ("logits", _F), ("pe_out", _F), ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64), ("pe_in", _F),
-                ("layout", C.POINTER(VitLayout))]
+                ("layout", C.POINTER(VitLayout)), ("weights_converted", C.c_int32)]
 
 
 class VitBackwardArgs(C.Structure):

@@ -220,7 +220,7 @@ int vit_forward(const uvc_vit_forward_args& a, cudaStream_t st) {
   const float scale = 1.0f / sqrtf((float)D.d);
 
   // patch embed: 16x16/16 conv == GEMM over im2col rows
-  UVC_TRY(round_weights(a.w, D, w.wr, st));
+  if (!a.weights_converted) UVC_TRY(round_weights(a.w, D, w.wr, st));
   const float* pe = a.pe_in;
   if (!pe) {
     UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));
@@ -565,7 +565,7 @@ int vit_forward_f16(const uvc_vit_forward_args& a, const Dims& D, cudaStream_t s
 
   const uvc_vit_layout* lay = a.layout;
   UVC_TRY(check_layout(lay, D, a.skip_host));
-  UVC_TRY(convert_weights16(a.w, D, w, save, st, lay, a.skip_host));
+  if (!a.weights_converted) UVC_TRY(convert_weights16(a.w, D, w, save, st, lay, a.skip_host));
   const float* pe = a.pe_in;
   if (!pe) {
     UVC_TRY(im2col16(a.x, w.cols, D.B, D.cin, D.img, D.patch, st, 1));

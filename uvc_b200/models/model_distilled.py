@@ -219,8 +219,10 @@ class _VitFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, blend, patch_scale, token_mask, skip, *params):
-        # (grad mode is always off inside Function.forward; ctx.needs_input_grad says whether a backward can follow)
-        need_grad = any(ctx.needs_input_grad)
+        # Can a backward follow?  ctx.needs_input_grad only says which inputs require grad -- it is True for the parameters under torch.no_grad()
+        # as well -- and grad mode is always off inside Function.forward, so the caller records the OUTER grad mode on the model before apply():
+        # a no_grad forward (the distillation teacher, validation) then runs the inference path (no activations kept, no gelu' stored).
+        need_grad = any(ctx.needs_input_grad) and getattr(model, "_outer_grad_enabled", True)
         logits = model._engine_forward(x, blend, patch_scale, token_mask, skip, save=need_grad)
         ctx.model, ctx.skip, ctx.B = model, skip, x.shape[0]
         ctx.pe_mode = x.dim() == 3      # x is [B, np, C] token embeddings computed by the caller (T2T front end), not images
@@ -353,6 +355,12 @@ class DistilledVisionTransformer(VisionTransformer):
             a.layout = C.pointer(lay.struct)
         ws = self._workspace(B, save)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        if getattr(self, "weights_frozen", False) and not save:
+            # a frozen model (the distillation teacher): its fp16 / TF32 operand copies in the workspace stay valid from call to call, so the
+            # per-forward conversion launch is skipped while nothing about the weights, the layout or the workspace has changed
+            key = (ws.data_ptr(), es.sig, sum(p._version for _, p in _engine_param_list(self) if p is not None), id(lay))
+            a.weights_converted = 1 if getattr(self, "_wconv_key", None) == key else 0
+            self._wconv_key = key
         _lib.check(lib.uvc_vit_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "uvc_vit_forward")
         return logits
 
@@ -487,7 +495,11 @@ class DistilledVisionTransformer(VisionTransformer):
             x = pe.contiguous()                      # [B, np, C]: the engine takes the embeddings as `pe_in`
         blend, skip = self._block_gates()
         params = [p for _, p in _engine_param_list(self)]
-        logits = _VitFunction.apply(self, x, blend, patch_scale, token_mask, skip, *params)
+        self._outer_grad_enabled = torch.is_grad_enabled()
+        try:
+            logits = _VitFunction.apply(self, x, blend, patch_scale, token_mask, skip, *params)
+        finally:
+            self._outer_grad_enabled = True
         executed = [True] * len(self.blocks) if skip is None else [not s for s in skip]
         return logits, self._macs(B, executed)
 

@@ -35,6 +35,8 @@ class DistillationLoss(nn.Module):
         assert distillation_type in ['none', 'soft', 'hard']
         self.base_criterion = base_criterion
         self.teacher_model = teacher_model
+        if teacher_model is not None and hasattr(teacher_model, "_engine_forward"):
+            teacher_model.weights_frozen = True      # never trained (utils/losses.py:47-49 runs it under no_grad): the engine keeps its converted weights
         self.distillation_type = distillation_type
         self.alpha = alpha
         self.tau = tau
