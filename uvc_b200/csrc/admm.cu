@@ -102,12 +102,15 @@ __global__ void __launch_bounds__(256) rank_kernel(int H, int d, int Fh, const f
 // prox shrink (uvc_utils.py:315-345): W[:, col] *= 1/(1+2 lr p) for the bottom-ceil(r) columns of each head, then *= 1/(1+2 lr y) for the
 // columns of the bottom-ceil(s0) heads (W1) / the bottom-ceil(s1) neurons (W3).  grid (ceil(cols/128), L, 2), block (32, 8): a thread owns
 // 4 adjacent columns (one 128-bit access per row) and every 8th row; threads whose 4 columns are all unselected exit without touching memory.
+constexpr int kProxRowSplit = 4;
 __global__ void __launch_bounds__(256) prox_kernel(const __grid_constant__ WPtrs P, int H, int d, int Fh, const int* __restrict__ rank1,
                                                    const int* __restrict__ rank2, const int* __restrict__ rank3, const float* __restrict__ s,
                                                    const float* __restrict__ r, const float* __restrict__ y, const float* __restrict__ p, double lr) {
+  // blockIdx.x = column group * kProxRowSplit + row slice: four times the blocks of the first version (288 blocks, 15 % occupancy, 1 TB/s)
   const int which = blockIdx.z, l = blockIdx.y, C = H * d;
   const int cols = which ? Fh : C;
-  const int col0 = blockIdx.x * 128 + threadIdx.x * 4;
+  const int rs = blockIdx.x % kProxRowSplit;
+  const int col0 = (blockIdx.x / kProxRowSplit) * 128 + threadIdx.x * 4;
   if (col0 >= cols) return;
   float fa[4], fb[4];
   bool any = false;
@@ -129,8 +132,9 @@ __global__ void __launch_bounds__(256) prox_kernel(const __grid_constant__ WPtrs
   if (!any) return;
   float* W = (which ? P.w3[l] : P.w1[l]) + col0;
   // the reference multiplies selected columns by the first factor, then by the second: keep the two roundings (x * 1.0f is exact)
+  const int rows_per = (C + kProxRowSplit - 1) / kProxRowSplit, row_lo = rs * rows_per, row_hi = min(C, row_lo + rows_per);
 #pragma unroll 4
-  for (int row = threadIdx.y; row < C; row += 8) {
+  for (int row = row_lo + threadIdx.y; row < row_hi; row += 8) {
     float4* q = reinterpret_cast<float4*>(W + (long long)row * cols);
     float4 v = *q;
     v.x = (v.x * fa[0]) * fb[0]; v.y = (v.y * fa[1]) * fb[1]; v.z = (v.z * fa[2]) * fb[2]; v.w = (v.w * fa[3]) * fb[3];
@@ -495,7 +499,7 @@ int admm_prox(const uvc_admm_args& a, cudaStream_t st) {
   bool vec_ok = (C % 4 == 0) && (a.Fh % 4 == 0);
   for (int l = 0; l < a.L && vec_ok; ++l) vec_ok = ((reinterpret_cast<uintptr_t>(a.w1[l]) | reinterpret_cast<uintptr_t>(a.w3[l])) & 15) == 0;
   if (vec_ok)
-    prox_kernel<<<dim3((mx + 127) / 128, a.L, 2), dim3(32, 8), 0, st>>>(make_ptrs(a, false), a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y, a.p, a.lr);
+    prox_kernel<<<dim3(((mx + 127) / 128) * kProxRowSplit, a.L, 2), dim3(32, 8), 0, st>>>(make_ptrs(a, false), a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y, a.p, a.lr);
   else
     prox_mask_kernel<<<dim3((mx + 127) / 128, a.L, 2), 128, 0, st>>>(make_ptrs(a, false), 0, a.H, a.d, a.Fh, a.rank1, a.rank2, a.rank3, a.s, a.r, a.y,
                                                                     a.p, a.lr);

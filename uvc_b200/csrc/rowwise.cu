@@ -505,12 +505,14 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__
   const int G = HW / P;                       // patches per side
   const long long total4 = (long long)B * G * G * Cin * P * (P / 4);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int kx4 = (int)(t % (P / 4)); t /= (P / 4);
-    const int ky = (int)(t % P); t /= P;
-    const int c = (int)(t % Cin); t /= Cin;
-    const int px = (int)(t % G); t /= G;
-    const int py = (int)(t % G); t /= G;
+    // 32-bit index arithmetic (the host checks total4 < 2^31): the 64-bit divisions made this copy issue-bound (70 % issue-active at 2.8 TB/s)
+    unsigned t = (unsigned)i;
+    const unsigned P4 = (unsigned)P / 4;
+    const int kx4 = (int)(t % P4); t /= P4;
+    const int ky = (int)(t % (unsigned)P); t /= (unsigned)P;
+    const int c = (int)(t % (unsigned)Cin); t /= (unsigned)Cin;
+    const int px = (int)(t % (unsigned)G); t /= (unsigned)G;
+    const int py = (int)(t % (unsigned)G); t /= (unsigned)G;
     const int b = (int)t;
     float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * Cin + c) * HW + (py * P + ky)) * HW + px * P + kx4 * 4);
     if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
@@ -578,13 +580,26 @@ __global__ void __launch_bounds__(128) assemble_tokens_bwd_kernel(const float* _
   }
 }
 // dpos[n,:] += sum_b g[b,n,:] ; dcls[:] += sum_b g[b,0,:]
-__global__ void __launch_bounds__(128) pos_cls_grad_kernel(const float* __restrict__ g, float* __restrict__ dpos, float* __restrict__ dcls, int B, int ntok, int C) {
-  const int n = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int b = 0; b < B; ++b) a += g[((long long)b * ntok + n) * C + c];
-    dpos[(long long)n * C + c] += a;
-    if (n == 0 && dcls) dcls[c] += a;
+// grid (ntok, batch slices): a thread owns 4 adjacent columns and sums its slice of the batch with four independent accumulators (the first version
+// walked all B images serially in one thread per column: 56 us for 39 MB; this one is bound by the read, ~10 us)
+__global__ void __launch_bounds__(256) pos_cls_grad_kernel(const float* __restrict__ g, float* __restrict__ dpos, float* __restrict__ dcls, int B, int ntok, int C) {
+  const int n = blockIdx.x, nv = C >> 2;
+  const int per = (B + gridDim.y - 1) / gridDim.y, b0 = blockIdx.y * per, b1 = min(B, b0 + per);
+  for (int c = threadIdx.x; c < nv; c += blockDim.x) {
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+    const float4* base = reinterpret_cast<const float4*>(g) + (long long)n * nv + c;
+    const long long stride = (long long)ntok * nv;
+    int b = b0;
+    for (; b + 3 < b1; b += 4) {
+      const float4 v0 = base[b * stride], v1 = base[(b + 1) * stride], v2 = base[(b + 2) * stride], v3 = base[(b + 3) * stride];
+      a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w; a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+      a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w; a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+    }
+    for (; b < b1; ++b) { const float4 v = base[b * stride]; a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+    const float sx = (a0.x + a1.x) + (a2.x + a3.x), sy = (a0.y + a1.y) + (a2.y + a3.y), sz = (a0.z + a1.z) + (a2.z + a3.z), sw = (a0.w + a1.w) + (a2.w + a3.w);
+    float* o = dpos + (long long)n * C + 4 * c;
+    atomicAdd(o, sx); atomicAdd(o + 1, sy); atomicAdd(o + 2, sz); atomicAdd(o + 3, sw);
+    if (n == 0 && dcls) { atomicAdd(dcls + 4 * c, sx); atomicAdd(dcls + 4 * c + 1, sy); atomicAdd(dcls + 4 * c + 2, sz); atomicAdd(dcls + 4 * c + 3, sw); }
   }
 }
 
@@ -614,7 +629,21 @@ __global__ void __launch_bounds__(1024) grad_scale_kernel(const float* __restric
   float S = fixed;
   if (!(fixed > 0.f)) {
     float mx = 0.f;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(dlogits[i]));     // NaN / inf entries: fmaxf drops NaN, inf gives S = 0 -> clamped below
+    // NaN / inf entries: fmaxf drops NaN, inf gives S = 0 -> clamped below.  One block (the result is one scalar): 128-bit loads, four in flight
+    long long i0 = 0;
+    if ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0) {
+      const float4* d4 = reinterpret_cast<const float4*>(dlogits);
+      const long long n4 = n >> 2;
+      long long i = threadIdx.x;
+      for (; i + 3 * blockDim.x < n4; i += 4 * blockDim.x) {
+        const float4 a = d4[i], b = d4[i + blockDim.x], c = d4[i + 2 * blockDim.x], d = d4[i + 3 * blockDim.x];
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))), fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+        mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))), fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+      }
+      for (; i < n4; i += blockDim.x) { const float4 a = d4[i]; mx = fmaxf(mx, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)))); }
+      i0 = n4 << 2;
+    }
+    for (long long i = i0 + threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(dlogits[i]));
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
@@ -646,7 +675,7 @@ __global__ void __launch_bounds__(256) round_segs_kernel(const __grid_constant__
 // fp32 weights -> fp16 operand copies, all GEMM weights of the model in one launch: dst [rows, cols] (K-major B operand of the forward
 // GEMM) and, when dstT != NULL, the transpose [cols, rows] (K-major B operand of the data-gradient GEMM, so no MN-major 16-bit path is
 // needed there).  32 x 32 tiles through shared memory; both stores are coalesced.
-struct CvtSegs { const float* src[kMaxRoundSegs]; __half* dst[kMaxRoundSegs]; __half* dstT[kMaxRoundSegs]; int rows[kMaxRoundSegs]; int cols[kMaxRoundSegs]; int nseg; };
+struct CvtSegs { const float* src[kMaxRoundSegs]; __half* dst[kMaxRoundSegs]; __half* dstT[kMaxRoundSegs]; int rows[kMaxRoundSegs]; int cols[kMaxRoundSegs]; int nseg; int vec; };
 __global__ void __launch_bounds__(256) cvt_f16_segs_kernel(const __grid_constant__ CvtSegs segs) {
   __shared__ float tile[32][33];
   const int seg = blockIdx.y;
@@ -654,8 +683,32 @@ __global__ void __launch_bounds__(256) cvt_f16_segs_kernel(const __grid_constant
   __half* __restrict__ dst = segs.dst[seg];
   __half* __restrict__ dstT = segs.dstT[seg];
   const int rows = segs.rows[seg], cols = segs.cols[seg];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int tc = (cols + 31) / 32, tr = (rows + 31) / 32;
+  if (segs.vec) {
+    // every matrix has rows, cols % 4 == 0 and 16-byte aligned rows: one 128-bit load and one 64-bit store per thread for the straight copy, four
+    // values down a column per 64-bit store for the transposed one (the scalar version below ran at 2 TB/s: 66 us for the 22 M DeiT-Small weights)
+    const int r_in = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;           // load: 32 rows x 8 float4
+    const int c_out = threadIdx.x >> 3, r4 = (threadIdx.x & 7) * 4;          // transposed store: 32 columns x 8 groups of 4 rows
+    for (int t = blockIdx.x; t < tc * tr; t += gridDim.x) {
+      const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
+      const int r = r0 + r_in, c = c0 + c4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows && c < cols) {
+        v = *reinterpret_cast<const float4*>(src + (long long)r * cols + c);
+        if (dst) *reinterpret_cast<uint2*>(dst + (long long)r * cols + c) = pack_half4(v.x, v.y, v.z, v.w);
+      }
+      if (dstT) {
+        tile[r_in][c4] = v.x; tile[r_in][c4 + 1] = v.y; tile[r_in][c4 + 2] = v.z; tile[r_in][c4 + 3] = v.w;
+        __syncthreads();
+        const int cc = c0 + c_out, rr = r0 + r4;
+        if (cc < cols && rr < rows)
+          *reinterpret_cast<uint2*>(dstT + (long long)cc * rows + rr) = pack_half4(tile[r4][c_out], tile[r4 + 1][c_out], tile[r4 + 2][c_out], tile[r4 + 3][c_out]);
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int t = blockIdx.x; t < tc * tr; t += gridDim.x) {
     const int r0 = (t / tc) * 32, c0 = (t % tc) * 32;
 #pragma unroll
@@ -798,6 +851,7 @@ int blend_dots(const float* g, const float* t, const float* x, float* dots, long
 int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStream_t st, int rnd) {
   UVC_REQUIRE(P % 4 == 0 && HW % P == 0, UVC_ERR_BAD_SHAPE, "im2col: patch %d must divide image %d and be a multiple of 4", P, HW);
   const long long total4 = (long long)B * Cin * HW * HW / 4;
+  UVC_REQUIRE(total4 < (1ll << 31), UVC_ERR_BAD_SHAPE, "im2col: batch too large (%lld elements)", total4 * 4);
   im2col16_kernel<<<grid_for(total4, 256, 148 * 16), 256, 0, st>>>(x, out, B, Cin, HW, P, rnd);
   return check_launch("im2col16");
 }
@@ -815,7 +869,7 @@ int assemble_tokens_bwd(const float* g, const float* pe, const float* pscale, co
   int rc = check_launch("assemble_tokens_bwd");
   if (rc) return rc;
   if (dpos) {
-    pos_cls_grad_kernel<<<np + 1, 128, 0, st>>>(g, dpos, dcls, B, np + 1, C);
+    pos_cls_grad_kernel<<<dim3(np + 1, B >= 32 ? 8 : 1), (C / 4 <= 128 ? 128 : 256), 0, st>>>(g, dpos, dcls, B, np + 1, C);
     rc = check_launch("pos_cls_grad");
   }
   return rc;
@@ -851,9 +905,12 @@ int cvt_f16_segs(const float* const* src, void* const* dst, void* const* dstT, c
     CvtSegs segs;
     segs.nseg = (nseg - base < kMaxRoundSegs) ? nseg - base : kMaxRoundSegs;
     long long mx = 0;
+    segs.vec = 1;
     for (int i = 0; i < segs.nseg; ++i) {
       segs.src[i] = src[base + i]; segs.dst[i] = static_cast<__half*>(dst[base + i]); segs.dstT[i] = dstT ? static_cast<__half*>(dstT[base + i]) : nullptr;
       segs.rows[i] = rows[base + i]; segs.cols[i] = cols[base + i];
+      if ((rows[base + i] & 3) || (cols[base + i] & 3) || (reinterpret_cast<uintptr_t>(segs.src[i]) & 15) || (reinterpret_cast<uintptr_t>(segs.dst[i]) & 7) ||
+          (reinterpret_cast<uintptr_t>(segs.dstT[i]) & 7)) segs.vec = 0;
       const long long tiles = (long long)((rows[base + i] + 31) / 32) * ((cols[base + i] + 31) / 32);
       if (tiles > mx) mx = tiles;
     }
