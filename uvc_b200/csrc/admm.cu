@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(256) colnorm_kernel(const __grid_constant__ WP
 
 // ranks ("k smallest" == rank < k, ties -> lower index first, as torch.topk(largest=False) on CPU).  grid (L, 1 + ceil(Fh/256)):
 //   blockIdx.y == 0 : head sums (fixed order: deterministic), ranks inside each head (c1) and across heads (c2)
-//   blockIdx.y >= 1 : 256 neurons of the layer each, ranked against all Fh (the O(Fh^2) part, spread over ~7 blocks per layer instead of one)
+//   blockIdx.y >= 1 : 128 neurons of the layer each, ranked against all Fh (the O(Fh^2) part, spread over 12 blocks per layer instead of one)
+constexpr int kRankPerBlock = 128;     // neurons ranked per block: 12 blocks per layer for Fh = 1536 (the grid then covers all SMs)
 __global__ void __launch_bounds__(256) rank_kernel(int H, int d, int Fh, const float* __restrict__ c1, float* __restrict__ c2,
                                                    const float* __restrict__ c3, int* __restrict__ rank1, int* __restrict__ rank2,
                                                    int* __restrict__ rank3) {
-  __shared__ float sv[kMaxFh];
+  __shared__ __align__(16) float sv[kMaxFh + 4];
   __shared__ float sh[kMaxH];
   const int l = blockIdx.x, C = H * d, tid = threadIdx.x;
   if (blockIdx.y == 0) {
@@ -88,14 +89,23 @@ __global__ void __launch_bounds__(256) rank_kernel(int H, int d, int Fh, const f
     return;
   }
   for (int i = tid; i < Fh; i += blockDim.x) sv[i] = c3[(long long)l * Fh + i];
+  for (int i = Fh + tid; i < ((Fh + 3) & ~3); i += blockDim.x) sv[i] = INFINITY;          // pad to a multiple of 4: +inf is never "smaller"
   __syncthreads();
-  const int i = (blockIdx.y - 1) * 256 + tid;
-  if (i < Fh) {
+  const int i = (blockIdx.y - 1) * kRankPerBlock + tid;
+  if (tid < kRankPerBlock && i < Fh) {
+    // rank = #{m : u_m < v} + #{m < i : u_m == v}: 128-bit broadcast reads, branch-free counting (two independent counters)
     const float v = sv[i];
-    int rk = 0;
+    int rk0 = 0, rk1 = 0;
+    const float4* sv4 = reinterpret_cast<const float4*>(sv);
+    const int n4 = (Fh + 3) >> 2;
 #pragma unroll 4
-    for (int m = 0; m < Fh; ++m) { const float u = sv[m]; rk += (u < v) || (u == v && m < i); }
-    rank3[(long long)l * Fh + i] = rk;
+    for (int m4 = 0; m4 < n4; ++m4) {
+      const float4 u = sv4[m4];
+      const int m = m4 * 4;
+      rk0 += (int)(u.x < v) + (int)((u.x == v) & (m < i)) + (int)(u.y < v) + (int)((u.y == v) & (m + 1 < i));
+      rk1 += (int)(u.z < v) + (int)((u.z == v) & (m + 2 < i)) + (int)(u.w < v) + (int)((u.w == v) & (m + 3 < i));
+    }
+    rank3[(long long)l * Fh + i] = rk0 + rk1;
   }
 }
 
@@ -486,7 +496,7 @@ int admm_scores(const uvc_admm_args& a, cudaStream_t st) {
   const int mx = a.Fh > C ? a.Fh : C;
   colnorm_kernel<<<dim3((mx + 31) / 32, a.L, 2), dim3(32, 8), 0, st>>>(make_ptrs(a, false), C, a.Fh, a.c1, a.c3);
   if ((rc = check_launch("admm colnorm"))) return rc;
-  rank_kernel<<<dim3(a.L, 1 + (a.Fh + 255) / 256), 256, 0, st>>>(a.H, a.d, a.Fh, a.c1, a.c2, a.c3, a.rank1, a.rank2, a.rank3);
+  rank_kernel<<<dim3(a.L, 1 + (a.Fh + kRankPerBlock - 1) / kRankPerBlock), 256, 0, st>>>(a.H, a.d, a.Fh, a.c1, a.c2, a.c3, a.rank1, a.rank2, a.rank3);
   return check_launch("admm rank");
 }
 

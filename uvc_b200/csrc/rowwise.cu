@@ -528,10 +528,11 @@ __global__ void __launch_bounds__(256) assemble_tokens_kernel(const float* __res
   const int nv = C >> 2;
   const long long total = (long long)B * (np + 1) * nv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % nv);
-    const long long r = i / nv;
-    const int n = (int)(r % (np + 1));
-    const int b = (int)(r / (np + 1));
+    const unsigned iu = (unsigned)i;                 // 32-bit index arithmetic (the host checks total < 2^31)
+    const int c = (int)(iu % (unsigned)nv);
+    const unsigned r = iu / (unsigned)nv;
+    const int n = (int)(r % (unsigned)(np + 1));
+    const int b = (int)(r / (unsigned)(np + 1));
     const float4 po = __ldg(reinterpret_cast<const float4*>(pos) + (long long)n * nv + c);
     float4 o;
     if (n == 0) {
@@ -858,6 +859,7 @@ int im2col16(const float* x, float* out, int B, int Cin, int HW, int P, cudaStre
 int assemble_tokens(const float* pe, const float* cls, const float* pos, const float* pscale, const float* tmask, float* tok, int B, int np, int C,
                     cudaStream_t st) {
   UVC_REQUIRE((C & 3) == 0, UVC_ERR_BAD_SHAPE, "assemble_tokens: C must be a multiple of 4");
+  UVC_REQUIRE((long long)B * (np + 1) * (C / 4) < (1ll << 31), UVC_ERR_BAD_SHAPE, "assemble_tokens: too many elements");
   assemble_tokens_kernel<<<grid_for((long long)B * (np + 1) * (C / 4), 256, 148 * 16), 256, 0, st>>>(pe, cls, pos, pscale, tmask, tok, B, np, C);
   return check_launch("assemble_tokens");
 }
