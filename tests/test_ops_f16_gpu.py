@@ -177,4 +177,5 @@ def test_layernorm_bwd_streamed_kernel_equals_register_kernel(ops, monkeypatch, 
         if bb.abs().max() == 0:
             assert a.abs().max() == 0, n
         else:
-            assert rel(a, bb) < (1e-6 if n == "dx" else 2e-4), (n, rel(a, bb))
+            # dx: summation order only; dx16: a 1-ulp difference of dx may flip an fp16 rounding (2^-11 of that element); sums: atomics order
+            assert rel(a, bb) < {"dx": 2e-6, "dx16": 6e-4}.get(n, 2e-4), (n, rel(a, bb))

@@ -227,7 +227,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 template <int NV, bool CS>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_stream_kernel(const __half* __restrict__ dy16, const float* __restrict__ x, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, (NV <= 3 ? 2 : 1)) layernorm_bwd_stream_kernel(const __half* __restrict__ dy16, const float* __restrict__ x, const float* __restrict__ mean,
                                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                       const float* __restrict__ r1, const float* __restrict__ r2, const float* __restrict__ s2_dev,
                                                                       float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -289,30 +289,33 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_stream_kernel(const __ha
     const float4* r2r = reinterpret_cast<const float4*>(base + off_r2) + (size_t)warp * nv;
     const float4* dtr = reinterpret_cast<const float4*>(base + off_t) + (size_t)warp * nv;
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[NV], gg[NV], res[NV];
+    // two passes over the staged row (shared memory is cheap to re-read; keeping xhat / g / residual in registers between the passes cost
+    // 12 * NV registers and spilled for C = 768): pass 1 reduces, pass 2 recomputes and writes
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
-      res[i] = make_float4(0, 0, 0, 0);
       if (c < nv) {
         const uint2 u = dyr[c];
         const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
         const float4 d = make_float4(lo.x * dy_scale, lo.y * dy_scale, hi.x * dy_scale, hi.y * dy_scale);
         const float4 xv = xr[c], gm = __ldg(g4 + c);
-        if (r1) res[i] = r1r[c];
-        if (r2) {
-          const float4 a = r2r[c];
-          res[i].x += s2 * a.x; res[i].y += s2 * a.y; res[i].z += s2 * a.z; res[i].w += s2 * a.w;
-          if (dot_x) acc_dx += (a.x * xv.x + a.y * xv.y) + (a.z * xv.z + a.w * xv.w);
-          if (dot_t) { const float4 tv = dtr[c]; acc_dt += (a.x * tv.x + a.y * tv.y) + (a.z * tv.z + a.w * tv.w); }
+        if (CS || dot_x || dot_t) {
+          float4 res = make_float4(0, 0, 0, 0);
+          if (r1) res = r1r[c];
+          if (r2) {
+            const float4 a = r2r[c];
+            res.x += s2 * a.x; res.y += s2 * a.y; res.z += s2 * a.z; res.w += s2 * a.w;
+            if (dot_x) acc_dx += (a.x * xv.x + a.y * xv.y) + (a.z * xv.z + a.w * xv.w);
+            if (dot_t) { const float4 tv = dtr[c]; acc_dt += (a.x * tv.x + a.y * tv.y) + (a.z * tv.z + a.w * tv.w); }
+          }
+          if (CS) { a1[i].x += res.x; a1[i].y += res.y; a1[i].z += res.z; a1[i].w += res.w; }
         }
-        if (CS) { a1[i].x += res[i].x; a1[i].y += res[i].y; a1[i].z += res[i].z; a1[i].w += res[i].w; }
-        xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs; xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
-        gg[i].x = d.x * gm.x; gg[i].y = d.y * gm.y; gg[i].z = d.z * gm.z; gg[i].w = d.w * gm.w;
-        sg += (gg[i].x + gg[i].y) + (gg[i].z + gg[i].w);
-        sgx += (gg[i].x * xh[i].x + gg[i].y * xh[i].y) + (gg[i].z * xh[i].z + gg[i].w * xh[i].w);
-        ag[i].x += d.x * xh[i].x; ag[i].y += d.y * xh[i].y; ag[i].z += d.z * xh[i].z; ag[i].w += d.w * xh[i].w;
+        const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        const float4 gg = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        sg += (gg.x + gg.y) + (gg.z + gg.w);
+        sgx += (gg.x * xh.x + gg.y * xh.y) + (gg.z * xh.z + gg.w * xh.w);
+        ag[i].x += d.x * xh.x; ag[i].y += d.y * xh.y; ag[i].z += d.z * xh.z; ag[i].w += d.w * xh.w;
         ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
       }
     }
@@ -322,9 +325,15 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_stream_kernel(const __ha
     for (int i = 0; i < NV; ++i) {
       const int c = lane + i * 32;
       if (c < nv) {
+        const uint2 u = dyr[c];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        const float4 xv = xr[c], gm = __ldg(g4 + c);
+        float4 res = make_float4(0, 0, 0, 0);
+        if (r1) res = r1r[c];
+        if (r2) { const float4 a = r2r[c]; res.x += s2 * a.x; res.y += s2 * a.y; res.z += s2 * a.z; res.w += s2 * a.w; }
         float4 o;
-        o.x = res[i].x + rs * (gg[i].x - mg - xh[i].x * mgx); o.y = res[i].y + rs * (gg[i].y - mg - xh[i].y * mgx);
-        o.z = res[i].z + rs * (gg[i].z - mg - xh[i].z * mgx); o.w = res[i].w + rs * (gg[i].w - mg - xh[i].w * mgx);
+        o.x = res.x + rs * ((lo.x * dy_scale) * gm.x - mg - ((xv.x - mu) * rs) * mgx); o.y = res.y + rs * ((lo.y * dy_scale) * gm.y - mg - ((xv.y - mu) * rs) * mgx);
+        o.z = res.z + rs * ((hi.x * dy_scale) * gm.z - mg - ((xv.z - mu) * rs) * mgx); o.w = res.w + rs * ((hi.y * dy_scale) * gm.w - mg - ((xv.w - mu) * rs) * mgx);
         if (CS) { ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w; }
         dxr[c] = o;
         if (dx16) reinterpret_cast<uint2*>(dx16 + (long long)row * C)[c] = pack_half4(o.x * out_scale, o.y * out_scale, o.z * out_scale, o.w * out_scale);
