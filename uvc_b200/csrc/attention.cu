@@ -778,11 +778,10 @@ static int attention_fwd_fused(const float* qkv, float* P, float* ctx, float* ls
   kp.P = P; kp.ctx = ctx; kp.lse = lse; kp.ldp = attn_ldp(N);
   kp.B = B; kp.H = H; kp.N = N; kp.C = (int)C; kp.ntiles = (N + 127) / 128; kp.save_P = P != nullptr;
   kp.scale_log2e = scale * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;       // devices this kernel's attribute has been set on
+  if (first_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kASmem);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn_fwd smem=%d): %s", kASmem, cudaGetErrorString(e));
-    attr_set = true;
   }
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -843,12 +842,11 @@ int attention_bwd_fused(const float* qkv, const float* lse, const float* ctx, co
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = B * H < sms ? B * H : sms;
   constexpr int smem1 = 2 * kBABytes + 3 * kBBBytes + 1024, smem2 = 2 * kBABytes + 2 * kBBBytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;       // devices this kernel's attribute has been set on
+  if (first_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(attn_bwd): %s", cudaGetErrorString(e));
-    attr_set = true;
   }
   AttnBwdParams kp;
   kp.lse = lse; kp.Dv = Dv; kp.ldo = ld3; kp.B = B; kp.H = H; kp.N = N; kp.ntiles = (N + 127) / 128;

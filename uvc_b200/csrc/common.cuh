@@ -21,6 +21,18 @@ void prof_end(cudaStream_t st);
 #define UVC_REQUIRE(cond, code, ...)                                   \
   do { if (!(cond)) { ::uvc::set_error(__VA_ARGS__); return (code); } } while (0)
 
+// ---------------------------------------------------------------- per-device one-time setup
+// Function attributes (opt-in shared memory sizes) and SM counts belong to a DEVICE, not to the process: a host thread that drives several GPUs
+// through this library must get them set / read on each one.  `mask` is a call site's static bit set of the devices it has already prepared.
+inline bool first_on_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch (PDL)
 // The engine enqueues ~35 dependent kernels per transformer block; with plain stream order each one pays the launch latency and its own
 // prologue (barrier init, TMEM allocation, tensor-map prefetch) after its predecessor has fully drained.  Kernels launched through

@@ -792,11 +792,10 @@ static int make_tmap_grouped(CUtensorMap* tm, const uvc_operand& op, int rows_mn
 template <int BN, int STAGES>
 static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;       // devices this kernel's attribute has been set on
+  if (first_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_set = true;
   }
   launch_pdl(gemm_tf32_kernel<BN, STAGES>, grid, dim3(kThreads), Cfg::SMEM_BYTES, st, kp);
   return check_launch("gemm_tf32_kernel");
@@ -806,11 +805,10 @@ static int launch(const GemmKParams& kp, dim3 grid, cudaStream_t st) {
 template <int BN, int STAGES, bool A_MN, bool B_MN, int MODE>
 static int launch2k(const GemmKParams& kp, int pairs, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN, STAGES, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;       // devices this kernel's attribute has been set on
+  if (first_on_device(&attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     UVC_REQUIRE(e == cudaSuccess, UVC_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
-    attr_set = true;
   }
   launch_pdl(gemm2_tf32_kernel<BN, STAGES, A_MN, B_MN, MODE>, dim3(2 * pairs), dim3(threads2(BN, MODE)), Cfg::SMEM_BYTES, st, kp);
   return check_launch("gemm2_tf32_kernel");
@@ -829,13 +827,16 @@ static int launch2(const GemmKParams& kp, int pairs, cudaStream_t st) {
 }
 
 static int sm_pairs() {
-  static int pairs = 0;
-  if (pairs == 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
-    pairs = sms / 2;
+  static int pairs[64] = {0};            // per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 74;
+  int& p = pairs[dev & 63];
+  if (p == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+    p = sms / 2;
   }
-  return pairs;
+  return p;
 }
 
 // 0 = always the 128 x 128 kernel, 1 = pick per shape (default), 2 = CTA-pair kernel whenever it is legal
