@@ -163,6 +163,7 @@ class EvalStep:
         self.loss_fct = torch.nn.CrossEntropyLoss()
         self.tau = 1 if args.enable_patch_gating == 2 else -1
         self.acc = None
+        self.images = self.batches = 0
 
     def __call__(self, x, y):
         with torch.no_grad():
@@ -170,17 +171,17 @@ class EvalStep:
             loss = self.loss_fct(logits, y)
             correct = (logits.argmax(dim=1) == y).sum()
             if self.acc is None:
-                self.acc = torch.zeros(4, device=logits.device, dtype=torch.float64)    # correct, images, loss sum, batches
-            self.acc += torch.stack([correct.double(), torch.tensor(float(x.size(0)), device=logits.device, dtype=torch.float64), loss.double(),
-                                     torch.ones((), device=logits.device, dtype=torch.float64)])
+                self.acc = torch.zeros(2, device=logits.device, dtype=torch.float64)    # correct predictions, sum of batch losses
+            self.acc += torch.stack([correct.double(), loss.double()])
+        self.images += int(x.size(0)); self.batches += 1         # host-known counts stay on the host (a device scalar built from a Python number is a synchronous copy)
         return {"loss": loss}
 
     def result(self):
         """(top-1 in percent, mean loss) -- the one device->host read of the loop"""
         if self.acc is None:
             return 0.0, 0.0
-        c, n, ls, nb = self.acc.tolist()
-        return 100.0 * c / max(n, 1.0), ls / max(nb, 1.0)
+        c, ls = self.acc.tolist()
+        return 100.0 * c / max(self.images, 1), ls / max(self.batches, 1)
 
 
 def valid(args, model, writer, test_loader, global_step):

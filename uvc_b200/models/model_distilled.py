@@ -186,7 +186,12 @@ class _EngineState:
 
 
 def _engine_param_list(model):
-    """(name, Parameter) in the fixed order the autograd Function receives them."""
+    """(name, Parameter) in the fixed order the autograd Function receives them.  Called a dozen times per step (forward, backward, optimiser,
+    DDP), so the list is built once per model and re-validated by identity of its first and last members (Parameters are replaced only by
+    surgery such as load_state_dict(assign=True); `.to()`, `flatten_parameters()` and optimiser updates keep the objects)."""
+    cached = model.__dict__.get("_uvc_plist")
+    if cached is not None and cached[-1][1] is model.blocks[-1].mlp.fc2.bias and cached[2][1] is model.cls_token and cached[6][1] is model.head.weight:
+        return cached
     pe = getattr(model, "patch_embed", None)      # absent for T2T-ViT: the tokens arrive from tokens_to_token (engine `pe_in`)
     out = [("patch_w", pe.proj.weight if pe is not None else None), ("patch_b", pe.proj.bias if pe is not None else None), ("cls_token", model.cls_token),
            ("pos_embed", model.pos_embed), ("norm_w", model.norm.weight), ("norm_b", model.norm.bias),
@@ -196,6 +201,7 @@ def _engine_param_list(model):
                 (f"b{i}.qkv_b", blk.attn.qkv.bias), (f"b{i}.proj_w", blk.attn.proj.weight), (f"b{i}.proj_b", blk.attn.proj.bias),
                 (f"b{i}.norm2_w", blk.norm2.weight), (f"b{i}.norm2_b", blk.norm2.bias), (f"b{i}.fc1_w", blk.mlp.fc1.weight),
                 (f"b{i}.fc1_b", blk.mlp.fc1.bias), (f"b{i}.fc2_w", blk.mlp.fc2.weight), (f"b{i}.fc2_b", blk.mlp.fc2.bias)]
+    model.__dict__["_uvc_plist"] = out
     return out
 
 
@@ -516,13 +522,14 @@ class DistilledVisionTransformer(VisionTransformer):
 def hard_skip_list(model):
     """Hard-skip decisions of `block_skip_gating` (reference models/model_distilled.py:496-500: a block runs iff gate[1] > gate[0]).
     The decision shapes the launch sequence, so it needs a host read -- per CHANGE of the gates, not per forward: in eval mode (the frozen
-    teacher of every training step, validation) the list is cached on the parameter's storage and version counter, so the teacher
-    forward issues no device-to-host read inside the training loop.  A training-mode model re-reads every time (the optimiser kernels
-    write parameters through raw pointers, which does not move the version counter)."""
+    teacher of every training step, validation) and whenever the gates are frozen (`requires_grad = False`: Stage 2, post_train.py:342) the list
+    is cached on the parameter's storage and version counter, so neither the teacher forward nor a Stage-2 step waits for the device.  A model that
+    trains its gates re-reads every time (the optimiser kernels write parameters through raw pointers, which does not move the version counter)."""
     g = model.block_skip_gating
     key = (g.data_ptr(), g._version)
     cached = getattr(model, "_skip_cache", None)
-    if model.training or cached is None or cached[0] != key:
+    frozen = (not model.training) or (not g.requires_grad)       # Stage 2 freezes the gates (post_train.py:342): no optimiser touches them
+    if not frozen or cached is None or cached[0] != key:
         cached = (key, [not (v[1] > v[0]) for v in g.detach().tolist()])
         model._skip_cache = cached
     return list(cached[1])
