@@ -245,3 +245,32 @@ def test_logits_match_oracle_at_bench_size():
     print(f"bench-size logits: max {e_max:.3e}  99.9th pct {e_999:.3e}  rms {e_rms:.3e}  (of the largest logit)")
     assert e_rms < 3e-4 and e_999 < LOGIT_TOL and e_max < 1.25e-3
     assert (out.argmax(1).cpu() == lo.argmax(1)).float().mean() > 0.97        # top-1 decisions agree except on near-ties of random-weight logits
+
+
+def test_teacher_prefetch_on_side_stream_gives_the_same_loss(monkeypatch):
+    """DistillationLoss.prefetch_teacher starts the teacher forward on a side stream next to the student forward; the loss (and its gradient) must be
+    the one the in-line teacher call gives, and a call with another input tensor must not pick the prefetched logits up."""
+    from uvc_b200.utils.losses import DistillationLoss
+    from uvc_b200.utils.mixup import SoftTargetCrossEntropy
+    sd, dims = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=3)
+    student = build("deit_tiny_patch16_224", 2, sd).train()
+    sd_t, _ = fx.make_state_dict("deit_tiny_patch16_224", 2, seed=5)
+    teacher = build("deit_tiny_patch16_224", 2, sd_t).eval()
+    crit = DistillationLoss(SoftTargetCrossEntropy(), teacher, "soft", 0.3, 1.0)
+    x, _ = fx.make_batch(4, seed=6)
+    x = x.cuda()
+    tgt = fx.soft_targets(4, seed=6).cuda()
+    res = []
+    for mode in ("inline", "prefetch", "stale"):
+        student.zero_grad(set_to_none=True)
+        if mode == "prefetch":
+            crit.prefetch_teacher(x)
+        if mode == "stale":
+            crit.prefetch_teacher(x * 2.0)                   # logits of ANOTHER tensor: must be ignored
+        out, _ = student(x)
+        loss = crit(x, out, tgt)
+        loss.backward()
+        res.append((float(loss), student.head.weight.grad.clone()))
+    assert crit._pref is None
+    for l, g in res[1:]:
+        assert abs(l - res[0][0]) < 1e-6 * abs(res[0][0]) and rel(g, res[0][1]) < 1e-6

@@ -246,6 +246,8 @@ class Stage1Step:
         if self.mixup_fn is not None:
             x, y = self.mixup_fn(x, y)
         self._mark("mixup")
+        if hasattr(self.criterion, "prefetch_teacher"):
+            self.criterion.prefetch_teacher(x)        # the dense teacher forward runs on a side stream next to the student forward
         outputs, flops_list = self.ddp_model(x, tau, args.patch_ratio)
         self._mark("student_fwd")
         loss = self.criterion(x, outputs, y)

@@ -75,6 +75,8 @@ class Stage2Step:
             x, y = x[:-1], y[:-1]
         if self.mixup_fn is not None:
             x, y = self.mixup_fn(x, y)
+        if hasattr(self.criterion, "prefetch_teacher"):
+            self.criterion.prefetch_teacher(x)
         outputs, _ = self.ddp_model(x)
         loss = self.criterion(x, outputs, y)
         loss.backward()

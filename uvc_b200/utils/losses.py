@@ -41,6 +41,37 @@ class DistillationLoss(nn.Module):
         self.alpha = alpha
         self.tau = tau
         self.last_parts = None      # device tensor (loss, base, kd) of the last fused call
+        self._side = None           # side stream of prefetch_teacher()
+        self._pref = None
+
+    def prefetch_teacher(self, inputs):
+        """Optional: start the teacher forward of `inputs` NOW, on a side stream, so that it runs next to the student forward the caller issues
+        after this call (the two are independent until the loss; utils/losses.py:47-49 runs the teacher inside the criterion, after the student).
+        Every hot kernel is persistent with a static share of the tiles, so a kernel's last wave leaves SMs idle (8.03 tile waves run as 9, 5.2
+        attention waves as 6); CTAs of the other stream's kernels move onto SMs as they are vacated.  `forward` picks the result up when it is called
+        with the same `inputs` tensor, and falls back to computing it itself otherwise.  UVC_TEACHER_STREAM=0 disables it."""
+        import os
+        self._pref = None
+        if self.distillation_type == 'none' or self.teacher_model is None or not inputs.is_cuda or os.environ.get("UVC_TEACHER_STREAM", "1") == "0":
+            return
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=inputs.device)
+        self._side.wait_stream(cur)                                  # the (mixed) inputs are ready
+        with torch.cuda.stream(self._side), torch.no_grad():
+            out, _ = self.teacher_model(inputs)
+        self._pref = (inputs.data_ptr(), inputs._version, out)
+
+    def _teacher(self, inputs):
+        pref, self._pref = self._pref, None
+        if pref is not None and pref[0] == inputs.data_ptr() and pref[1] == inputs._version:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self._side)
+            pref[2].record_stream(cur)                               # allocated on the side stream, consumed here
+            return pref[2]
+        with torch.no_grad():
+            out, _ = self.teacher_model(inputs)
+        return out
 
     def _targets(self, outputs, labels):
         """soft-target matrix equivalent to the base criterion, or None if the criterion is not one of the fusable ones"""
@@ -67,8 +98,7 @@ class DistillationLoss(nn.Module):
         fused = targets is not None and (self.distillation_type == 'none' or outputs_kd is outputs)
         teacher_outputs = None
         if self.distillation_type != 'none':
-            with torch.no_grad():
-                teacher_outputs, _ = self.teacher_model(inputs)
+            teacher_outputs = self._teacher(inputs)
         if fused:
             T = float(self.tau)
             if self.distillation_type == 'soft':
