@@ -389,10 +389,18 @@ def run_gpu(a):
     clk = clocks.stop([(w0, w1, "timed region"), (w2, w3, "end-to-end leg (timed region too short for a sample)")]) if rank == 0 else None
 
     # ---- roofline leg: every GEMM launch of 2 instrumented steps timed with a CUDA-event pair on the launching stream
+    # (the teacher forward normally runs on a side stream next to the student forward; for this leg it is put back in line so that every
+    # launch is timed alone on the GPU -- a kernel that shares the SMs with another stream's kernel is not a roofline measurement)
+    prev_ts = os.environ.get("UVC_TEACHER_STREAM")
+    os.environ["UVC_TEACHER_STREAM"] = "0"
     lib.uvc_gemm_profile(1)
     for i in range(2):
         dev_step(i)
     torch.cuda.synchronize()
+    if prev_ts is None:
+        os.environ.pop("UVC_TEACHER_STREAM", None)
+    else:
+        os.environ["UVC_TEACHER_STREAM"] = prev_ts
     import ctypes
     f16_mode = bool(model._dims(B).operand_f16)
     t_ms, t_fl, n_l = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -431,7 +439,9 @@ def run_gpu(a):
                   "optimizer, ADMM in f32)" if f16_mode else "tf32 (fp32 storage, fp32 accumulate)"), "data": "synthetic",
         "config": {"workload": cfg["workload"], "name": a.config, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "host_numa_binding": numa, "l2": "inputs + activations per step (>8 GB) far exceed the 126 MB L2; no explicit flush",
-                   "parity_unpinned": "Mixup / soft-target CE / AdamW grouping follow timm's public semantics (timm is absent from the reference tree)", **info},
+                   "parity_unpinned": "Mixup / soft-target CE / AdamW grouping follow timm's public semantics (timm is absent from the reference tree)",
+                   **({"teacher_forward": ("in line" if os.environ.get("UVC_TEACHER_STREAM", "1") == "0" else "on a side stream next to the student forward")}
+                      if cfg["stage"] != "eval" else {}), **info},
         "clocks": clk,
         "e2e": {"value": round(imgs / (ms_e2e / 1e3), 1), "unit": "images/sec", "ms_per_step": round(ms_e2e / a.steps, 3),
                 "h2d_bytes_per_step": int(x_host[0].numel() * 4 + y_host[0].numel() * 8), "d2h_bytes_per_step": int(d2h[0]),
