@@ -10,9 +10,12 @@ What is removed is exactly what cannot influence the output (so the compact forw
   * a head all of whose 64 input columns of `attn.proj.weight` are masked: its q, k, v rows, its attention and its proj columns;
   * a neuron whose column of `mlp.fc2.weight` is masked: the fc1 row (and bias entry) and the fc2 column.
 Dimensions pruned INSIDE a surviving head (the `r` variables) keep their zeroed proj columns: the fused attention kernel works on 64-wide
-heads; cutting them needs a ragged value width and is left with the training-side compaction (dX / dW on compact tensors and the
-clip-norm question: the reference clips over gradients of masked weights too, and those are not zero -- e.g. d fc2.weight[:, n] =
-gelu(fc1.bias[n]) * colsum(dY) for a pruned neuron n) for the next round.  `macs()` reports what the layout saves.
+heads.  `macs()` reports what the layout saves.
+
+Training on the compacted model: `EngineLayout` / `engine_layout_for(model)` build the `uvc_vit_layout` the whole-model engine takes
+(include/uvc_b200.h; csrc/compact.cu gathers live rows / columns while converting the weights and scatters the compact gradients back);
+`post_train.py --compact_train {1,2}` switches it on.  What the gradient of a masked weight is under compaction -- the reference's
+`clip_grad_norm_` counts it -- is spelled out in DESIGN.md section 5.7 and tested in tests/test_compact_train_gpu.py.
 """
 import torch
 
