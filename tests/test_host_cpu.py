@@ -100,3 +100,50 @@ def test_cli_flag_compatibility():
     assert a.budget == 0.5 and a.distillation_type == "soft" and a.seed == 730 and a.enable_patch_gating == 1
     b = pt.build_parser().parse_args("--name y --model_type deit_base_patch16_224 --train_batch_size 256 --local-rank 1".split())
     assert b.local_rank == 1 and b.model_type == "deit_base_patch16_224"
+
+
+def test_hard_skip_list_cache_rules():
+    """The hard-skip decision needs a host read of the gates; it is cached (per storage + version) only where the gates cannot move behind the
+    version counter's back: eval mode or frozen gates (Stage 2).  A model that trains its gates re-reads every call."""
+    import types
+    import torch
+    from uvc_b200.models.model_distilled import hard_skip_list
+    m = types.SimpleNamespace(block_skip_gating=torch.nn.Parameter(torch.tensor([[-1.0, 1.0], [1.0, -1.0], [0.5, 0.5]])), training=True)
+    assert hard_skip_list(m) == [False, True, True]                       # runs iff gate[1] > gate[0] (ties skip, models/model_distilled.py:498)
+    reads = []
+    orig = torch.Tensor.tolist
+    torch.Tensor.tolist = lambda self: (reads.append(1), orig(self))[1]
+    try:
+        hard_skip_list(m); hard_skip_list(m)
+        assert len(reads) == 2                                             # training + trainable gates: read every time
+        m.block_skip_gating.requires_grad = False                          # Stage 2 (post_train.py:342)
+        hard_skip_list(m); hard_skip_list(m); hard_skip_list(m)
+        assert len(reads) == 2                                             # the cache made by the last read is valid: no further reads
+        with torch.no_grad():
+            m.block_skip_gating[0] = torch.tensor([1.0, -1.0])             # in-place change moves the version counter
+        assert hard_skip_list(m) == [True, True, True] and len(reads) == 3
+        m.block_skip_gating.requires_grad = True; m.training = False       # eval mode (the teacher)
+        hard_skip_list(m); hard_skip_list(m)
+        assert len(reads) == 3
+    finally:
+        torch.Tensor.tolist = orig
+
+
+def test_engine_param_list_is_cached_and_revalidated():
+    import torch
+    from uvc_b200.models.model_distilled import _engine_param_list, deit_tiny_patch16_224
+    m = deit_tiny_patch16_224()
+    a = _engine_param_list(m)
+    assert _engine_param_list(m) is a and len(a) == 8 + 12 * 12
+    assert [n for n, _ in a[:8]] == ["patch_w", "patch_b", "cls_token", "pos_embed", "norm_w", "norm_b", "head_w", "head_b"]
+    m.head.weight = torch.nn.Parameter(torch.zeros_like(m.head.weight))    # surgery: the cached list must not survive it
+    b = _engine_param_list(m)
+    assert b is not a and b[6][1] is m.head.weight
+
+
+def test_distillation_loss_prefetch_is_a_noop_off_device():
+    import torch
+    from uvc_b200.utils.losses import DistillationLoss
+    crit = DistillationLoss(torch.nn.CrossEntropyLoss(), None, "none", 0.0, 1.0)
+    crit.prefetch_teacher(torch.zeros(2, 3))
+    assert crit._pref is None
